@@ -1,0 +1,157 @@
+/*
+ * tfrs_b200.h -- C ABI of libtfrs_b200.so: the B200 (sm_100a) kernels behind the TensorFlow
+ * Recommenders retrieval / ranking hot path.
+ *
+ * The reference (tensorflow/recommenders v0.7.7) has no native/FFI layer: its boundary with native
+ * code is "call public tf.* ops" from Python.  Each entry point below therefore replaces one TF op
+ * call site of the reference (cited per function, paths relative to tensorflow_recommenders/).
+ * The Python mirror of the reference API (recommenders_b200/) is the only intended caller and binds
+ * these symbols with ctypes (see INTEGRATION.md for the binding a maintainer would add).
+ *
+ * Conventions
+ *  - Every function returns 0 on success or a negative TFRS_ERR_* code; tfrs_last_error() returns a
+ *    thread-local message.  No C++ exception or abort crosses the boundary.
+ *  - All data pointers are DEVICE pointers owned by the caller (e.g. torch storage .data_ptr());
+ *    the library never frees or retains them past the call.  Pointer ARRAYS (tables / ids lists)
+ *    are HOST arrays of device pointers.
+ *  - No hidden allocation: scratch memory is caller-provided, its size comes from *_workspace_bytes().
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream).
+ *    No implicit synchronisation; calls are CUDA-graph capturable.
+ *  - Matrices are row-major fp32 unless stated otherwise.
+ */
+#ifndef TFRS_B200_H_
+#define TFRS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFRS_B200_VERSION 100 /* 0.1.0 */
+
+enum {
+  TFRS_OK = 0,
+  TFRS_ERR_INVALID_ARG = -1,
+  TFRS_ERR_UNSUPPORTED = -2,
+  TFRS_ERR_CUDA = -3,
+  TFRS_ERR_WORKSPACE_TOO_SMALL = -4
+};
+
+enum { TFRS_I32 = 0, TFRS_I64 = 1 };
+
+int tfrs_version(void);
+const char* tfrs_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t tfrs_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  embedding gather.  Replaces tf.keras.layers.Embedding -> tf.gather in the user towers
+ * (README.md:62-66,77-78; experimental/layers/embedding/partial_tpu_embedding.py:81-85,127).
+ *   out[i, out_col_off[t] .. +dims[t]) = tables[t][ids[t][i], :]     for t < n_tables, i < n
+ * Writes straight into a concatenated [n, out_ld] activation (the layout Cross consumes).
+ * Out-of-range ids produce zero rows.  dims[t] % 4 == 0 and 16-byte aligned rows take the
+ * vectorised path; anything else a scalar path.
+ * ------------------------------------------------------------------------------------------- */
+int tfrs_gather_f32(const float* const* tables, const int64_t* rows, const int32_t* dims, int n_tables,
+                    const void* const* ids, int ids_dtype, int64_t n, float* out, int64_t out_ld,
+                    const int32_t* out_col_off, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  brute-force top-K scan.  Replaces  scores = matmul(q, c^T); top_k(scores, k)
+ * (layers/factorized_top_k.py:603-605 BruteForce.call; :424-438,:440-472 Streaming.call).
+ * Scores are the canonical sequential fmaf chain over k = 0..d-1; order = (score desc, index asc).
+ * `state_*` (nullable, state_k entries per query) is Streaming's carried state; it takes part in
+ * the selection with its own indices.  New candidates get index = index_offset + row (shard /
+ * chunk offset).  Output: min(k, state_k + N) entries per query, written with row stride k.
+ * k <= 2048.
+ *
+ * tfrs_topk_scan_f32      exact fp32 CUDA-core path (any N, d; used for small corpora/chunks).
+ * tfrs_index_*            builds the tensor-core screening image of a corpus (bf16, UMMA
+ *                         SWIZZLE_128B K-major tiles + row-norm bound); done once at index() time
+ *                         (BruteForce.index, factorized_top_k.py:540-584).
+ * tfrs_topk_tc_f32        tcgen05 screening GEMM (bf16 in / fp32 accumulate in TMEM) with a fused
+ *                         threshold filter, then exact fp32 rescoring of the survivors -- same
+ *                         bit-exact result as tfrs_topk_scan_f32.  Needs N >= 4096 and k <= 512.
+ * ------------------------------------------------------------------------------------------- */
+size_t tfrs_topk_scan_workspace_bytes(int64_t Q, int64_t N, int d, int k);
+int tfrs_topk_scan_f32(const float* q, int64_t Q, const float* corpus, int64_t N, int d, int k,
+                       int64_t index_offset, const float* state_scores, const int64_t* state_idx,
+                       int state_k, float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes,
+                       void* stream);
+
+size_t tfrs_index_bytes(int64_t N, int d);
+int tfrs_index_build(const float* corpus, int64_t N, int d, void* index_buf, size_t index_bytes,
+                     void* stream);
+size_t tfrs_topk_tc_workspace_bytes(int64_t Q, int64_t N, int d, int k);
+int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, const void* index_buf, int64_t N,
+                     int d, int k, int64_t index_offset, float* out_scores, int64_t* out_idx, void* ws,
+                     size_t ws_bytes, void* stream);
+
+/* K2m  merge n_lists per-shard/per-chunk [Q, k_in] lists (list-major: [n_lists, Q, k_in]) into the
+ * best k_out = min(k_out, n_lists*k_in) per query (Streaming reduce :440-472; shard merge after the
+ * all-gather).  Order = (score desc, index asc). */
+int tfrs_topk_merge(const float* scores, const int64_t* idx, int n_lists, int64_t Q, int k_in, int k_out,
+                    float* out_scores, int64_t* out_idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Score helpers (exact fp32, canonical fmaf chain, one owner thread per output).
+ * tfrs_sgemm_f32: C[M,N] (+)= opA(A) . opB(B); opA(m,k) = transA ? A[k*lda+m] : A[m*lda+k],
+ *   opB(k,n) = transB ? B[n*ldb+k] : B[k*ldb+n].  transA=0, transB=1 is `_compute_score`
+ *   = matmul(q, c^T) (layers/factorized_top_k.py:320-333; tasks/retrieval.py:178-180); the other
+ *   modes serve its backward and the low-rank Cross (dcn.py:131-148,178-179).
+ * tfrs_rowwise_dot_f32: out[i] = sum_k a[i,k]*b[i,k]  (positive scores,
+ *   metrics/factorized_top_k.py:133-134).
+ * ------------------------------------------------------------------------------------------- */
+int tfrs_sgemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                   const float* B, int64_t ldb, float* C, int64_t ldc, int accumulate, void* stream);
+int tfrs_rowwise_dot_f32(const float* a, const float* b, int64_t rows, int d, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3  in-batch softmax loss of tfrs.tasks.Retrieval (tasks/retrieval.py:178-185,187-188,210):
+ *   s = (q . c^T) * inv_temperature ; loss = sum_i w_i * (logsumexp_j s_ij - s_ii)
+ * C >= B (extra negatives, positives are the first B rows).  `lse` [B] is saved for backward.
+ * Backward (tape.gradient at models/base.py:77): G = (softmax(s) - I) * w * grad_loss * inv_temperature,
+ *   dq = G . c   [B,d] ;  dc = G^T . q   [C,d].
+ * ------------------------------------------------------------------------------------------- */
+size_t tfrs_inbatch_softmax_workspace_bytes(int64_t B, int64_t C, int d);
+int tfrs_inbatch_softmax_fwd(const float* q, const float* c, int64_t B, int64_t C, int d,
+                             float inv_temperature, const float* sample_weight, float* loss, float* lse,
+                             void* ws, size_t ws_bytes, void* stream);
+int tfrs_inbatch_softmax_bwd(const float* q, const float* c, int64_t B, int64_t C, int d,
+                             float inv_temperature, const float* sample_weight, const float* lse,
+                             const float* grad_loss, float* dq, float* dc, void* ws, size_t ws_bytes,
+                             void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  sparse Adagrad on the rows touched by a batch (optimizer.apply_gradients with IndexedSlices,
+ * models/base.py:77-78; Adagrad chosen by the user, README.md:84).  Duplicate ids are summed in
+ * order of occurrence, then  acc += g*g ; var -= lr*g / sqrt(acc+eps)   (eps_inside_sqrt != 0)
+ *                       or   acc += g*g ; var -= lr*g / (sqrt(acc)+eps) (eps_inside_sqrt == 0).
+ * Deterministic (sort + segmented reduction, no float atomics).  n < 2^24.
+ * ------------------------------------------------------------------------------------------- */
+size_t tfrs_sparse_adagrad_workspace_bytes(int64_t n, int d);
+int tfrs_sparse_adagrad_f32(float* table, float* accum, int64_t rows, int d, const void* ids, int ids_dtype,
+                            int64_t n, const float* grad_rows, float lr, float eps, int eps_inside_sqrt,
+                            void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5  DCN-v2 cross layer (layers/feature_interaction/dcn.py:176-186, full-rank, no preactivation):
+ *   out = x0 * (x . W + bias + diag_scale * x) + x ,  W [D,D] in Keras [in,out] layout.
+ * x0, x, out have row stride ld (>= D).  `prod` (nullable) receives x.W + bias + diag_scale*x for
+ * the backward pass.  Backward:
+ *   dx0 = g*prod ; gp = g*x0 ; dx = gp . W^T + diag_scale*gp + g ; dW = x^T . gp ; dbias = colsum(gp).
+ * dx0/dx/dW/dbias are nullable (skipped when NULL).  ws holds gp: B*D floats.
+ * ------------------------------------------------------------------------------------------- */
+int tfrs_cross_fwd_f32(const float* x0, const float* x, const float* W, const float* bias, int64_t B, int D,
+                       int64_t ld, float diag_scale, float* out, float* prod, void* stream);
+size_t tfrs_cross_bwd_workspace_bytes(int64_t B, int D);
+int tfrs_cross_bwd_f32(const float* x0, const float* x, const float* W, const float* prod, const float* dout,
+                       int64_t B, int D, int64_t ld, float diag_scale, float* dx0, float* dx, float* dW,
+                       float* dbias, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFRS_B200_H_ */

@@ -1,0 +1,53 @@
+// common.cuh -- shared helpers for libtfrs_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/tfrs_b200.h"
+
+namespace tfrs {
+
+// thread-local error text behind tfrs_last_error()
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define TFRS_CHECK_ARG(cond, ...)                          \
+  do {                                                     \
+    if (!(cond)) {                                         \
+      ::tfrs::set_error(__VA_ARGS__);                      \
+      return TFRS_ERR_INVALID_ARG;                         \
+    }                                                      \
+  } while (0)
+
+#define TFRS_CUDA(expr)                                                                          \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess) {                                                                    \
+      ::tfrs::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__));   \
+      return TFRS_ERR_CUDA;                                                                      \
+    }                                                                                            \
+  } while (0)
+
+#define TFRS_LAUNCH_CHECK()                                                                      \
+  do {                                                                                           \
+    ::tfrs::count_launch();                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                                        \
+    if (e__ != cudaSuccess) {                                                                    \
+      ::tfrs::set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return TFRS_ERR_CUDA;                                                                      \
+    }                                                                                            \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// (score desc, index asc): the total order of tf.math.top_k that the whole path relies on.
+__host__ __device__ __forceinline__ bool better(float sa, long long ia, float sb, long long ib) {
+  return (sa > sb) || (sa == sb && ia < ib);
+}
+
+int sm_count();
+
+}  // namespace tfrs

@@ -1,0 +1,133 @@
+// cross.cu -- K5/K5b: DCN-v2 cross layer, full-rank (layers/feature_interaction/dcn.py:176-186).
+//   fwd: out = x0 * (x . W + bias + diag_scale * x) + x     W is [in,out] (Keras Dense, dcn.py:121-130)
+//        one exact SGEMM whose epilogue applies bias / diag / x0 / residual, so the [B,D] product
+//        never makes a separate HBM round trip (the reference runs MatMul, BiasAdd, Mul, Add).
+//   bwd: gp = g*x0 ; dx0 = g*prod ; dx = gp . W^T + diag*gp + g ; dW = x^T . gp (deterministic split-K) ;
+//        dbias = colsum(gp) (two-level fixed-order reduction).
+#include "sgemm.cuh"
+
+namespace tfrs {
+
+struct EpiCrossFwd {
+  const float* x0; const float* x; const float* bias; float diag; long long ld; float* out; float* prod;
+  __device__ __forceinline__ void operator()(int m, int n, float acc, int) const {
+    long long o = (long long)m * ld + n;
+    float xv = x[o];
+    float p = acc;
+    if (bias) p += bias[n];
+    if (diag != 0.f) p += diag * xv;
+    if (prod) prod[o] = p;
+    out[o] = x0[o] * p + xv;
+  }
+};
+
+struct EpiCrossDx {
+  const float* gp; long long ldgp; const float* g; long long ld; float diag; float* dx;
+  __device__ __forceinline__ void operator()(int m, int n, float acc, int) const {
+    float v = acc + g[(long long)m * ld + n];
+    if (diag != 0.f) v += diag * gp[(long long)m * ldgp + n];
+    dx[(long long)m * ld + n] = v;
+  }
+};
+
+__global__ void __launch_bounds__(256)
+cross_bwd_elem(const float* __restrict__ x0, const float* __restrict__ prod, const float* __restrict__ g,
+               long long B, int D, long long ld, float* __restrict__ gp, float* __restrict__ dx0) {
+  const long long total = B * D;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    long long m = e / D; int n = (int)(e - m * D);
+    long long o = m * ld + n;
+    float gv = g[o];
+    gp[e] = gv * x0[o];
+    if (dx0) dx0[o] = gv * prod[o];
+  }
+}
+
+// partial[z][n] = sum over rows of split z (fixed order)
+__global__ void __launch_bounds__(256)
+cross_colsum_partial(const float* __restrict__ gp, long long B, int D, long long rows_per_split, float* __restrict__ partial) {
+  int n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= D) return;
+  long long r0 = (long long)blockIdx.y * rows_per_split;
+  long long r1 = r0 + rows_per_split < B ? r0 + rows_per_split : B;
+  float a = 0.f;
+  for (long long r = r0; r < r1; ++r) a += gp[r * D + n];
+  partial[(long long)blockIdx.y * D + n] = a;
+}
+
+// out[e] = sum_z partial[z][e]  (z ascending)
+__global__ void __launch_bounds__(256)
+cross_reduce_splits(const float* __restrict__ partial, long long elems, int splits, float* __restrict__ out) {
+  long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (e >= elems) return;
+  float a = partial[e];
+  for (int z = 1; z < splits; ++z) a += partial[(long long)z * elems + e];
+  out[e] = a;
+}
+
+static int cross_splits(long long B) { long long z = ceil_div(B, 4096); return (int)(z < 1 ? 1 : (z > 16 ? 16 : z)); }
+constexpr int CROSS_COL_SPLITS = 64;
+
+}  // namespace tfrs
+using namespace tfrs;
+
+extern "C" int tfrs_cross_fwd_f32(const float* x0, const float* x, const float* W, const float* bias, int64_t B,
+                                  int D, int64_t ld, float diag_scale, float* out, float* prod, void* stream) {
+  TFRS_CHECK_ARG(x0 && x && W && out, "cross_fwd: NULL pointer");
+  TFRS_CHECK_ARG(B >= 0 && D > 0 && ld >= D, "cross_fwd: bad shape B=%lld D=%d ld=%lld", (long long)B, D, (long long)ld);
+  TFRS_CHECK_ARG(diag_scale >= 0.f, "`diag_scale` should be non-negative. Got `diag_scale` = %g", diag_scale);
+  TFRS_CHECK_ARG(B < (1ll << 31), "cross_fwd: B too large");
+  if (B == 0) return TFRS_OK;
+  EpiCrossFwd epi{x0, x, bias, diag_scale, ld, out, prod};
+  return launch_sgemm<false, false>(x, ld, W, D, (int)B, D, D, 1, epi, (cudaStream_t)stream);
+}
+
+extern "C" size_t tfrs_cross_bwd_workspace_bytes(int64_t B, int D) {
+  if (B <= 0 || D <= 0) return 256;
+  return align_up((size_t)B * D * 4, 256) + align_up((size_t)cross_splits(B) * D * D * 4, 256) +
+         align_up((size_t)CROSS_COL_SPLITS * D * 4, 256);
+}
+
+extern "C" int tfrs_cross_bwd_f32(const float* x0, const float* x, const float* W, const float* prod,
+                                  const float* dout, int64_t B, int D, int64_t ld, float diag_scale, float* dx0,
+                                  float* dx, float* dW, float* dbias, void* ws, size_t ws_bytes, void* stream) {
+  TFRS_CHECK_ARG(x0 && x && W && dout, "cross_bwd: NULL pointer");
+  TFRS_CHECK_ARG(B > 0 && D > 0 && ld >= D && B < (1ll << 31), "cross_bwd: bad shape");
+  TFRS_CHECK_ARG(!dx0 || prod, "cross_bwd: dx0 needs the saved `prod`");
+  if (!ws || ws_bytes < tfrs_cross_bwd_workspace_bytes(B, D)) { set_error("cross_bwd: workspace too small"); return TFRS_ERR_WORKSPACE_TOO_SMALL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* w = (unsigned char*)ws;
+  float* gp = (float*)w; w += align_up((size_t)B * D * 4, 256);
+  const int Z = cross_splits(B);
+  float* part = (float*)w; w += align_up((size_t)Z * D * D * 4, 256);
+  float* colpart = (float*)w;
+
+  long long total = (long long)B * D;
+  unsigned blocks = (unsigned)(ceil_div(total, 256) < 148 * 16 ? ceil_div(total, 256) : 148 * 16);
+  cross_bwd_elem<<<blocks, 256, 0, st>>>(x0, prod, dout, B, D, ld, gp, dx0);
+  TFRS_LAUNCH_CHECK();
+  int rc;
+  if (dx) {
+    rc = launch_sgemm<false, true>(gp, D, W, D, (int)B, D, D, 1, EpiCrossDx{gp, D, dout, ld, diag_scale, dx}, st);
+    if (rc) return rc;
+  }
+  if (dW) {
+    rc = launch_sgemm<true, false>(x, ld, gp, D, D, D, (int)B, Z, EpiStoreSplit{part, D, (long long)D * D}, st);
+    if (rc) return rc;
+    // launch_sgemm may use fewer splits than Z when B is small; recompute what it used
+    int kps = (int)(ceil_div(ceil_div(B, Z), SG_BK) * SG_BK);
+    int used = Z > 1 ? (int)ceil_div(B, kps) : 1;
+    cross_reduce_splits<<<(unsigned)ceil_div((long long)D * D, 256), 256, 0, st>>>(part, (long long)D * D, used, dW);
+    TFRS_LAUNCH_CHECK();
+  }
+  if (dbias) {
+    long long rps = ceil_div(B, CROSS_COL_SPLITS);
+    int used = (int)ceil_div(B, rps);
+    dim3 grid((unsigned)ceil_div(D, 256), (unsigned)used);
+    cross_colsum_partial<<<grid, 256, 0, st>>>(gp, B, D, rps, colpart);
+    TFRS_LAUNCH_CHECK();
+    cross_reduce_splits<<<(unsigned)ceil_div(D, 256), 256, 0, st>>>(colpart, D, used, dbias);
+    TFRS_LAUNCH_CHECK();
+  }
+  return TFRS_OK;
+}

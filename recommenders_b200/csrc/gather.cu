@@ -1,0 +1,107 @@
+// gather.cu -- K1: multi-table embedding row gather into a concatenated activation.
+// Replaces tf.keras.layers.Embedding -> tf.gather (README.md:62-66,77-78).  HBM-bound:
+// algorithmic bytes = n * sum(dims) * 4 read + the same written (+ ids).  One 16-byte lane per
+// thread, consecutive threads cover one row (coalesced 128..256 B row reads and writes), the
+// table is selected by blockIdx.y so the inner index math is a single divide.
+#include "common.cuh"
+
+namespace tfrs {
+
+constexpr int GT_MAX_TABLES = 32;
+constexpr int GT_THREADS = 256;
+constexpr int GT_ROWS_PER_THREAD = 4;  // independent loads in flight per thread
+
+struct GatherParams {
+  const float* table[GT_MAX_TABLES];
+  const void* ids[GT_MAX_TABLES];
+  long long rows[GT_MAX_TABLES];
+  int dim[GT_MAX_TABLES];
+  int col_off[GT_MAX_TABLES];
+};
+
+template <typename IdT, bool VEC>
+__global__ void __launch_bounds__(GT_THREADS)
+gather_kernel(GatherParams p, long long n, float* __restrict__ out, long long out_ld) {
+  const int t = blockIdx.y;
+  const float* __restrict__ table = p.table[t];
+  const IdT* __restrict__ ids = reinterpret_cast<const IdT*>(p.ids[t]);
+  const long long rows = p.rows[t];
+  const int dim = p.dim[t];
+  const int lanes = VEC ? dim / 4 : dim;  // work items per row
+  const long long total = n * lanes;
+  const long long stride = (long long)gridDim.x * GT_THREADS;
+  long long w = (long long)blockIdx.x * GT_THREADS + threadIdx.x;
+  // each thread handles GT_ROWS_PER_THREAD items `stride` apart: loads first, then stores
+  for (; w < total; w += stride * GT_ROWS_PER_THREAD) {
+    float4 v4[GT_ROWS_PER_THREAD]; float v1[GT_ROWS_PER_THREAD];
+    long long dst[GT_ROWS_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < GT_ROWS_PER_THREAD; ++u) {
+      long long e = w + u * stride;
+      dst[u] = -1;
+      if (e < total) {
+        long long i = e / lanes; int l = (int)(e - i * lanes);
+        long long r = (long long)ids[i];
+        bool ok = (r >= 0 && r < rows);
+        if (VEC) {
+          v4[u] = ok ? __ldg(reinterpret_cast<const float4*>(table + r * dim) + l) : make_float4(0.f, 0.f, 0.f, 0.f);
+          dst[u] = i * out_ld + p.col_off[t] + l * 4;
+        } else {
+          v1[u] = ok ? __ldg(table + r * dim + l) : 0.f;
+          dst[u] = i * out_ld + p.col_off[t] + l;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < GT_ROWS_PER_THREAD; ++u) {
+      if (dst[u] >= 0) {
+        if (VEC) *reinterpret_cast<float4*>(out + dst[u]) = v4[u];
+        else out[dst[u]] = v1[u];
+      }
+    }
+  }
+}
+
+}  // namespace tfrs
+using namespace tfrs;
+
+extern "C" int tfrs_gather_f32(const float* const* tables, const int64_t* rows, const int32_t* dims, int n_tables,
+                               const void* const* ids, int ids_dtype, int64_t n, float* out, int64_t out_ld,
+                               const int32_t* out_col_off, void* stream) {
+  TFRS_CHECK_ARG(n_tables > 0 && tables && rows && dims && ids && out && out_col_off, "gather: NULL argument");
+  TFRS_CHECK_ARG(ids_dtype == TFRS_I32 || ids_dtype == TFRS_I64, "gather: ids_dtype must be I32 or I64");
+  TFRS_CHECK_ARG(n >= 0 && out_ld > 0, "gather: bad n / out_ld");
+  if (n == 0) return TFRS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int t0 = 0; t0 < n_tables; t0 += GT_MAX_TABLES) {
+    int nt = n_tables - t0 < GT_MAX_TABLES ? n_tables - t0 : GT_MAX_TABLES;
+    GatherParams p;
+    bool vec = (out_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    int max_dim = 0;
+    for (int t = 0; t < nt; ++t) {
+      TFRS_CHECK_ARG(tables[t0 + t] && ids[t0 + t] && dims[t0 + t] > 0 && rows[t0 + t] >= 0, "gather: bad table %d", t0 + t);
+      TFRS_CHECK_ARG(out_col_off[t0 + t] >= 0 && out_col_off[t0 + t] + dims[t0 + t] <= out_ld,
+                     "gather: table %d columns [%d,%d) exceed out_ld=%lld", t0 + t, out_col_off[t0 + t],
+                     out_col_off[t0 + t] + dims[t0 + t], (long long)out_ld);
+      p.table[t] = tables[t0 + t]; p.ids[t] = ids[t0 + t]; p.rows[t] = rows[t0 + t];
+      p.dim[t] = dims[t0 + t]; p.col_off[t] = out_col_off[t0 + t];
+      vec = vec && (dims[t0 + t] % 4 == 0) && (out_col_off[t0 + t] % 4 == 0) &&
+            ((reinterpret_cast<uintptr_t>(tables[t0 + t]) & 15) == 0);
+      if (dims[t0 + t] > max_dim) max_dim = dims[t0 + t];
+    }
+    long long items = n * (vec ? max_dim / 4 : max_dim);
+    long long blocks = ceil_div(items, (long long)GT_THREADS * GT_ROWS_PER_THREAD);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 1 << 20) blocks = 1 << 20;
+    dim3 grid((unsigned)blocks, (unsigned)nt);
+    if (ids_dtype == TFRS_I32) {
+      if (vec) gather_kernel<int32_t, true><<<grid, GT_THREADS, 0, st>>>(p, n, out, out_ld);
+      else gather_kernel<int32_t, false><<<grid, GT_THREADS, 0, st>>>(p, n, out, out_ld);
+    } else {
+      if (vec) gather_kernel<int64_t, true><<<grid, GT_THREADS, 0, st>>>(p, n, out, out_ld);
+      else gather_kernel<int64_t, false><<<grid, GT_THREADS, 0, st>>>(p, n, out, out_ld);
+    }
+    TFRS_LAUNCH_CHECK();
+  }
+  return TFRS_OK;
+}

@@ -1,0 +1,304 @@
+"""Functional wrappers over the C ABI (one Python function per entry point of include/tfrs_b200.h).
+
+Everything here takes/returns CUDA torch tensors; torch only provides memory, streams and the
+autograd tape.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _ffi
+from ._ffi import c_f, c_i, c_l, c_sz, check, f32c, lib, ptr, require_cuda, stream, workspace
+
+# Corpora at least this large go through the tensor-core screening path when an index image exists.
+TC_MIN_N = 16384
+TC_MAX_K = 512
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 gather
+# ------------------------------------------------------------------------------------------------
+def gather(tables: Sequence[torch.Tensor], ids: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None,
+           col_offsets: Optional[Sequence[int]] = None) -> torch.Tensor:
+  """out[i, off_t:off_t+dim_t] = tables[t][ids[t][i]]  -- concatenated multi-table embedding lookup."""
+  nt = len(tables)
+  if nt == 0 or len(ids) != nt:
+    raise ValueError("gather: need as many id tensors as tables")
+  n = ids[0].numel()
+  dims = [int(t.shape[1]) for t in tables]
+  if col_offsets is None:
+    col_offsets, o = [], 0
+    for d in dims:
+      col_offsets.append(o); o += d
+    width = o
+  else:
+    width = max(o + d for o, d in zip(col_offsets, dims))
+  dev = tables[0].device
+  tabs = [f32c(t, "table") for t in tables]
+  code = _ffi.ids_dtype_code(ids[0])
+  idl = []
+  for x in ids:
+    require_cuda(x, "ids")
+    if _ffi.ids_dtype_code(x) != code or x.numel() != n:
+      raise ValueError("gather: all id tensors must share dtype and length")
+    idl.append(x.contiguous().view(-1))
+  if out is None:
+    out = torch.empty((n, width), dtype=torch.float32, device=dev)
+  else:
+    require_cuda(out, "out")
+    if out.dtype != torch.float32 or out.stride(-1) != 1 or out.shape[0] != n:
+      raise ValueError("gather: out must be float32 [n, >=width] with unit inner stride")
+  out_ld = out.stride(0) if out.dim() == 2 else width
+  tp = (ctypes.c_void_p * nt)(*[t.data_ptr() for t in tabs])
+  ip = (ctypes.c_void_p * nt)(*[x.data_ptr() for x in idl])
+  rows = (ctypes.c_int64 * nt)(*[int(t.shape[0]) for t in tabs])
+  dm = (ctypes.c_int32 * nt)(*dims)
+  co = (ctypes.c_int32 * nt)(*[int(c) for c in col_offsets])
+  check(lib().tfrs_gather_f32(tp, rows, dm, nt, ip, code, n, ptr(out), out_ld, co, stream()), "gather")
+  return out
+
+
+# ------------------------------------------------------------------------------------------------
+# K2 top-k
+# ------------------------------------------------------------------------------------------------
+def topk_scan(q: torch.Tensor, corpus: torch.Tensor, k: int, index_offset: int = 0,
+              state: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+  """Exact brute-force top-k (CUDA-core path) with optional carried state. Returns ([Q,k_out] f32, [Q,k_out] i64)."""
+  q = f32c(q, "queries"); corpus = f32c(corpus, "candidates")
+  if q.dim() != 2 or corpus.dim() != 2 or q.shape[1] != corpus.shape[1]:
+    raise ValueError(f"topk_scan: shape mismatch {tuple(q.shape)} vs {tuple(corpus.shape)}")
+  Q, d = q.shape; N = corpus.shape[0]
+  st_s = st_i = None; st_k = 0
+  if state is not None and state[0].shape[1] > 0:
+    st_s = f32c(state[0], "state scores"); st_i = require_cuda(state[1], "state idx").to(torch.int64).contiguous()
+    st_k = st_s.shape[1]
+  k_out = min(k, st_k + N)
+  out_s = torch.empty((Q, k), dtype=torch.float32, device=q.device)
+  out_i = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+  if Q == 0 or k_out == 0:
+    return out_s[:, :0], out_i[:, :0]
+  wsb = lib().tfrs_topk_scan_workspace_bytes(Q, N, d, k)
+  ws = workspace(wsb, q.device, "scan")
+  check(lib().tfrs_topk_scan_f32(ptr(q), Q, ptr(corpus), N, d, k, index_offset, ptr(st_s), ptr(st_i), st_k,
+                                 ptr(out_s), ptr(out_i), ptr(ws), ws.numel(), stream()), "topk_scan")
+  return out_s[:, :k_out], out_i[:, :k_out]
+
+
+def index_build(corpus: torch.Tensor) -> torch.Tensor:
+  """Builds the tensor-core screening image (bf16 UMMA tiles + norm bound) of a corpus."""
+  corpus = f32c(corpus, "candidates")
+  N, d = corpus.shape
+  nb = lib().tfrs_index_bytes(N, d)
+  if nb == 0:
+    raise NotImplementedError("tensor-core index not available for this shape")
+  buf = torch.empty(nb, dtype=torch.uint8, device=corpus.device)
+  check(lib().tfrs_index_build(ptr(corpus), N, d, ptr(buf), nb, stream()), "index_build")
+  return buf
+
+
+def topk_tc(q: torch.Tensor, corpus: torch.Tensor, index_buf: torch.Tensor, k: int, index_offset: int = 0
+            ) -> Tuple[torch.Tensor, torch.Tensor]:
+  """tcgen05 screening + exact rescoring; bit-identical to topk_scan."""
+  q = f32c(q, "queries"); corpus = f32c(corpus, "candidates")
+  Q, d = q.shape; N = corpus.shape[0]
+  out_s = torch.empty((Q, k), dtype=torch.float32, device=q.device)
+  out_i = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+  if Q == 0:
+    return out_s, out_i
+  wsb = lib().tfrs_topk_tc_workspace_bytes(Q, N, d, k)
+  ws = workspace(wsb, q.device, "tc")
+  check(lib().tfrs_topk_tc_f32(ptr(q), Q, ptr(corpus), ptr(index_buf), N, d, k, index_offset, ptr(out_s),
+                               ptr(out_i), ptr(ws), ws.numel(), stream()), "topk_tc")
+  return out_s, out_i
+
+
+def topk_merge(scores: torch.Tensor, idx: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+  """Merge [L,Q,k_in] lists into the best min(k, L*k_in) per query."""
+  scores = f32c(scores, "scores"); idx = require_cuda(idx, "idx").to(torch.int64).contiguous()
+  L, Q, k_in = scores.shape
+  k_out = min(k, L * k_in)
+  out_s = torch.empty((Q, k_out), dtype=torch.float32, device=scores.device)
+  out_i = torch.empty((Q, k_out), dtype=torch.int64, device=scores.device)
+  check(lib().tfrs_topk_merge(ptr(scores), ptr(idx), L, Q, k_in, k_out, ptr(out_s), ptr(out_i), stream()), "topk_merge")
+  return out_s, out_i
+
+
+# ------------------------------------------------------------------------------------------------
+# exact matmul / scores (autograd-aware)
+# ------------------------------------------------------------------------------------------------
+def sgemm(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: bool = False,
+          out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+  a = f32c(a, "a"); b = f32c(b, "b")
+  M, K = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
+  Kb, N = (b.shape[1], b.shape[0]) if trans_b else (b.shape[0], b.shape[1])
+  if K != Kb:
+    raise ValueError(f"sgemm: inner dimensions differ ({K} vs {Kb})")
+  if out is None:
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+  check(lib().tfrs_sgemm_f32(int(trans_a), int(trans_b), M, N, K, ptr(a), a.stride(0), ptr(b), b.stride(0),
+                             ptr(out), out.stride(0), int(accumulate), stream()), "sgemm")
+  return out
+
+
+class _Scores(torch.autograd.Function):
+  """`_compute_score` = matmul(q, c^T) (layers/factorized_top_k.py:320-333) with exact backward."""
+
+  @staticmethod
+  def forward(ctx, q, c):
+    q = f32c(q, "queries"); c = f32c(c, "candidates")
+    ctx.save_for_backward(q, c)
+    return sgemm(q, c, False, True)
+
+  @staticmethod
+  def backward(ctx, g):
+    q, c = ctx.saved_tensors
+    g = f32c(g, "grad")
+    dq = sgemm(g, c, False, False) if ctx.needs_input_grad[0] else None
+    dc = sgemm(g, q, True, False) if ctx.needs_input_grad[1] else None
+    return dq, dc
+
+
+def scores(q: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+  return _Scores.apply(q, c)
+
+
+class _Matmul(torch.autograd.Function):
+  """x @ w with our exact SGEMM (used by the low-rank Cross path)."""
+
+  @staticmethod
+  def forward(ctx, x, w):
+    x = f32c(x, "x"); w = f32c(w, "w")
+    ctx.save_for_backward(x, w)
+    return sgemm(x, w, False, False)
+
+  @staticmethod
+  def backward(ctx, g):
+    x, w = ctx.saved_tensors
+    g = f32c(g, "grad")
+    dx = sgemm(g, w, False, True) if ctx.needs_input_grad[0] else None
+    dw = sgemm(x, g, True, False) if ctx.needs_input_grad[1] else None
+    return dx, dw
+
+
+def matmul(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+  return _Matmul.apply(x, w)
+
+
+def rowwise_dot(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+  a = f32c(a, "a"); b = f32c(b, "b")
+  out = torch.empty((a.shape[0],), dtype=torch.float32, device=a.device)
+  check(lib().tfrs_rowwise_dot_f32(ptr(a), ptr(b), a.shape[0], a.shape[1], ptr(out), stream()), "rowwise_dot")
+  return out
+
+
+# ------------------------------------------------------------------------------------------------
+# K3 in-batch softmax loss
+# ------------------------------------------------------------------------------------------------
+class _InBatchSoftmax(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, q, c, sample_weight, inv_temperature):
+    q = f32c(q, "query_embeddings"); c = f32c(c, "candidate_embeddings")
+    B, d = q.shape; C = c.shape[0]
+    w = None if sample_weight is None else f32c(sample_weight, "sample_weight").view(-1)
+    loss = torch.empty((1,), dtype=torch.float32, device=q.device)
+    lse = torch.empty((B,), dtype=torch.float32, device=q.device)
+    wsb = lib().tfrs_inbatch_softmax_workspace_bytes(B, C, d)
+    ws = workspace(wsb, q.device, "softmax")
+    check(lib().tfrs_inbatch_softmax_fwd(ptr(q), ptr(c), B, C, d, c_f(inv_temperature), ptr(w), ptr(loss), ptr(lse),
+                                         ptr(ws), ws.numel(), stream()), "inbatch_softmax_fwd")
+    ctx.save_for_backward(q, c, lse, w if w is not None else torch.empty(0, device=q.device))
+    ctx.has_w = w is not None
+    ctx.inv_t = inv_temperature
+    return loss.view(())
+
+  @staticmethod
+  def backward(ctx, g):
+    q, c, lse, w = ctx.saved_tensors
+    B, d = q.shape; C = c.shape[0]
+    g = f32c(g, "grad").view(1)
+    dq = torch.empty_like(q); dc = torch.empty_like(c)
+    wsb = lib().tfrs_inbatch_softmax_workspace_bytes(B, C, d)
+    ws = workspace(wsb, q.device, "softmax")
+    check(lib().tfrs_inbatch_softmax_bwd(ptr(q), ptr(c), B, C, d, c_f(ctx.inv_t), ptr(w) if ctx.has_w else None,
+                                         ptr(lse), ptr(g), ptr(dq), ptr(dc), ptr(ws), ws.numel(), stream()),
+          "inbatch_softmax_bwd")
+    return dq, dc, None, None
+
+
+def inbatch_softmax_loss(q: torch.Tensor, c: torch.Tensor, sample_weight: Optional[torch.Tensor] = None,
+                         temperature: Optional[float] = None) -> torch.Tensor:
+  """sum_i w_i * (logsumexp_j(q_i.c_j / T) - q_i.c_i / T)  -- tasks/retrieval.py:178-210 default path."""
+  inv_t = 1.0 if temperature is None else 1.0 / float(temperature)
+  return _InBatchSoftmax.apply(q, c, sample_weight, inv_t)
+
+
+# ------------------------------------------------------------------------------------------------
+# K4 sparse Adagrad
+# ------------------------------------------------------------------------------------------------
+def sparse_adagrad_(table: torch.Tensor, accum: torch.Tensor, ids: torch.Tensor, grad_rows: torch.Tensor,
+                    lr: float, eps: float = 1e-7, eps_inside_sqrt: bool = True) -> None:
+  require_cuda(table, "table"); require_cuda(accum, "accum")
+  if table.dtype != torch.float32 or not table.is_contiguous() or accum.dtype != torch.float32 or not accum.is_contiguous():
+    raise ValueError("sparse_adagrad_: table/accum must be contiguous float32")
+  ids = require_cuda(ids, "ids").contiguous().view(-1)
+  g = f32c(grad_rows, "grad_rows")
+  n = ids.numel(); d = table.shape[1]
+  if g.shape != (n, d):
+    raise ValueError(f"sparse_adagrad_: grad_rows must be [{n},{d}], got {tuple(g.shape)}")
+  wsb = lib().tfrs_sparse_adagrad_workspace_bytes(n, d)
+  ws = workspace(wsb, table.device, "adagrad")
+  check(lib().tfrs_sparse_adagrad_f32(ptr(table), ptr(accum), table.shape[0], d, ptr(ids), _ffi.ids_dtype_code(ids), n,
+                                      ptr(g), c_f(lr), c_f(eps), int(eps_inside_sqrt), ptr(ws), ws.numel(), stream()),
+        "sparse_adagrad")
+
+
+# ------------------------------------------------------------------------------------------------
+# K5 cross
+# ------------------------------------------------------------------------------------------------
+class _Cross(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x0, x, W, bias, diag_scale):
+    x0 = f32c(x0, "x0"); x = f32c(x, "x"); W = f32c(W, "kernel")
+    b = None if bias is None else f32c(bias, "bias")
+    B, D = x0.shape
+    out = torch.empty_like(x0)
+    need_grad = any(ctx.needs_input_grad[:4])
+    prod = torch.empty_like(x0) if need_grad else None
+    check(lib().tfrs_cross_fwd_f32(ptr(x0), ptr(x), ptr(W), ptr(b), B, D, D, c_f(diag_scale), ptr(out), ptr(prod),
+                                   stream()), "cross_fwd")
+    if need_grad:
+      ctx.save_for_backward(x0, x, W, prod)
+    ctx.diag = diag_scale
+    ctx.has_bias = b is not None
+    return out
+
+  @staticmethod
+  def backward(ctx, g):
+    x0, x, W, prod = ctx.saved_tensors
+    g = f32c(g, "grad")
+    B, D = x0.shape
+    n0, n1, n2, n3 = ctx.needs_input_grad[:4]
+    dx0 = torch.empty_like(x0) if n0 else None
+    dx = torch.empty_like(x) if n1 else None
+    dW = torch.empty_like(W) if n2 else None
+    db = torch.empty((D,), dtype=torch.float32, device=x0.device) if (n3 and ctx.has_bias) else None
+    wsb = lib().tfrs_cross_bwd_workspace_bytes(B, D)
+    ws = workspace(wsb, x0.device, "cross")
+    check(lib().tfrs_cross_bwd_f32(ptr(x0), ptr(x), ptr(W), ptr(prod), ptr(g), B, D, D, c_f(ctx.diag), ptr(dx0), ptr(dx),
+                                   ptr(dW), ptr(db), ptr(ws), ws.numel(), stream()), "cross_bwd")
+    return dx0, dx, dW, db, None
+
+
+def cross(x0: torch.Tensor, x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], diag_scale: float = 0.0
+          ) -> torch.Tensor:
+  """x0 * (x @ W + bias + diag_scale * x) + x   (layers/feature_interaction/dcn.py:176-186)."""
+  return _Cross.apply(x0, x, W, bias, float(diag_scale))
+
+
+def launch_count() -> int:
+  return int(lib().tfrs_launch_count())
