@@ -89,6 +89,13 @@ int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, const void*
                      int d, int k, int64_t index_offset, float* out_scores, int64_t* out_idx, void* ws,
                      size_t ws_bytes, void* stream);
 
+/* Optional per-stage device timing of tfrs_topk_tc_f32 (CUDA events on the launch stream; used by
+ * bench.py for the roofline figure).  tfrs_profile_read synchronises the device and returns the summed
+ * times in ms of stage 0 = query image, 1 = sampled pass + threshold, 2 = full filter pass (the
+ * dominant kernel), 3 = exact re-scoring (+ fallback), over `calls` recorded calls. */
+int tfrs_profile_enable(int on);
+int tfrs_profile_read(float* stage_ms, int* calls);
+
 /* K2m  merge n_lists per-shard/per-chunk [Q, k_in] lists (list-major: [n_lists, Q, k_in]) into the
  * best k_out = min(k_out, n_lists*k_in) per query (Streaming reduce :440-472; shard merge after the
  * all-gather).  Order = (score desc, index asc). */

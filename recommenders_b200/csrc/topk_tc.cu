@@ -1,7 +1,697 @@
-// placeholder until the tcgen05 path lands
-#include "common.cuh"
+// topk_tc.cu -- K2: brute-force top-K on the 5th-gen tensor cores (tcgen05 + TMEM + bulk-TMA), sm_100a.
+//
+// Replaces  scores = matmul(q, c^T); top_k(scores, k)  (layers/factorized_top_k.py:603-605) for large
+// corpora.  The [Q,N] score matrix never exists in HBM:
+//
+//   index time   tfrs_index_build : corpus fp32 -> bf16 image, pre-tiled as 128-row UMMA SWIZZLE_128B
+//                K-major tiles (one contiguous 16 KB block per 64-wide K slab), + max row norm.
+//   query time   (0) tc_qprep    : queries -> the same bf16 tile image; per-query error margin
+//                (1) tc_scan<SAMPLE> : screening GEMM over every 4th corpus tile; epilogue keeps only the
+//                    per-(query, 64-column bin) max  -> K-th largest bin max = a valid lower bound L_q of
+//                    the K-th best screening score (K distinct bins hold K distinct candidates >= it)
+//                (2) tc_scan<FILTER> : screening GEMM over the whole corpus; epilogue compares the fp32
+//                    accumulators (read from TMEM) with T_q = L_q - margin_q and appends the rare
+//                    survivors (score, index) to a per-query list -- nothing else leaves the SM
+//                (3) tc_finalize : per query: tau = K-th best screening score; survivors within the error
+//                    band of tau are re-scored EXACTLY (sequential fp32 fmaf chain on the fp32 corpus),
+//                    sorted by (score desc, index asc) -> bit-identical to the exact CUDA-core path.
+//                (4) overflow fallback (list capacity exceeded; adversarial inputs only): exact scan.
+//
+// Why the result is exact: |screen(q,c) - exact(q,c)| <= eps_q = E_REL*|q|*max|c| (bf16 rounding of both
+// operands: (2u+u^2) sum|q_k c_k| with u = 2^-8, plus accumulation slack; Cauchy-Schwarz).  Any member
+// of the exact top-K has screening score >= tau - 2*eps_q >= L_q - 2*eps_q, so it is in the list and in
+// the re-scored band.
+//
+// Kernel shape (per CTA, 1 CTA / SM, 384 threads): 256 queries (two 128-row A blocks, resident in smem)
+// x a contiguous range of 128-row corpus tiles streamed through a 4-6 stage bulk-TMA ring; warp 0 = TMA
+// producer, warp 1 = MMA issuer (one thread, tcgen05.mma M=128 N=128 K=16, bf16 -> fp32 in TMEM),
+// warp 2 = TMEM allocator, warps 4-11 = epilogue (one query row per thread, tcgen05.ld 32x32b.x32).
+// TMEM holds 2 A-blocks x 2 buffers x 128 columns = all 512 columns, so tile t+1's MMAs overlap tile
+// t's epilogue.  Each B tile feeds two MMAs (both A blocks): 16 KB of L2->smem traffic per 512
+// tensor-core cycles keeps the chip under the ~6.3 KB/clk L2 fabric limit.
+#include <cuda_bf16.h>
+#include "rowselect.cuh"
+
+namespace tfrs {
+namespace tc {
+
+constexpr int TILE_N = 128;          // corpus rows per B tile
+constexpr int TILE_M = 128;          // query rows per A block
+constexpr int QBLK = 256;            // queries per CTA (2 A blocks)
+constexpr int KSLAB = 64;            // bf16 elements per 128-byte swizzle row
+constexpr int SLAB_BYTES = TILE_N * 128;  // 16 KB: 128 rows x 128 B
+constexpr int HEADER_BYTES = 1024;
+constexpr int THREADS = 384;
+constexpr int EPI_WARP0 = 4;
+constexpr int BIN_COLS = 64;         // columns per threshold bin (2 bins per tile row)
+constexpr int CAND_CAP = 2048;       // survivors kept per query
+constexpr int MAX_SAMPLE_STRIDE = 4;
+constexpr float E_REL = 0.0083f;     // see header comment
+constexpr float E_ACC = 0.0010f;     // run-to-run accumulation slack between the two passes
+
+struct IndexHeader {
+  unsigned int max_norm2_bits;  // max_i |c_i|^2 (float bits; non-negative so uint order == float order)
+  int d, d_pad, kb;
+  long long n, n_tiles;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, M=128, N=128, K=16
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// tcgen05.wait::ld, with the 32 destination registers threaded through as in/out operands so the
+// compiler cannot schedule a use of the loaded values above the wait.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+}
+
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both, N=128, M=128
+constexpr uint32_t IDESC_BF16_M128_N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// ------------------------------------------------------------------------------------------------
+// image builders: fp32 [rows, d] -> bf16 128-row tiles, each K slab of 64 as one swizzled 16 KB block
+//   byte offset of element (r, k) inside a tile = (k/64)*16384 + r*128 + (((k%64)/8) ^ (r%8))*16 + (k%8)*2
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tile_image_kernel(const float* __restrict__ src, long long rows, int d, int kb, long long n_tiles,
+                  unsigned char* __restrict__ img) {
+  const long long total = n_tiles * TILE_N * (long long)kb * 8;  // 16-byte chunks
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    int chunk = (int)(e % (kb * 8));
+    long long row = e / (kb * 8);
+    int slab = chunk / 8, cj = chunk % 8;
+    int r = (int)(row % TILE_N);
+    long long tile = row / TILE_N;
+    int k0 = slab * KSLAB + cj * 8;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float f = (row < rows && k0 + j < d) ? src[row * d + k0 + j] : 0.f;
+      v[j] = __float2bfloat16_rn(f);
+    }
+    unsigned char* dst = img + tile * ((long long)kb * SLAB_BYTES) + (long long)slab * SLAB_BYTES + r * 128 + ((cj ^ (r & 7)) * 16);
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+max_norm_kernel(const float* __restrict__ src, long long rows, int d, unsigned int* __restrict__ max_bits) {
+  long long row = (long long)blockIdx.x * 256 + threadIdx.x;
+  float n2 = 0.f;
+  if (row < rows) {
+    const float* p = src + row * d;
+    for (int k = 0; k < d; ++k) n2 = fmaf(p[k], p[k], n2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n2 = fmaxf(n2, __shfl_xor_sync(0xffffffffu, n2, o));
+  if ((threadIdx.x & 31) == 0 && n2 > 0.f) atomicMax(max_bits, __float_as_uint(n2));
+}
+
+__global__ void header_kernel(IndexHeader* dst, IndexHeader h) { *dst = h; }
+
+// per-query margins from |q| and the corpus max norm
+__global__ void __launch_bounds__(256)
+qmargin_kernel(const float* __restrict__ q, long long Q, long long Qp, int d, const IndexHeader* __restrict__ hdr,
+               float* __restrict__ margin, float* __restrict__ cut) {
+  long long row = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (row >= Qp) return;
+  float n2 = 0.f;
+  if (row < Q) {
+    const float* p = q + row * d;
+    for (int k = 0; k < d; ++k) n2 = fmaf(p[k], p[k], n2);
+  }
+  float cn = sqrtf(__uint_as_float(hdr->max_norm2_bits)) * 1.001f;
+  float qn = sqrtf(n2) * 1.001f;
+  float e = E_REL * qn * cn + 1e-30f;
+  margin[row] = 2.f * e + E_ACC * qn * cn;
+  cut[row] = 2.f * e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the screening GEMM
+// ------------------------------------------------------------------------------------------------
+enum { MODE_SAMPLE = 0, MODE_FILTER = 1 };
+
+struct ScanParams {
+  const unsigned char* qimg;    // query tile image  [2*nqb tiles][KB][16 KB]
+  const unsigned char* cimg;    // corpus tile image [n_tiles][KB][16 KB]
+  long long Q, N;
+  int nqb, parts, n_seq, stride;  // tile sequence: tile(u) = u * stride, u in [0, n_seq)
+  long long n_tiles;
+  // SAMPLE
+  float* binmax; int bins_ld;     // [Qp, bins_ld], 2 bins per sampled tile
+  // FILTER
+  const float* thr;               // [Qp]
+  unsigned int* count;            // [Qp]
+  uint2* cand;                    // [Qp, CAND_CAP] (score bits, local index)
+};
+
+template <int KB, int STAGES, int MODE>
+__global__ void __launch_bounds__(THREADS, 1)
+tc_scan_kernel(const ScanParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // carve: [A: 2*KB slabs][B: STAGES*KB slabs][barriers]
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + 2 * KB * SLAB_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * KB * SLAB_BYTES);
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* a_full = bars + 2 * STAGES;  // [1]
+  uint64_t* t_full = a_full + 1;         // [2]
+  uint64_t* t_empty = t_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = blockIdx.x % p.nqb, part = blockIdx.x / p.nqb;
+  const int u_begin = (int)((long long)part * p.n_seq / p.parts);
+  const int u_end = (int)((long long)(part + 1) * p.n_seq / p.parts);
+  const int n_iter = u_end - u_begin;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(a_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== bulk-TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(a_full, 2 * KB * SLAB_BYTES);
+      bulk_g2s(sA, p.qimg + (long long)qb * 2 * KB * SLAB_BYTES, 2 * KB * SLAB_BYTES, a_full);
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < n_iter; ++it) {
+        const long long tile = (long long)(u_begin + it) * p.stride;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], KB * SLAB_BYTES);
+        bulk_g2s(sB + stage * KB * SLAB_BYTES, p.cimg + tile * ((long long)KB * SLAB_BYTES), KB * SLAB_BYTES, &full[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread) =====
+    if (lane == 0) {
+      mbar_wait(a_full, 0);
+      tc_fence_after();
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < n_iter; ++it) {
+        const int buf = it & 1;
+        const uint32_t tphase = (it >> 1) & 1;
+        mbar_wait(&t_empty[buf], tphase ^ 1);   // epilogue drained this accumulator buffer
+        mbar_wait(&full[stage], phase);         // B tile landed
+        tc_fence_after();
+#pragma unroll
+        for (int ab = 0; ab < 2; ++ab) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)((ab * 2 + buf) * TILE_N);
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint64_t a_desc = make_smem_desc(smem_u32(sA + (ab * KB + kb) * SLAB_BYTES));
+            const uint64_t b_desc = make_smem_desc(smem_u32(sB + (stage * KB + kb) * SLAB_BYTES));
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)  // 4 x (K=16 bf16 = 32 B) inside the 128-byte swizzle row
+              umma_bf16(d_tmem, a_desc + (uint64_t)(k4 * 2), b_desc + (uint64_t)(k4 * 2), IDESC_BF16_M128_N128,
+                        (uint32_t)((kb | k4) != 0));
+          }
+        }
+        umma_commit(&empty[stage]);   // smem slot free once these MMAs retire
+        umma_commit(&t_full[buf]);    // accumulators ready for the epilogue
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===== epilogue: one query row per thread =====
+    const int ew = warp - EPI_WARP0;       // 0..7
+    const int ab = ew >> 2, quad = ew & 3; // TMEM lane quadrant == warp % 4
+    const long long row = (long long)qb * QBLK + ab * TILE_M + quad * 32 + lane;
+    const bool row_ok = row < p.Q;
+    float thr = INFINITY;
+    if (MODE == MODE_FILTER && row_ok) thr = p.thr[row];
+    for (int it = 0; it < n_iter; ++it) {
+      const int buf = it & 1;
+      const uint32_t tphase = (it >> 1) & 1;
+      const int u = u_begin + it;
+      const long long tile = (long long)u * p.stride;
+      const long long col0 = tile * TILE_N;
+      const int n_valid = (int)min((long long)TILE_N, p.N - col0);  // < 128 only on the last tile
+      mbar_wait(&t_full[buf], tphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ab * 2 + buf) * TILE_N);
+      float binm[2] = {-INFINITY, -INFINITY};
+      uint32_t rbuf[2][32];
+      tmem_ld32(taddr, rbuf[0]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t (&r)[32] = rbuf[c & 1];
+        tmem_ld_wait(r);                                         // chunk c has landed
+        if (c < 3) tmem_ld32(taddr + (c + 1) * 32, rbuf[(c + 1) & 1]);  // prefetch chunk c+1 under the math
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (n_valid < TILE_N) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (c * 32 + j >= n_valid) v[j] = -INFINITY;
+        }
+        // 8 group maxima of 4, then their max
+        float g[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = fmaxf(max3(v[4 * i], v[4 * i + 1], v[4 * i + 2]), v[4 * i + 3]);
+        const float m = fmaxf(max3(g[0], g[1], g[2]), fmaxf(max3(g[3], g[4], g[5]), fmaxf(g[6], g[7])));
+        if (MODE == MODE_SAMPLE) {
+          binm[c >> 1] = fmaxf(binm[c >> 1], m);
+        } else {
+          if (m >= thr) {  // rare: some lane of this warp has a survivor in these 32 columns
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (g[i] >= thr) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float s = v[4 * i + j];
+                  if (s >= thr) {
+                    const unsigned int pos = atomicAdd(&p.count[row], 1u);
+                    if (pos < CAND_CAP)
+                      p.cand[row * CAND_CAP + pos] = make_uint2(__float_as_uint(s), (unsigned int)(col0 + c * 32 + 4 * i + j));
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      // all TMEM reads of this buffer are complete (wait::ld above): hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[buf]);
+      if (MODE == MODE_SAMPLE && row_ok)
+        *reinterpret_cast<float2*>(p.binmax + row * p.bins_ld + 2 * u) = make_float2(binm[0], binm[1]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// threshold from the bin maxima; finalize; fallback
+// ------------------------------------------------------------------------------------------------
+struct BinProvider {
+  const float* binmax; int bins_ld; int n_bins;
+  __device__ void begin(int, void*) {}
+  __device__ long long count(int) const { return n_bins; }
+  __device__ void get(int row, long long t, float& s, long long& i) const { s = binmax[(long long)row * bins_ld + t]; i = t; }
+};
+
+__global__ void __launch_bounds__(256)
+thr_kernel(const float* __restrict__ bin_top, int k, long long Q, long long Qp, const float* __restrict__ margin,
+           float* __restrict__ thr, unsigned int* __restrict__ count, unsigned int* __restrict__ overflow) {
+  long long row = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (row >= Qp) return;
+  count[row] = 0;
+  if (row < Q) { thr[row] = bin_top[row * k + (k - 1)] - margin[row]; overflow[row] = 0; }
+  else thr[row] = INFINITY;
+}
+
+__global__ void __launch_bounds__(256)
+tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus, int d, int k, long long index_offset,
+                   const unsigned int* __restrict__ count, const uint2* __restrict__ cand, const float* __restrict__ cut,
+                   unsigned int* __restrict__ overflow, float* __restrict__ out_s, long long* __restrict__ out_i) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  long long* bi = reinterpret_cast<long long*>(fsm);                 // [CAND_CAP]
+  float* bs = reinterpret_cast<float*>(fsm + (size_t)CAND_CAP * 8);  // [CAND_CAP]
+  float* qs = bs + CAND_CAP;                                          // [d]
+  __shared__ int m_sh;
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const unsigned int n_raw = count[row];
+  if (n_raw > (unsigned)CAND_CAP || n_raw < (unsigned)k) {  // overflow (or impossible underflow): exact fallback
+    if (tid == 0) overflow[row] = 1;
+    return;
+  }
+  const int n = (int)n_raw;
+  for (int t = tid; t < d; t += 256) qs[t] = q[(long long)row * d + t];
+  int P = 2; while (P < n) P <<= 1;
+  for (int t = tid; t < P; t += 256) {
+    if (t < n) { uint2 e = cand[(long long)row * CAND_CAP + t]; bs[t] = __uint_as_float(e.x); bi[t] = (long long)e.y; }
+    else { bs[t] = -INFINITY; bi[t] = LLONG_MAX; }
+  }
+  if (tid == 0) m_sh = 0;
+  __syncthreads();
+  bitonic_sort_desc(bs, bi, P);  // by screening score
+  // survivors inside the error band of tau = k-th best screening score
+  const float lim = bs[k - 1] - cut[row];
+  int local = 0;
+  for (int t = tid; t < n; t += 256) local += (bs[t] >= lim) ? 1 : 0;
+  if (local) atomicAdd(&m_sh, local);
+  __syncthreads();
+  const int m = m_sh;  // sorted desc => exactly the first m entries
+  __syncthreads();
+  // exact re-scoring: the canonical sequential fmaf chain on the fp32 corpus
+  for (int t = tid; t < m; t += 256) {
+    const float* c = corpus + bi[t] * d;
+    float acc = 0.f;
+    if ((d & 3) == 0) {
+      for (int kk = 0; kk < d; kk += 4) {
+        float4 cv = __ldg(reinterpret_cast<const float4*>(c + kk));
+        acc = fmaf(qs[kk], cv.x, acc); acc = fmaf(qs[kk + 1], cv.y, acc);
+        acc = fmaf(qs[kk + 2], cv.z, acc); acc = fmaf(qs[kk + 3], cv.w, acc);
+      }
+    } else {
+      for (int kk = 0; kk < d; ++kk) acc = fmaf(qs[kk], __ldg(c + kk), acc);
+    }
+    bs[t] = acc;
+  }
+  int P2 = 2; while (P2 < m) P2 <<= 1;
+  __syncthreads();
+  for (int t = m + tid; t < P2; t += 256) { bs[t] = -INFINITY; bi[t] = LLONG_MAX; }
+  __syncthreads();
+  bitonic_sort_desc(bs, bi, P2);  // (exact score desc, index asc)
+  for (int t = tid; t < k; t += 256) {
+    out_s[(long long)row * k + t] = bs[t];
+    out_i[(long long)row * k + t] = bi[t] + index_offset;
+  }
+}
+
+struct FallbackProvider {
+  const float* q; const float* corpus; long long N; int d; long long index_offset; const unsigned int* overflow;
+  float* qs;
+  __device__ void begin(int row, void* extra) {
+    qs = reinterpret_cast<float*>(extra);
+    if (overflow[row]) for (int t = threadIdx.x; t < d; t += blockDim.x) qs[t] = q[(long long)row * d + t];
+  }
+  __device__ long long count(int row) const { return overflow[row] ? N : 0; }
+  __device__ void get(int, long long t, float& s, long long& i) const {
+    const float* c = corpus + t * d;
+    float acc = 0.f;
+    for (int kk = 0; kk < d; ++kk) acc = fmaf(qs[kk], __ldg(c + kk), acc);
+    s = acc; i = index_offset + t;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+// Optional per-stage device timing (bench.py's roofline leg): CUDA events recorded on the launch stream
+// around the stages of tfrs_topk_tc_f32.  Off by default; adds two event records per stage when on.
+struct Prof {
+  bool on = false;
+  static constexpr int MAXC = 512, STAGES_ = 4;  // 0 prep, 1 sample(+threshold), 2 filter, 3 finalize(+fallback)
+  cudaEvent_t ev[MAXC][STAGES_ + 1];
+  int created = 0, calls = 0;
+};
+static Prof g_prof;
+static void prof_mark(cudaStream_t st, int stage) {
+  if (!g_prof.on || g_prof.calls >= Prof::MAXC) return;
+  int c = g_prof.calls;
+  while (g_prof.created <= c) {
+    for (int s = 0; s <= Prof::STAGES_; ++s) cudaEventCreate(&g_prof.ev[g_prof.created][s]);
+    ++g_prof.created;
+  }
+  cudaEventRecord(g_prof.ev[c][stage], st);
+  if (stage == Prof::STAGES_) ++g_prof.calls;
+}
+
+struct Plan {
+  int kb, stages; long long n_tiles; int nqb; long long Qp;
+  int stride, n_sample, n_bins, bins_ld, parts_sample, parts_full;
+  size_t smem;
+  // workspace offsets
+  size_t o_qimg, o_margin, o_cut, o_thr, o_count, o_ovf, o_binmax, o_bintop_s, o_bintop_i, o_cand, total;
+};
+
+static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
+  if (d <= 0 || d > 256 || Q <= 0 || N <= 0 || k <= 0) return false;
+  pl.kb = (d + KSLAB - 1) / KSLAB;
+  pl.stages = pl.kb == 1 ? 6 : 4;
+  pl.n_tiles = ceil_div(N, TILE_N);
+  pl.nqb = (int)ceil_div(Q, QBLK);
+  pl.Qp = (long long)pl.nqb * QBLK;
+  if (pl.kb > 2) return false;          // d > 128: smem budget (A blocks + ring) not laid out yet
+  if (k > 512 || N >= (1ll << 31)) return false;
+  // sample every stride-th tile; keep at least 4k bins so the k-th largest bin max is a tight bound
+  pl.stride = MAX_SAMPLE_STRIDE;
+  while (pl.stride > 1 && 2 * ceil_div(pl.n_tiles, pl.stride) < 4ll * k) pl.stride >>= 1;
+  pl.n_sample = (int)ceil_div(pl.n_tiles, pl.stride);
+  pl.n_bins = pl.n_sample * 2;
+  pl.bins_ld = (pl.n_bins + 3) / 4 * 4;
+  if (pl.n_bins < 4 * k) return false;  // too few bins for a useful threshold -> caller uses the exact path
+  const int sms = sm_count();
+  int parts = sms / pl.nqb; if (parts < 1) parts = 1;
+  pl.parts_sample = parts < pl.n_sample ? parts : pl.n_sample;
+  pl.parts_full = (long long)parts < pl.n_tiles ? parts : (int)pl.n_tiles;
+  pl.smem = (size_t)(2 + pl.stages) * pl.kb * SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 1024); return r; };
+  pl.o_qimg = take((size_t)pl.nqb * 2 * pl.kb * SLAB_BYTES);
+  pl.o_margin = take((size_t)pl.Qp * 4);
+  pl.o_cut = take((size_t)pl.Qp * 4);
+  pl.o_thr = take((size_t)pl.Qp * 4);
+  pl.o_count = take((size_t)pl.Qp * 4);
+  pl.o_ovf = take((size_t)pl.Qp * 4);
+  pl.o_binmax = take((size_t)pl.Qp * pl.bins_ld * 4);
+  pl.o_bintop_s = take((size_t)Q * k * 4);
+  pl.o_bintop_i = take((size_t)Q * k * 8);
+  pl.o_cand = take((size_t)pl.Qp * CAND_CAP * 8);
+  pl.total = o;
+  return true;
+}
+
+template <int KB, int STAGES>
+static int launch_scans(const Plan& pl, ScanParams sp, cudaStream_t st, int mode) {
+  auto ks = tc_scan_kernel<KB, STAGES, MODE_SAMPLE>;
+  auto kf = tc_scan_kernel<KB, STAGES, MODE_FILTER>;
+  static bool attr = false;
+  if (!attr) {
+    TFRS_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    TFRS_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    attr = true;
+  }
+  if (mode == MODE_SAMPLE) {
+    sp.parts = pl.parts_sample; sp.n_seq = pl.n_sample; sp.stride = pl.stride;
+    ks<<<(unsigned)(pl.nqb * sp.parts), THREADS, pl.smem, st>>>(sp);
+  } else {
+    sp.parts = pl.parts_full; sp.n_seq = (int)pl.n_tiles; sp.stride = 1;
+    kf<<<(unsigned)(pl.nqb * sp.parts), THREADS, pl.smem, st>>>(sp);
+  }
+  TFRS_LAUNCH_CHECK();
+  return TFRS_OK;
+}
+
+static int launch_scan_mode(const Plan& pl, const ScanParams& sp, cudaStream_t st, int mode) {
+  if (pl.kb == 1) return launch_scans<1, 6>(pl, sp, st, mode);
+  return launch_scans<2, 4>(pl, sp, st, mode);
+}
+
+}  // namespace tc
+}  // namespace tfrs
+
 using namespace tfrs;
-extern "C" size_t tfrs_index_bytes(int64_t, int) { return 0; }
-extern "C" int tfrs_index_build(const float*, int64_t, int, void*, size_t, void*) { set_error("tc path not built"); return TFRS_ERR_UNSUPPORTED; }
-extern "C" size_t tfrs_topk_tc_workspace_bytes(int64_t, int64_t, int, int) { return 0; }
-extern "C" int tfrs_topk_tc_f32(const float*, int64_t, const float*, const void*, int64_t, int, int, int64_t, float*, int64_t*, void*, size_t, void*) { set_error("tc path not built"); return TFRS_ERR_UNSUPPORTED; }
+using namespace tfrs::tc;
+
+extern "C" size_t tfrs_index_bytes(int64_t N, int d) {
+  if (N <= 0 || d <= 0 || d > 128) return 0;
+  int kb = (d + KSLAB - 1) / KSLAB;
+  return (size_t)HEADER_BYTES + (size_t)ceil_div(N, TILE_N) * kb * SLAB_BYTES;
+}
+
+extern "C" int tfrs_index_build(const float* corpus, int64_t N, int d, void* index_buf, size_t index_bytes, void* stream) {
+  TFRS_CHECK_ARG(corpus && index_buf && N > 0 && d > 0, "index_build: bad arguments");
+  if (d > 128) { set_error("index_build: d=%d > 128 is not supported by the tensor-core path", d); return TFRS_ERR_UNSUPPORTED; }
+  TFRS_CHECK_ARG(index_bytes >= tfrs_index_bytes(N, d), "index_build: buffer too small");
+  TFRS_CHECK_ARG((reinterpret_cast<uintptr_t>(index_buf) & 15) == 0, "index_build: buffer must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  IndexHeader h{};
+  h.d = d; h.kb = (d + KSLAB - 1) / KSLAB; h.d_pad = h.kb * KSLAB; h.n = N; h.n_tiles = ceil_div(N, TILE_N);
+  h.max_norm2_bits = 0;
+  TFRS_CUDA(cudaMemsetAsync(index_buf, 0, HEADER_BYTES, st));
+  header_kernel<<<1, 1, 0, st>>>(reinterpret_cast<IndexHeader*>(index_buf), h);
+  TFRS_LAUNCH_CHECK();
+  max_norm_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(corpus, N, d, reinterpret_cast<unsigned int*>(index_buf));
+  TFRS_LAUNCH_CHECK();
+  long long chunks = h.n_tiles * TILE_N * (long long)h.kb * 8;
+  unsigned blocks = (unsigned)(ceil_div(chunks, 256) < (1 << 20) ? ceil_div(chunks, 256) : (1 << 20));
+  tile_image_kernel<<<blocks, 256, 0, st>>>(corpus, N, d, h.kb, h.n_tiles, (unsigned char*)index_buf + HEADER_BYTES);
+  TFRS_LAUNCH_CHECK();
+  return TFRS_OK;
+}
+
+extern "C" size_t tfrs_topk_tc_workspace_bytes(int64_t Q, int64_t N, int d, int k) {
+  Plan pl;
+  if (!make_plan(Q, N, d, k, pl)) return 0;
+  return pl.total;
+}
+
+extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, const void* index_buf, int64_t N, int d,
+                                int k, int64_t index_offset, float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes,
+                                void* stream) {
+  TFRS_CHECK_ARG(q && corpus && index_buf && out_scores && out_idx, "topk_tc: NULL pointer");
+  TFRS_CHECK_ARG(k <= N, "input must have at least k columns. Had %lld, needed %d", (long long)N, k);
+  Plan pl;
+  if (!make_plan(Q, N, d, k, pl)) {
+    set_error("topk_tc: shape (Q=%lld N=%lld d=%d k=%d) is outside the tensor-core path; use tfrs_topk_scan_f32",
+              (long long)Q, (long long)N, d, k);
+    return TFRS_ERR_UNSUPPORTED;
+  }
+  if (!ws || ws_bytes < pl.total) { set_error("topk_tc: workspace too small (%zu < %zu)", ws_bytes, pl.total); return TFRS_ERR_WORKSPACE_TOO_SMALL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* w = (unsigned char*)(((uintptr_t)ws + 15) & ~(uintptr_t)15);
+  unsigned char* qimg = w + pl.o_qimg;
+  float* margin = (float*)(w + pl.o_margin);
+  float* cut = (float*)(w + pl.o_cut);
+  float* thr = (float*)(w + pl.o_thr);
+  unsigned int* count = (unsigned int*)(w + pl.o_count);
+  unsigned int* ovf = (unsigned int*)(w + pl.o_ovf);
+  float* binmax = (float*)(w + pl.o_binmax);
+  float* bintop_s = (float*)(w + pl.o_bintop_s);
+  long long* bintop_i = (long long*)(w + pl.o_bintop_i);
+  uint2* cand = (uint2*)(w + pl.o_cand);
+  const IndexHeader* hdr = (const IndexHeader*)index_buf;
+  const unsigned char* cimg = (const unsigned char*)index_buf + HEADER_BYTES;
+
+  prof_mark(st, 0);
+  // (0) query image + margins
+  {
+    long long chunks = (long long)pl.nqb * 2 * TILE_N * pl.kb * 8;
+    tile_image_kernel<<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(q, Q, d, pl.kb, (long long)pl.nqb * 2, qimg);
+    TFRS_LAUNCH_CHECK();
+    qmargin_kernel<<<(unsigned)ceil_div(pl.Qp, 256), 256, 0, st>>>(q, Q, pl.Qp, d, hdr, margin, cut);
+    TFRS_LAUNCH_CHECK();
+  }
+  ScanParams sp{};
+  sp.qimg = qimg; sp.cimg = cimg; sp.Q = Q; sp.N = N; sp.nqb = pl.nqb; sp.n_tiles = pl.n_tiles;
+  sp.binmax = binmax; sp.bins_ld = pl.bins_ld; sp.thr = thr; sp.count = count; sp.cand = cand;
+  prof_mark(st, 1);
+  // (1) sampled pass -> bin maxima -> k-th largest -> threshold
+  int rc = launch_scan_mode(pl, sp, st, MODE_SAMPLE);
+  if (rc) return rc;
+  {
+    BinProvider bp{binmax, pl.bins_ld, pl.n_bins};
+    int cap = rowselect_cap(k);
+    static bool attr = false;
+    if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(row_topk_kernel<BinProvider>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
+    row_topk_kernel<BinProvider><<<(unsigned)Q, RS_THREADS, rowselect_smem(cap, 0), st>>>(bp, k, cap, bintop_s, bintop_i, k);
+    TFRS_LAUNCH_CHECK();
+    thr_kernel<<<(unsigned)ceil_div(pl.Qp, 256), 256, 0, st>>>(bintop_s, k, Q, pl.Qp, margin, thr, count, ovf);
+    TFRS_LAUNCH_CHECK();
+  }
+  prof_mark(st, 2);
+  // (2) full pass with the fused threshold filter
+  rc = launch_scan_mode(pl, sp, st, MODE_FILTER);
+  if (rc) return rc;
+  prof_mark(st, 3);
+  // (3) exact re-scoring + final order
+  {
+    size_t smem = (size_t)CAND_CAP * 12 + (size_t)d * 4 + 16;
+    static bool attr = false;
+    if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
+    tc_finalize_kernel<<<(unsigned)Q, 256, smem, st>>>(q, corpus, d, k, index_offset, count, cand, cut, ovf, out_scores,
+                                                     (long long*)out_idx);
+    TFRS_LAUNCH_CHECK();
+  }
+  // (4) exact fallback for overflowed queries (CTAs of non-flagged queries exit immediately)
+  {
+    FallbackProvider fp{q, corpus, N, d, index_offset, ovf, nullptr};
+    int cap = rowselect_cap(k);
+    static bool attr = false;
+    if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(row_topk_kernel<FallbackProvider>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
+    row_topk_kernel<FallbackProvider><<<(unsigned)Q, RS_THREADS, rowselect_smem(cap, (size_t)d * 4), st>>>(
+        fp, k, cap, out_scores, (long long*)out_idx, k);
+    TFRS_LAUNCH_CHECK();
+  }
+  prof_mark(st, 4);
+  return TFRS_OK;
+}
+
+extern "C" int tfrs_profile_enable(int on) {
+  g_prof.on = on != 0;
+  g_prof.calls = 0;
+  return TFRS_OK;
+}
+
+// Synchronises the device, then returns the summed stage times (ms) over the calls recorded since
+// tfrs_profile_enable(1): stage_ms[0..3] = prep, sample+threshold, filter, finalize+fallback.
+extern "C" int tfrs_profile_read(float* stage_ms, int* calls) {
+  TFRS_CHECK_ARG(stage_ms && calls, "profile_read: NULL pointer");
+  TFRS_CUDA(cudaDeviceSynchronize());
+  for (int s = 0; s < 4; ++s) stage_ms[s] = 0.f;
+  for (int c = 0; c < g_prof.calls; ++c)
+    for (int s = 0; s < 4; ++s) {
+      float ms = 0.f;
+      TFRS_CUDA(cudaEventElapsedTime(&ms, g_prof.ev[c][s], g_prof.ev[c][s + 1]));
+      stage_ms[s] += ms;
+    }
+  *calls = g_prof.calls;
+  return TFRS_OK;
+}

@@ -277,14 +277,12 @@ class BruteForce(TopK):
     self._candidates = cands
     self._identifiers = identifiers
     self._tc_index = None
-    if self.use_tensor_cores and cands.shape[0] >= ops.TC_MIN_N:
-      try:
-        self._tc_index = ops.index_build(cands)
-      except NotImplementedError:
-        self._tc_index = None
+    if self.use_tensor_cores and cands.shape[0] >= ops.TC_MIN_N and cands.shape[1] <= 128:
+      self._tc_index = ops.index_build(cands)
 
   def _local_topk(self, queries: Tensor, k: int, offset: int):
-    if self._tc_index is not None and k <= ops.TC_MAX_K:
+    if self._tc_index is not None and ops.tc_supported(queries.shape[0], self._candidates.shape[0],
+                                                       self._candidates.shape[1], k):
       return ops.topk_tc(queries, self._candidates, self._tc_index, k, index_offset=offset)
     return ops.topk_scan(queries, self._candidates, k, index_offset=offset)
 

@@ -115,6 +115,22 @@ def topk_tc(q: torch.Tensor, corpus: torch.Tensor, index_buf: torch.Tensor, k: i
   return out_s, out_i
 
 
+def tc_supported(Q: int, N: int, d: int, k: int) -> bool:
+  """True when (Q, N, d, k) is inside the tensor-core path (otherwise callers use topk_scan)."""
+  return lib().tfrs_topk_tc_workspace_bytes(Q, N, d, k) > 0
+
+
+def profile_enable(on: bool) -> None:
+  check(lib().tfrs_profile_enable(int(on)), "profile_enable")
+
+
+def profile_read():
+  """-> (stage_ms[4], calls): prep, sample+threshold, filter, finalize; synchronises the device."""
+  ms = (ctypes.c_float * 4)(); calls = ctypes.c_int(0)
+  check(lib().tfrs_profile_read(ms, ctypes.byref(calls)), "profile_read")
+  return [float(x) for x in ms], int(calls.value)
+
+
 def topk_merge(scores: torch.Tensor, idx: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
   """Merge [L,Q,k_in] lists into the best min(k, L*k_in) per query."""
   scores = f32c(scores, "scores"); idx = require_cuda(idx, "idx").to(torch.int64).contiguous()

@@ -1,0 +1,102 @@
+"""GPU parity tests of the tensor-core top-K path (tcgen05 screening + exact re-scoring), through the C ABI.
+Bar: bit-exact ids and scores against the CPU oracle and against the exact CUDA-core path."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+  from recommenders_b200 import ops as o
+  return o
+
+
+def _rand(shape, seed, scale=1.0):
+  g = torch.Generator(device="cuda"); g.manual_seed(seed)
+  return torch.randn(shape, generator=g, device="cuda") * scale
+
+
+def _check(ops, q, c, k, offset=0, oracle_rows=32):
+  idx = ops.index_build(c)
+  assert ops.tc_supported(q.shape[0], c.shape[0], c.shape[1], k)
+  s, i = ops.topk_tc(q, c, idx, k, index_offset=offset)
+  es, ei = ops.topk_scan(q, c, k, index_offset=offset)
+  assert torch.equal(i, ei) and torch.equal(s, es), "tensor-core path differs from the exact CUDA-core path"
+  r = min(oracle_rows, q.shape[0])
+  os_, oi = orc.topk_scan(q[:r].cpu().numpy(), c.cpu().numpy(), k, index_offset=offset)
+  np.testing.assert_array_equal(i[:r].cpu().numpy(), oi)
+  np.testing.assert_array_equal(s[:r].cpu().numpy().view(np.uint32), os_.view(np.uint32))
+  return s, i
+
+
+@pytest.mark.parametrize("Q,N,d,k", [(300, 40000, 64, 100), (256, 32768, 64, 100), (1000, 200000, 128, 10),
+                                     (17, 65537, 33, 50), (513, 100001, 100, 128), (4096, 131072, 64, 100)])
+def test_tc_matches_exact(ops, Q, N, d, k):
+  _check(ops, _rand((Q, d), 2), _rand((N, d), 1), k)
+
+
+def test_tc_index_offset_and_negative_scores(ops):
+  # all scores negative and N not a multiple of 128: zero-padded rows must never be returned
+  c = torch.rand((50001, 64), device="cuda") + 0.1
+  q = -(torch.rand((64, 64), device="cuda") + 0.1)
+  s, i = _check(ops, q, c, 20, offset=123456789)
+  assert int(i.min()) >= 123456789 and int(i.max()) < 123456789 + 50001 and float(s.max()) < 0
+
+
+def test_tc_ties_overflow_fallback(ops):
+  # every candidate identical -> every screening score ties -> survivor lists overflow -> exact fallback
+  c = torch.ones((40000, 64), device="cuda"); q = _rand((40, 64), 3)
+  s, i = _check(ops, q, c, 10)
+  assert torch.equal(i, torch.arange(10, device="cuda").expand(40, 10))
+  # duplicated corpus blocks: exact duplicates across tiles, lowest index must win
+  base = _rand((20000, 64), 4)
+  _check(ops, _rand((100, 64), 5), torch.cat([base, base, base], 0), 30)
+
+
+def test_tc_scaled_inputs(ops):
+  # large dynamic range: margins scale with |q| * max|c|
+  _check(ops, _rand((128, 64), 6, 1e3), _rand((60000, 64), 7, 1e-3), 25)
+  c = _rand((60000, 64), 8); c[12345] *= 1000.0   # one huge-norm row inflates the bound -> more survivors, same answer
+  _check(ops, _rand((64, 64), 9), c, 10)
+
+
+def test_tc_full_size_properties(ops):
+  """BASELINE config 2 at full size (1M x 64, 4096 queries, top-100): size-independent properties +
+  exact-path equality on a slice + oracle on a few rows."""
+  N, d, Q, k = 1_000_000, 64, 4096, 100
+  c = _rand((N, d), 1); q = _rand((Q, d), 2)
+  idx = ops.index_build(c)
+  s, i = ops.topk_tc(q, c, idx, k)
+  assert bool((s[:, :-1] >= s[:, 1:]).all()), "scores must be sorted descending"
+  assert int(i.min()) >= 0 and int(i.max()) < N
+  assert all(len(set(r)) == k for r in i[:64].cpu().tolist()), "indices must be distinct"
+  # returned scores are the exact chain of the returned rows
+  rows = torch.arange(0, Q, 37, device="cuda")
+  for j in (0, 57, 99):
+    assert torch.equal(ops.rowwise_dot(q[rows], c[i[rows, j]]), s[rows, j])
+  es, ei = ops.topk_scan(q[:256], c, k)
+  assert torch.equal(i[:256], ei) and torch.equal(s[:256], es)
+  os_, oi = orc.topk_scan(q[4000:4008].cpu().numpy(), c.cpu().numpy(), k)
+  np.testing.assert_array_equal(i[4000:4008].cpu().numpy(), oi)
+  np.testing.assert_array_equal(s[4000:4008].cpu().numpy(), os_)
+
+
+def test_bruteforce_layer_uses_tc_and_shards(ops):
+  import recommenders_b200 as tfrs
+  c = _rand((70000, 64), 11); q = _rand((200, 64), 12)
+  layer = tfrs.layers.factorized_top_k.BruteForce(k=50).index(c)
+  assert layer._tc_index is not None
+  s, i = layer(q)
+  es, ei = ops.topk_scan(q, c, 50)
+  assert torch.equal(i.to(torch.int64), ei) and torch.equal(s, es) and i.dtype == torch.int32
+  # emulate the 2-shard protocol in one process: local scans with offsets, then the merge kernel
+  parts = []
+  for lo, hi in (tfrs.layers.factorized_top_k.shard_bounds(70000, r, 2) for r in range(2)):
+    l = tfrs.layers.factorized_top_k.BruteForce(k=50).index(c[lo:hi])
+    parts.append(l._local_topk(q, 50, lo))
+  ms, mi = ops.topk_merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), 50)
+  assert torch.equal(mi, ei) and torch.equal(ms, es)
