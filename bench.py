@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: queries/sec of brute-force top-K retrieval (BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm: the reference's op sequence on host cores)
+
+A "step" = one BruteForce.call: 4096 queries x (1M x 64) corpus -> top-100 (BASELINE configs[1]).  At N>1
+the same corpus is row-sharded over the ranks (strong scaling): every rank scans its shard, ONE all-gather
+of the per-shard (score, index) top-K, merge on every rank.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N, d, Q, k)
+    "cfg2": (1_000_000, 64, 4096, 100),    # BASELINE configs[1]: the config the metric is quoted on
+    "cfg4": (8_000_000, 128, 4096, 100),   # BASELINE configs[3]: the 8-GPU sharded corpus
+    "small": (131072, 64, 1024, 100),
+}
+METRIC = "queries/sec brute-force top-K (1Mx64 candidates)"
+
+
+class ClockSampler(threading.Thread):
+  """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+  def __init__(self, index: int):
+    super().__init__(daemon=True)
+    self.index = index
+    self.rows = []
+    self._stop = threading.Event()
+    self.proc = None
+
+  def run(self):
+    q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                    "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      for line in self.proc.stdout:
+        if self._stop.is_set():
+          break
+        self.rows.append([x.strip() for x in line.split(",")])
+    except Exception:
+      pass
+
+  def stop(self):
+    self._stop.set()
+    if self.proc is not None:
+      try:
+        self.proc.terminate()
+      except Exception:
+        pass
+
+  def summary(self):
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for r in self.rows:
+      try:
+        sm.append(float(r[0])); mx.append(float(r[1]))
+        for n, v in zip(names, r[3:7]):
+          if v.lower().startswith("active"):
+            reasons.add(n)
+      except Exception:
+        continue
+    if not sm:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    sm_sorted = sorted(sm)
+    busy = [x for x in sm_sorted if x > 0.5 * max(sm_sorted)] or sm_sorted
+    return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_arm_step(orc, q, c, k):
+  """The reference's CPU op sequence (matmul -> top_k -> gather ids, factorized_top_k.py:603-607) via BLAS."""
+  return orc.brute_force_blas(q, c, k)
+
+
+def run_reference(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return 0
+  import numpy as np
+  from oracle import oracle as orc
+  N, d, Q, k = WORKLOADS[args.workload]
+  sample_q = args.cpu_queries
+  c = np.random.default_rng(1).standard_normal((N, d), dtype=np.float32)
+  q = np.random.RandomState(2).normal(size=(sample_q, d)).astype(np.float32)
+  for _ in range(max(1, min(args.warmup, 2))):
+    cpu_arm_step(orc, q, c, k)
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    cpu_arm_step(orc, q, c, k)
+  dt = time.perf_counter() - t0
+  value = sample_q * args.steps / dt
+  cores = os.cpu_count() or 1
+  line = {
+      "impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+      "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+      "config": {"workload": f"{args.workload}: N={N} d={d} K={k}; each step scores a {sample_q}-query sample of the 4096-query batch "
+                             "against the full corpus", "note": "TensorFlow is not installable here; this is the reference's op "
+                             "sequence (sgemm -> top_k -> gather) restated on NumPy/BLAS (oracle port)"},
+      "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
+                       "sample": f"{sample_q} queries x {N} candidates x {args.steps} steps"},
+      "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+      "gpu_launches": 0,
+  }
+  print(json.dumps(line))
+  return 0
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=20)
+  ap.add_argument("--warmup", type=int, default=5)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+  ap.add_argument("--cpu-queries", type=int, default=64, help="queries per CPU-arm step (bounded sample)")
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-tensor-cores", action="store_true", help="force the exact CUDA-core path (debug)")
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3)
+  if args.impl == "reference":
+    return run_reference(args)
+
+  import numpy as np
+  import torch
+  import torch.distributed as dist
+  import recommenders_b200 as tfrs
+  from recommenders_b200 import ops
+  from recommenders_b200.layers.factorized_top_k import shard_bounds
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  if world > 1:
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+
+  N, d, Q, k = WORKLOADS[args.workload]
+  lo, hi = shard_bounds(N, rank, world)
+  # synthetic corpus: every rank generates the SAME full-corpus stream in 1M-row blocks and keeps its rows
+  g = torch.Generator(device=dev)
+  blocks = []
+  for b0 in range(0, N, 1_000_000):
+    g.manual_seed(1 + b0)
+    blk = torch.randn((min(1_000_000, N - b0), d), generator=g, device=dev)
+    s0, s1 = max(lo, b0), min(hi, b0 + blk.shape[0])
+    if s1 > s0:
+      blocks.append(blk[s0 - b0:s1 - b0].clone())
+    del blk
+  corpus_local = torch.cat(blocks, 0) if len(blocks) > 1 else blocks[0]
+  del blocks
+  g.manual_seed(2)
+  queries = torch.randn((Q, d), generator=g, device=dev)
+
+  layer = tfrs.layers.factorized_top_k.BruteForce(k=k)
+  layer.use_tensor_cores = not args.no_tensor_cores
+  if world > 1:
+    layer.index_shard(corpus_local, lo)
+  else:
+    layer.index(corpus_local)
+  used_tc = layer._tc_index is not None and ops.tc_supported(Q, corpus_local.shape[0], d, k)
+
+  def sync_all():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  # ---------------- device-resident throughput (`value`) ----------------
+  for _ in range(args.warmup):
+    out = layer(queries)
+  sync_all()
+  sampler = ClockSampler(local_rank)
+  sampler.start()
+  time.sleep(0.15)
+  launches0 = ops.launch_count()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  sync_all()
+  e0.record()
+  for _ in range(args.steps):
+    out = layer(queries)
+  e1.record()
+  torch.cuda.synchronize()
+  launches = ops.launch_count() - launches0
+  ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+  if world > 1:
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+  ms_total = float(ms)
+  value = Q * args.steps / (ms_total * 1e-3)
+
+  # ---------------- end-to-end through the public API with host buffers (`e2e`) ----------------
+  q_host = queries.cpu().pin_memory()
+  s_host = torch.empty((Q, k), dtype=torch.float32).pin_memory()
+  i_host = torch.empty((Q, k), dtype=torch.int32).pin_memory()
+  q_dev = torch.empty_like(queries)
+
+  def e2e_step():
+    q_dev.copy_(q_host, non_blocking=True)
+    s, i = layer(q_dev)
+    s_host.copy_(s, non_blocking=True)
+    i_host.copy_(i, non_blocking=True)
+    torch.cuda.current_stream().synchronize()  # the caller reads the result every step
+
+  for _ in range(args.warmup):
+    e2e_step()
+  sync_all()
+  e0.record()
+  for _ in range(args.steps):
+    e2e_step()
+  e1.record()
+  torch.cuda.synchronize()
+  ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+  if world > 1:
+    dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+  e2e_value = Q * args.steps / (float(ms2) * 1e-3)
+  sampler.stop()
+
+  # ---------------- roofline of the dominant kernel (full filter pass), CUDA events inside the ABI ----------------
+  roofline = None
+  if used_tc:
+    ops.profile_enable(True)
+    for _ in range(args.steps):
+      layer(queries)
+    stage_ms, calls = ops.profile_read()
+    ops.profile_enable(False)
+    peaks = {}
+    try:
+      peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+      pass
+    peak = peaks.get("bf16_tflops", 1590.0)
+    which = "measured bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback 1590"
+    n_local = corpus_local.shape[0]
+    flops = 2.0 * Q * n_local * d  # algorithmic: 2*Q*N*d per launch (128 MFLOP/query at N=1M,d=64)
+    t_filter = stage_ms[2] / max(calls, 1) * 1e-3
+    achieved = flops / t_filter / 1e12
+    roofline = {"bound": "tensor", "kernel": "tc_scan_kernel<FILTER>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "peak_source": which, "traffic": None,
+                "stage_ms_per_call": {"qprep": stage_ms[0] / calls, "sample_pass+threshold": stage_ms[1] / calls,
+                                      "filter_pass": stage_ms[2] / calls, "rescore+finalize": stage_ms[3] / calls}}
+
+  # ---------------- parity of the timed outputs against the oracle (rank 0, a few rows) ----------------
+  checked = None
+  if rank == 0:
+    from oracle import oracle as orc
+    rows = [0, Q // 2, Q - 1]
+    s, i = out
+    if world == 1:
+      es, ei = orc.topk_scan(queries[rows].cpu().numpy(), corpus_local.cpu().numpy(), k)
+      checked = bool(np.array_equal(i[rows].cpu().numpy(), ei) and np.array_equal(s[rows].cpu().numpy(), es))
+    else:
+      checked = bool((s[:, :-1] >= s[:, 1:]).all())  # full oracle needs the whole corpus on one host; see tests
+
+  # ---------------- CPU baseline beside it (rank 0, N=1 only, bounded sample) ----------------
+  cpu_baseline = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    from oracle import oracle as orc
+    cq = args.cpu_queries
+    c_np = corpus_local.cpu().numpy(); q_np = queries[:cq].cpu().numpy()
+    cpu_arm_step(orc, q_np, c_np, k)
+    reps, t0 = 0, time.perf_counter()
+    while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 50):
+      cpu_arm_step(orc, q_np, c_np, k); reps += 1
+    dt = time.perf_counter() - t0
+    cpu_baseline = {"value": cq * reps / dt, "unit": "queries/s", "cores": os.cpu_count() or 1, "kind": "port",
+                    "sample": f"{cq} queries x {N} candidates, {reps} reps (NumPy/BLAS sgemm -> top_k, the reference's op sequence)"}
+
+  if rank == 0:
+    line = {
+        "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 (bf16 tcgen05 screening + exact fp32 re-scoring)" if used_tc else "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: BruteForce top-{k}, {Q} queries x {N}x{d} corpus (N(0,1), seeds 1/2), "
+                               f"row-sharded over {world} GPU(s)",
+                   "path": "tcgen05 screening + exact rescoring" if used_tc else "exact CUDA-core scan",
+                   "l2": "inputs (bf16 image 128 MB + fp32 corpus 256 MB per 1M rows) exceed the 126 MB L2 between steps",
+                   "parallelism": f"corpus-shard x{world}"},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": Q * d * 4, "d2h_bytes_per_step": Q * k * 8,
+                "ms_per_step": float(ms2) / args.steps},
+        "gpu_launches": int(launches),
+        "outputs_match_oracle": checked,
+    }
+    if roofline is not None:
+      line["roofline"] = roofline
+    if cpu_baseline is not None:
+      line["cpu_baseline"] = cpu_baseline
+    print(json.dumps(line))
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+  return 0
+
+
+if __name__ == "__main__":
+  sys.exit(main())

@@ -210,8 +210,9 @@ struct ScanParams {
   float* binmax; int bins_ld;     // [Qp, bins_ld], 2 bins per sampled tile
   // FILTER
   const float* thr;               // [Qp]
-  unsigned int* count;            // [Qp]
-  uint2* cand;                    // [Qp, CAND_CAP] (score bits, local index)
+  unsigned int* count;            // [Qp, parts]   survivors found by each (query, corpus part)
+  uint2* cand;                    // [Qp, parts, cap_part] (score bits, local index): one private segment per
+  int cap_part;                   //   (query row, part) => appended by its single owner thread, no atomics
 };
 
 template <int KB, int STAGES, int MODE>
@@ -300,6 +301,9 @@ tc_scan_kernel(const ScanParams p) {
     const bool row_ok = row < p.Q;
     float thr = INFINITY;
     if (MODE == MODE_FILTER && row_ok) thr = p.thr[row];
+    uint2* my_list = nullptr;
+    unsigned int my_cnt = 0;
+    if (MODE == MODE_FILTER) my_list = p.cand + ((long long)row * p.parts + part) * p.cap_part;
     for (int it = 0; it < n_iter; ++it) {
       const int buf = it & 1;
       const uint32_t tphase = (it >> 1) & 1;
@@ -341,9 +345,9 @@ tc_scan_kernel(const ScanParams p) {
                 for (int j = 0; j < 4; ++j) {
                   const float s = v[4 * i + j];
                   if (s >= thr) {
-                    const unsigned int pos = atomicAdd(&p.count[row], 1u);
-                    if (pos < CAND_CAP)
-                      p.cand[row * CAND_CAP + pos] = make_uint2(__float_as_uint(s), (unsigned int)(col0 + c * 32 + 4 * i + j));
+                    if (my_cnt < (unsigned)p.cap_part)
+                      my_list[my_cnt] = make_uint2(__float_as_uint(s), (unsigned int)(col0 + c * 32 + 4 * i + j));
+                    ++my_cnt;
                   }
                 }
               }
@@ -358,6 +362,7 @@ tc_scan_kernel(const ScanParams p) {
       if (MODE == MODE_SAMPLE && row_ok)
         *reinterpret_cast<float2*>(p.binmax + row * p.bins_ld + 2 * u) = make_float2(binm[0], binm[1]);
     }
+    if (MODE == MODE_FILTER) p.count[(long long)row * p.parts + part] = my_cnt;
   }
 
   tc_fence_before();
@@ -377,36 +382,46 @@ struct BinProvider {
 
 __global__ void __launch_bounds__(256)
 thr_kernel(const float* __restrict__ bin_top, int k, long long Q, long long Qp, const float* __restrict__ margin,
-           float* __restrict__ thr, unsigned int* __restrict__ count, unsigned int* __restrict__ overflow) {
+           float* __restrict__ thr, unsigned int* __restrict__ overflow) {
   long long row = (long long)blockIdx.x * 256 + threadIdx.x;
   if (row >= Qp) return;
-  count[row] = 0;
   if (row < Q) { thr[row] = bin_top[row * k + (k - 1)] - margin[row]; overflow[row] = 0; }
   else thr[row] = INFINITY;
 }
 
 __global__ void __launch_bounds__(256)
 tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus, int d, int k, long long index_offset,
-                   const unsigned int* __restrict__ count, const uint2* __restrict__ cand, const float* __restrict__ cut,
-                   unsigned int* __restrict__ overflow, float* __restrict__ out_s, long long* __restrict__ out_i) {
+                   const unsigned int* __restrict__ count, const uint2* __restrict__ cand, int parts, int cap_part,
+                   const float* __restrict__ cut, unsigned int* __restrict__ overflow, float* __restrict__ out_s,
+                   long long* __restrict__ out_i) {
   extern __shared__ __align__(16) unsigned char fsm[];
   long long* bi = reinterpret_cast<long long*>(fsm);                 // [CAND_CAP]
   float* bs = reinterpret_cast<float*>(fsm + (size_t)CAND_CAP * 8);  // [CAND_CAP]
   float* qs = bs + CAND_CAP;                                          // [d]
   __shared__ int m_sh;
   const int row = blockIdx.x, tid = threadIdx.x;
-  const unsigned int n_raw = count[row];
-  if (n_raw > (unsigned)CAND_CAP || n_raw < (unsigned)k) {  // overflow (or impossible underflow): exact fallback
+  // gather this query's per-part segments (all threads walk the same part loop: uniform control flow)
+  unsigned int n_raw = 0; bool part_ovf = false;
+  for (int pt = 0; pt < parts; ++pt) {
+    unsigned int c = count[(long long)row * parts + pt];
+    part_ovf |= c > (unsigned)cap_part;
+    n_raw += c;
+  }
+  if (part_ovf || n_raw > (unsigned)CAND_CAP || n_raw < (unsigned)k) {  // overflow (or impossible underflow): exact fallback
     if (tid == 0) overflow[row] = 1;
     return;
   }
   const int n = (int)n_raw;
   for (int t = tid; t < d; t += 256) qs[t] = q[(long long)row * d + t];
-  int P = 2; while (P < n) P <<= 1;
-  for (int t = tid; t < P; t += 256) {
-    if (t < n) { uint2 e = cand[(long long)row * CAND_CAP + t]; bs[t] = __uint_as_float(e.x); bi[t] = (long long)e.y; }
-    else { bs[t] = -INFINITY; bi[t] = LLONG_MAX; }
+  int base = 0;
+  for (int pt = 0; pt < parts; ++pt) {
+    const int c = (int)count[(long long)row * parts + pt];
+    const uint2* seg = cand + ((long long)row * parts + pt) * cap_part;
+    for (int t = tid; t < c; t += 256) { uint2 e = seg[t]; bs[base + t] = __uint_as_float(e.x); bi[base + t] = (long long)e.y; }
+    base += c;
   }
+  int P = 2; while (P < n) P <<= 1;
+  for (int t = n + tid; t < P; t += 256) { bs[t] = -INFINITY; bi[t] = LLONG_MAX; }
   if (tid == 0) m_sh = 0;
   __syncthreads();
   bitonic_sort_desc(bs, bi, P);  // by screening score
@@ -485,7 +500,7 @@ static void prof_mark(cudaStream_t st, int stage) {
 
 struct Plan {
   int kb, stages; long long n_tiles; int nqb; long long Qp;
-  int stride, n_sample, n_bins, bins_ld, parts_sample, parts_full;
+  int stride, n_sample, n_bins, bins_ld, parts_sample, parts_full, cap_part;
   size_t smem;
   // workspace offsets
   size_t o_qimg, o_margin, o_cut, o_thr, o_count, o_ovf, o_binmax, o_bintop_s, o_bintop_i, o_cand, total;
@@ -511,6 +526,11 @@ static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
   int parts = sms / pl.nqb; if (parts < 1) parts = 1;
   pl.parts_sample = parts < pl.n_sample ? parts : pl.n_sample;
   pl.parts_full = (long long)parts < pl.n_tiles ? parts : (int)pl.n_tiles;
+  {
+    int cp = 2 * CAND_CAP / pl.parts_full;  // segments add up to ~2x the per-query capacity
+    int p2 = 32; while (p2 * 2 <= cp && p2 < CAND_CAP) p2 <<= 1;
+    pl.cap_part = p2;
+  }
   pl.smem = (size_t)(2 + pl.stages) * pl.kb * SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 1024); return r; };
@@ -518,12 +538,12 @@ static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
   pl.o_margin = take((size_t)pl.Qp * 4);
   pl.o_cut = take((size_t)pl.Qp * 4);
   pl.o_thr = take((size_t)pl.Qp * 4);
-  pl.o_count = take((size_t)pl.Qp * 4);
+  pl.o_count = take((size_t)pl.Qp * pl.parts_full * 4);
   pl.o_ovf = take((size_t)pl.Qp * 4);
   pl.o_binmax = take((size_t)pl.Qp * pl.bins_ld * 4);
   pl.o_bintop_s = take((size_t)Q * k * 4);
   pl.o_bintop_i = take((size_t)Q * k * 8);
-  pl.o_cand = take((size_t)pl.Qp * CAND_CAP * 8);
+  pl.o_cand = take((size_t)pl.Qp * pl.parts_full * pl.cap_part * 8);
   pl.total = o;
   return true;
 }
@@ -631,7 +651,7 @@ extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, 
   }
   ScanParams sp{};
   sp.qimg = qimg; sp.cimg = cimg; sp.Q = Q; sp.N = N; sp.nqb = pl.nqb; sp.n_tiles = pl.n_tiles;
-  sp.binmax = binmax; sp.bins_ld = pl.bins_ld; sp.thr = thr; sp.count = count; sp.cand = cand;
+  sp.binmax = binmax; sp.bins_ld = pl.bins_ld; sp.thr = thr; sp.count = count; sp.cand = cand; sp.cap_part = pl.cap_part;
   prof_mark(st, 1);
   // (1) sampled pass -> bin maxima -> k-th largest -> threshold
   int rc = launch_scan_mode(pl, sp, st, MODE_SAMPLE);
@@ -643,7 +663,7 @@ extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, 
     if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(row_topk_kernel<BinProvider>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
     row_topk_kernel<BinProvider><<<(unsigned)Q, RS_THREADS, rowselect_smem(cap, 0), st>>>(bp, k, cap, bintop_s, bintop_i, k);
     TFRS_LAUNCH_CHECK();
-    thr_kernel<<<(unsigned)ceil_div(pl.Qp, 256), 256, 0, st>>>(bintop_s, k, Q, pl.Qp, margin, thr, count, ovf);
+    thr_kernel<<<(unsigned)ceil_div(pl.Qp, 256), 256, 0, st>>>(bintop_s, k, Q, pl.Qp, margin, thr, ovf);
     TFRS_LAUNCH_CHECK();
   }
   prof_mark(st, 2);
@@ -656,8 +676,8 @@ extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, 
     size_t smem = (size_t)CAND_CAP * 12 + (size_t)d * 4 + 16;
     static bool attr = false;
     if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
-    tc_finalize_kernel<<<(unsigned)Q, 256, smem, st>>>(q, corpus, d, k, index_offset, count, cand, cut, ovf, out_scores,
-                                                     (long long*)out_idx);
+    tc_finalize_kernel<<<(unsigned)Q, 256, smem, st>>>(q, corpus, d, k, index_offset, count, cand, pl.parts_full, pl.cap_part,
+                                                     cut, ovf, out_scores, (long long*)out_idx);
     TFRS_LAUNCH_CHECK();
   }
   // (4) exact fallback for overflowed queries (CTAs of non-flagged queries exit immediately)
