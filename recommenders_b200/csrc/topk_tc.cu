@@ -30,6 +30,7 @@
 // t's epilogue.  Each B tile feeds two MMAs (both A blocks): 16 KB of L2->smem traffic per 512
 // tensor-core cycles keeps the chip under the ~6.3 KB/clk L2 fabric limit.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "rowselect.cuh"
 
 namespace tfrs {
@@ -43,7 +44,6 @@ constexpr int SLAB_BYTES = TILE_N * 128;  // 16 KB: 128 rows x 128 B
 constexpr int HEADER_BYTES = 1024;
 constexpr int THREADS = 384;
 constexpr int EPI_WARP0 = 4;
-constexpr int BIN_COLS = 64;         // columns per threshold bin (2 bins per tile row)
 constexpr int CAND_CAP = 2048;       // survivors kept per query
 constexpr int MAX_SAMPLE_STRIDE = 4;
 constexpr float E_REL = 0.0083f;     // see header comment
@@ -198,7 +198,7 @@ qmargin_kernel(const float* __restrict__ q, long long Q, long long Qp, int d, co
 // ------------------------------------------------------------------------------------------------
 // the screening GEMM
 // ------------------------------------------------------------------------------------------------
-enum { MODE_SAMPLE = 0, MODE_FILTER = 1 };
+enum { MODE_SAMPLE = 0, MODE_FILTER = 1, MODE_DBG_LDONLY = 2, MODE_DBG_NOLD = 3 };  // 2,3: sample-pass experiments
 
 struct ScanParams {
   const unsigned char* qimg;    // query tile image  [2*nqb tiles][KB][16 KB]
@@ -316,12 +316,18 @@ tc_scan_kernel(const ScanParams p) {
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ab * 2 + buf) * TILE_N);
       float binm[2] = {-INFINITY, -INFINITY};
       uint32_t rbuf[2][32];
-      tmem_ld32(taddr, rbuf[0]);
-#pragma unroll
+      if (MODE != MODE_DBG_NOLD) tmem_ld32(taddr, rbuf[0]);
+#pragma unroll 2   // two chunk bodies (register buffers 0/1), executed twice: keeps the code inside the I-cache
       for (int c = 0; c < 4; ++c) {
         uint32_t (&r)[32] = rbuf[c & 1];
-        tmem_ld_wait(r);                                         // chunk c has landed
-        if (c < 3) tmem_ld32(taddr + (c + 1) * 32, rbuf[(c + 1) & 1]);  // prefetch chunk c+1 under the math
+        if (MODE != MODE_DBG_NOLD) {
+          tmem_ld_wait(r);                                         // chunk c has landed
+          if (c < 3) tmem_ld32(taddr + (c + 1) * 32, rbuf[(c + 1) & 1]);  // prefetch chunk c+1 under the math
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = (uint32_t)(it * 131 + j * 7 + c + lane);
+        }
+        if (MODE == MODE_DBG_LDONLY) { binm[c >> 1] = fmaxf(binm[c >> 1], __uint_as_float(r[0] ^ r[31])); continue; }
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -334,19 +340,21 @@ tc_scan_kernel(const ScanParams p) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = fmaxf(max3(v[4 * i], v[4 * i + 1], v[4 * i + 2]), v[4 * i + 3]);
         const float m = fmaxf(max3(g[0], g[1], g[2]), fmaxf(max3(g[3], g[4], g[5]), fmaxf(g[6], g[7])));
-        if (MODE == MODE_SAMPLE) {
+        if (MODE != MODE_FILTER) {
           binm[c >> 1] = fmaxf(binm[c >> 1], m);
         } else {
-          if (m >= thr) {  // rare: some lane of this warp has a survivor in these 32 columns
+          // Survivors are rare.  All branches below are WARP-UNIFORM (vote results), the per-lane work is a
+          // short predicated store: no divergence, and a hit costs ~40 instructions for the whole warp.
+          if (__any_sync(0xffffffffu, m >= thr)) {
+            const unsigned int idx0 = (unsigned int)(col0 + c * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              if (g[i] >= thr) {
+              if (__any_sync(0xffffffffu, g[i] >= thr)) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const float s = v[4 * i + j];
-                  if (s >= thr) {
-                    if (my_cnt < (unsigned)p.cap_part)
-                      my_list[my_cnt] = make_uint2(__float_as_uint(s), (unsigned int)(col0 + c * 32 + 4 * i + j));
+                  const float sc = v[4 * i + j];
+                  if (sc >= thr) {
+                    if (my_cnt < (unsigned)p.cap_part) my_list[my_cnt] = make_uint2(__float_as_uint(sc), idx0 + 4 * i + j);
                     ++my_cnt;
                   }
                 }
@@ -359,7 +367,7 @@ tc_scan_kernel(const ScanParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[buf]);
-      if (MODE == MODE_SAMPLE && row_ok)
+      if (MODE != MODE_FILTER && row_ok)
         *reinterpret_cast<float2*>(p.binmax + row * p.bins_ld + 2 * u) = make_float2(binm[0], binm[1]);
     }
     if (MODE == MODE_FILTER) p.count[(long long)row * p.parts + part] = my_cnt;
@@ -373,21 +381,75 @@ tc_scan_kernel(const ScanParams p) {
 // ------------------------------------------------------------------------------------------------
 // threshold from the bin maxima; finalize; fallback
 // ------------------------------------------------------------------------------------------------
-struct BinProvider {
-  const float* binmax; int bins_ld; int n_bins;
-  __device__ void begin(int, void*) {}
-  __device__ long long count(int) const { return n_bins; }
-  __device__ void get(int row, long long t, float& s, long long& i) const { s = binmax[(long long)row * bins_ld + t]; i = t; }
-};
-
-__global__ void __launch_bounds__(256)
-thr_kernel(const float* __restrict__ bin_top, int k, long long Q, long long Qp, const float* __restrict__ margin,
-           float* __restrict__ thr, unsigned int* __restrict__ overflow) {
-  long long row = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (row >= Qp) return;
-  if (row < Q) { thr[row] = bin_top[row * k + (k - 1)] - margin[row]; overflow[row] = 0; }
-  else thr[row] = INFINITY;
+// orderable key: larger float <=> larger unsigned (NaN sorts above +inf; -0 < +0 is harmless here)
+__device__ __forceinline__ unsigned int f2key(float f) {
+  unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+__device__ __forceinline__ float key2f(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// Block-wide k-th largest of n keys by 4 passes of 8-bit radix histograms (256 threads).
+// `key_at(i)` must be cheap and repeatable.  Returns the k-th largest key (1-based k <= n) to all threads.
+template <class KeyAt>
+__device__ unsigned int block_kth_largest(KeyAt key_at, int n, int k, unsigned int* hist /*[256] smem*/, unsigned int* bcast /*[2] smem*/) {
+  unsigned int prefix = 0, mask = 0;
+  int remaining = k;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) hist[t] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      unsigned int key = key_at(i);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      // lane l owns buckets [8l, 8l+8); walk from the top bucket down until `remaining` is covered
+      const int lane = threadIdx.x;
+      unsigned int loc[8], tot = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) { loc[b] = hist[lane * 8 + b]; tot += loc[b]; }
+      // suffix sum over lanes above
+      unsigned int above = 0;
+#pragma unroll
+      for (int l = 31; l >= 0; --l) {  // every lane executes every shuffle
+        const unsigned int tl = __shfl_sync(0xffffffffu, tot, l);
+        if (l > lane) above += tl;
+      }
+      unsigned int run = above;
+      int found = -1; unsigned int before = 0;
+#pragma unroll
+      for (int b = 7; b >= 0; --b) {
+        if (found < 0 && run + loc[b] >= (unsigned)remaining) { found = lane * 8 + b; before = run; }
+        run += loc[b];
+      }
+      const bool mine = (found >= 0) && (above < (unsigned)remaining);
+      if (mine) { bcast[0] = (unsigned int)found; bcast[1] = before; }
+    }
+    __syncthreads();
+    const unsigned int bucket = bcast[0];
+    remaining -= (int)bcast[1];
+    prefix |= bucket << shift;
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  return prefix;
+}
+
+// k-th largest bin maximum of the sampled pass -> filter threshold T = L - margin
+__global__ void __launch_bounds__(256)
+tc_threshold_kernel(const float* __restrict__ binmax, int bins_ld, int n_bins, int k, const float* __restrict__ margin,
+                    float* __restrict__ thr, unsigned int* __restrict__ overflow) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int bcast[2];
+  const int row = blockIdx.x;
+  const float* src = binmax + (long long)row * bins_ld;
+  const unsigned int kth = block_kth_largest([&](int i) { return f2key(__ldg(src + i)); }, n_bins, k, hist, bcast);
+  if (threadIdx.x == 0) { thr[row] = key2f(kth) - margin[row]; overflow[row] = 0; }
+}
+
+constexpr int FIN_MAXM = 1024;  // survivors re-scored exactly per query (band around tau)
 
 __global__ void __launch_bounds__(256)
 tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus, int d, int k, long long index_offset,
@@ -395,9 +457,13 @@ tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus
                    const float* __restrict__ cut, unsigned int* __restrict__ overflow, float* __restrict__ out_s,
                    long long* __restrict__ out_i) {
   extern __shared__ __align__(16) unsigned char fsm[];
-  long long* bi = reinterpret_cast<long long*>(fsm);                 // [CAND_CAP]
-  float* bs = reinterpret_cast<float*>(fsm + (size_t)CAND_CAP * 8);  // [CAND_CAP]
-  float* qs = bs + CAND_CAP;                                          // [d]
+  long long* ei = reinterpret_cast<long long*>(fsm);                       // [FIN_MAXM]  exact stage indices
+  float* es = reinterpret_cast<float*>(fsm + (size_t)FIN_MAXM * 8);         // [FIN_MAXM]  exact scores
+  float* as = es + FIN_MAXM;                                                // [CAND_CAP]  screening scores
+  unsigned int* ai = reinterpret_cast<unsigned int*>(as + CAND_CAP);        // [CAND_CAP]  local indices
+  float* qs = reinterpret_cast<float*>(ai + CAND_CAP);                      // [d]
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int bcast[2];
   __shared__ int m_sh;
   const int row = blockIdx.x, tid = threadIdx.x;
   // gather this query's per-part segments (all threads walk the same part loop: uniform control flow)
@@ -417,25 +483,29 @@ tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus
   for (int pt = 0; pt < parts; ++pt) {
     const int c = (int)count[(long long)row * parts + pt];
     const uint2* seg = cand + ((long long)row * parts + pt) * cap_part;
-    for (int t = tid; t < c; t += 256) { uint2 e = seg[t]; bs[base + t] = __uint_as_float(e.x); bi[base + t] = (long long)e.y; }
+    for (int t = tid; t < c; t += 256) { uint2 e = seg[t]; as[base + t] = __uint_as_float(e.x); ai[base + t] = e.y; }
     base += c;
   }
-  int P = 2; while (P < n) P <<= 1;
-  for (int t = n + tid; t < P; t += 256) { bs[t] = -INFINITY; bi[t] = LLONG_MAX; }
   if (tid == 0) m_sh = 0;
   __syncthreads();
-  bitonic_sort_desc(bs, bi, P);  // by screening score
-  // survivors inside the error band of tau = k-th best screening score
-  const float lim = bs[k - 1] - cut[row];
-  int local = 0;
-  for (int t = tid; t < n; t += 256) local += (bs[t] >= lim) ? 1 : 0;
-  if (local) atomicAdd(&m_sh, local);
+  // tau = k-th best screening score; keep the survivors inside its error band
+  const unsigned int tau_key = block_kth_largest([&](int i) { return f2key(as[i]); }, n, k, hist, bcast);
+  const float lim = key2f(tau_key) - cut[row];
+  for (int t = tid; t < n; t += 256) {
+    if (as[t] >= lim) {
+      int pos = atomicAdd(&m_sh, 1);
+      if (pos < FIN_MAXM) ei[pos] = (long long)ai[t];
+    }
+  }
   __syncthreads();
-  const int m = m_sh;  // sorted desc => exactly the first m entries
-  __syncthreads();
+  const int m = m_sh;
+  if (m > FIN_MAXM) {  // band too crowded (massive ties): exact fallback
+    if (tid == 0) overflow[row] = 1;
+    return;
+  }
   // exact re-scoring: the canonical sequential fmaf chain on the fp32 corpus
   for (int t = tid; t < m; t += 256) {
-    const float* c = corpus + bi[t] * d;
+    const float* c = corpus + ei[t] * d;
     float acc = 0.f;
     if ((d & 3) == 0) {
       for (int kk = 0; kk < d; kk += 4) {
@@ -446,16 +516,15 @@ tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus
     } else {
       for (int kk = 0; kk < d; ++kk) acc = fmaf(qs[kk], __ldg(c + kk), acc);
     }
-    bs[t] = acc;
+    es[t] = acc;
   }
   int P2 = 2; while (P2 < m) P2 <<= 1;
+  for (int t = m + tid; t < P2; t += 256) { es[t] = -INFINITY; ei[t] = LLONG_MAX; }
   __syncthreads();
-  for (int t = m + tid; t < P2; t += 256) { bs[t] = -INFINITY; bi[t] = LLONG_MAX; }
-  __syncthreads();
-  bitonic_sort_desc(bs, bi, P2);  // (exact score desc, index asc)
+  bitonic_sort_desc(es, ei, P2);  // (exact score desc, index asc)
   for (int t = tid; t < k; t += 256) {
-    out_s[(long long)row * k + t] = bs[t];
-    out_i[(long long)row * k + t] = bi[t] + index_offset;
+    out_s[(long long)row * k + t] = es[t];
+    out_i[(long long)row * k + t] = ei[t] + index_offset;
   }
 }
 
@@ -503,7 +572,7 @@ struct Plan {
   int stride, n_sample, n_bins, bins_ld, parts_sample, parts_full, cap_part;
   size_t smem;
   // workspace offsets
-  size_t o_qimg, o_margin, o_cut, o_thr, o_count, o_ovf, o_binmax, o_bintop_s, o_bintop_i, o_cand, total;
+  size_t o_qimg, o_margin, o_cut, o_thr, o_count, o_ovf, o_binmax, o_cand, total;
 };
 
 static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
@@ -541,8 +610,6 @@ static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
   pl.o_count = take((size_t)pl.Qp * pl.parts_full * 4);
   pl.o_ovf = take((size_t)pl.Qp * 4);
   pl.o_binmax = take((size_t)pl.Qp * pl.bins_ld * 4);
-  pl.o_bintop_s = take((size_t)Q * k * 4);
-  pl.o_bintop_i = take((size_t)Q * k * 8);
   pl.o_cand = take((size_t)pl.Qp * pl.parts_full * pl.cap_part * 8);
   pl.total = o;
   return true;
@@ -560,6 +627,17 @@ static int launch_scans(const Plan& pl, ScanParams sp, cudaStream_t st, int mode
   }
   if (mode == MODE_SAMPLE) {
     sp.parts = pl.parts_sample; sp.n_seq = pl.n_sample; sp.stride = pl.stride;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("TFRS_TC_DEBUG_MODE"); dbg = e ? atoi(e) : 0; }
+    if (dbg == 2) {
+      auto k2 = tc_scan_kernel<KB, STAGES, MODE_DBG_LDONLY>;
+      TFRS_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+      k2<<<(unsigned)(pl.nqb * sp.parts), THREADS, pl.smem, st>>>(sp);
+    } else if (dbg == 3) {
+      auto k3 = tc_scan_kernel<KB, STAGES, MODE_DBG_NOLD>;
+      TFRS_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+      k3<<<(unsigned)(pl.nqb * sp.parts), THREADS, pl.smem, st>>>(sp);
+    } else
     ks<<<(unsigned)(pl.nqb * sp.parts), THREADS, pl.smem, st>>>(sp);
   } else {
     sp.parts = pl.parts_full; sp.n_seq = (int)pl.n_tiles; sp.stride = 1;
@@ -634,8 +712,6 @@ extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, 
   unsigned int* count = (unsigned int*)(w + pl.o_count);
   unsigned int* ovf = (unsigned int*)(w + pl.o_ovf);
   float* binmax = (float*)(w + pl.o_binmax);
-  float* bintop_s = (float*)(w + pl.o_bintop_s);
-  long long* bintop_i = (long long*)(w + pl.o_bintop_i);
   uint2* cand = (uint2*)(w + pl.o_cand);
   const IndexHeader* hdr = (const IndexHeader*)index_buf;
   const unsigned char* cimg = (const unsigned char*)index_buf + HEADER_BYTES;
@@ -656,16 +732,8 @@ extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, 
   // (1) sampled pass -> bin maxima -> k-th largest -> threshold
   int rc = launch_scan_mode(pl, sp, st, MODE_SAMPLE);
   if (rc) return rc;
-  {
-    BinProvider bp{binmax, pl.bins_ld, pl.n_bins};
-    int cap = rowselect_cap(k);
-    static bool attr = false;
-    if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(row_topk_kernel<BinProvider>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
-    row_topk_kernel<BinProvider><<<(unsigned)Q, RS_THREADS, rowselect_smem(cap, 0), st>>>(bp, k, cap, bintop_s, bintop_i, k);
-    TFRS_LAUNCH_CHECK();
-    thr_kernel<<<(unsigned)ceil_div(pl.Qp, 256), 256, 0, st>>>(bintop_s, k, Q, pl.Qp, margin, thr, ovf);
-    TFRS_LAUNCH_CHECK();
-  }
+  tc_threshold_kernel<<<(unsigned)Q, 256, 0, st>>>(binmax, pl.bins_ld, pl.n_bins, k, margin, thr, ovf);
+  TFRS_LAUNCH_CHECK();
   prof_mark(st, 2);
   // (2) full pass with the fused threshold filter
   rc = launch_scan_mode(pl, sp, st, MODE_FILTER);
@@ -673,7 +741,7 @@ extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, 
   prof_mark(st, 3);
   // (3) exact re-scoring + final order
   {
-    size_t smem = (size_t)CAND_CAP * 12 + (size_t)d * 4 + 16;
+    size_t smem = (size_t)FIN_MAXM * 12 + (size_t)CAND_CAP * 8 + (size_t)d * 4 + 16;
     static bool attr = false;
     if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
     tc_finalize_kernel<<<(unsigned)Q, 256, smem, st>>>(q, corpus, d, k, index_offset, count, cand, pl.parts_full, pl.cap_part,

@@ -282,8 +282,8 @@ def test_two_tower_model_trains(tfrs):
   ut = model.user_model.weight.cpu().numpy().copy(); it = model.item_model.weight.cpu().numpy().copy()
   ua = np.full_like(ut, 0.1); ia = np.full_like(it, 0.1)
   losses = []
-  for step in range(3):
-    uid = rng.randint(0, U, size=B).astype(np.int64); iid = rng.randint(0, I, size=B).astype(np.int64)
+  uid = rng.randint(0, U, size=B).astype(np.int64); iid = rng.randint(0, I, size=B).astype(np.int64)
+  for step in range(3):  # the same batch three times: the loss must fall
     out = model.train_step({"user_id": cu(uid), "movie_id": cu(iid)})
     assert set(out) >= {"loss", "regularization_loss", "total_loss"}
     losses.append(float(out["loss"]))
