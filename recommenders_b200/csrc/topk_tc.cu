@@ -304,13 +304,13 @@ tc_scan_kernel(const ScanParams p) {
     uint2* my_list = nullptr;
     unsigned int my_cnt = 0;
     if (MODE == MODE_FILTER) my_list = p.cand + ((long long)row * p.parts + part) * p.cap_part;
+    const unsigned int cap = (unsigned int)p.cap_part;
     for (int it = 0; it < n_iter; ++it) {
       const int buf = it & 1;
       const uint32_t tphase = (it >> 1) & 1;
       const int u = u_begin + it;
       const long long tile = (long long)u * p.stride;
-      const long long col0 = tile * TILE_N;
-      const int n_valid = (int)min((long long)TILE_N, p.N - col0);  // < 128 only on the last tile
+      const long long col0 = tile * TILE_N;  // zero-padded rows of the last tile score 0: dropped in finalize (idx >= N)
       mbar_wait(&t_full[buf], tphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ab * 2 + buf) * TILE_N);
@@ -331,10 +331,6 @@ tc_scan_kernel(const ScanParams p) {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (n_valid < TILE_N) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (c * 32 + j >= n_valid) v[j] = -INFINITY;
-        }
         // 8 group maxima of 4, then their max
         float g[8];
 #pragma unroll
@@ -343,20 +339,23 @@ tc_scan_kernel(const ScanParams p) {
         if (MODE != MODE_FILTER) {
           binm[c >> 1] = fmaxf(binm[c >> 1], m);
         } else {
-          // Survivors are rare.  All branches below are WARP-UNIFORM (vote results), the per-lane work is a
-          // short predicated store: no divergence, and a hit costs ~40 instructions for the whole warp.
+          // Survivors are rare.  Every branch below is WARP-UNIFORM: one vote on the chunk max, then one
+          // REDUX.OR of the per-lane 8-bit group mask; the per-lane work is predicated stores only.
           if (__any_sync(0xffffffffu, m >= thr)) {
+            unsigned int gmask = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gmask |= (g[i] >= thr) ? (1u << i) : 0u;
+            const unsigned int umask = __reduce_or_sync(0xffffffffu, gmask);
             const unsigned int idx0 = (unsigned int)(col0 + c * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              if (__any_sync(0xffffffffu, g[i] >= thr)) {
+              if (umask & (1u << i)) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float sc = v[4 * i + j];
-                  if (sc >= thr) {
-                    if (my_cnt < (unsigned)p.cap_part) my_list[my_cnt] = make_uint2(__float_as_uint(sc), idx0 + 4 * i + j);
-                    ++my_cnt;
-                  }
+                  const bool hit = sc >= thr;
+                  if (hit && my_cnt < cap) my_list[my_cnt] = make_uint2(__float_as_uint(sc), idx0 + 4 * i + j);
+                  my_cnt += hit ? 1u : 0u;
                 }
               }
             }
@@ -454,8 +453,8 @@ constexpr int FIN_MAXM = 1024;  // survivors re-scored exactly per query (band a
 __global__ void __launch_bounds__(256)
 tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus, int d, int k, long long index_offset,
                    const unsigned int* __restrict__ count, const uint2* __restrict__ cand, int parts, int cap_part,
-                   const float* __restrict__ cut, unsigned int* __restrict__ overflow, float* __restrict__ out_s,
-                   long long* __restrict__ out_i) {
+                   const float* __restrict__ cut, const float* __restrict__ thr, long long N,
+                   unsigned int* __restrict__ overflow, float* __restrict__ out_s, long long* __restrict__ out_i) {
   extern __shared__ __align__(16) unsigned char fsm[];
   long long* ei = reinterpret_cast<long long*>(fsm);                       // [FIN_MAXM]  exact stage indices
   float* es = reinterpret_cast<float*>(fsm + (size_t)FIN_MAXM * 8);         // [FIN_MAXM]  exact scores
@@ -483,7 +482,12 @@ tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus
   for (int pt = 0; pt < parts; ++pt) {
     const int c = (int)count[(long long)row * parts + pt];
     const uint2* seg = cand + ((long long)row * parts + pt) * cap_part;
-    for (int t = tid; t < c; t += 256) { uint2 e = seg[t]; as[base + t] = __uint_as_float(e.x); ai[base + t] = e.y; }
+    for (int t = tid; t < c; t += 256) {
+      uint2 e = seg[t];
+      // rows of the zero-padded last tile are not candidates: sink them below everything
+      as[base + t] = (e.y < (unsigned long long)N) ? __uint_as_float(e.x) : -INFINITY;
+      ai[base + t] = e.y;
+    }
     base += c;
   }
   if (tid == 0) m_sh = 0;
@@ -491,6 +495,12 @@ tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus
   // tau = k-th best screening score; keep the survivors inside its error band
   const unsigned int tau_key = block_kth_largest([&](int i) { return f2key(as[i]); }, n, k, hist, bcast);
   const float lim = key2f(tau_key) - cut[row];
+  // Self-check that makes the threshold choice a pure performance matter: the whole band [lim, inf) must
+  // lie above the filter threshold, otherwise survivors could be missing -> exact fallback.
+  if (!(lim >= thr[row]) || !(lim > -INFINITY)) {
+    if (tid == 0) overflow[row] = 1;
+    return;
+  }
   for (int t = tid; t < n; t += 256) {
     if (as[t] >= lim) {
       int pos = atomicAdd(&m_sh, 1);
@@ -585,9 +595,11 @@ static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
   if (pl.kb > 2) return false;          // d > 128: smem budget (A blocks + ring) not laid out yet
   if (k > 512 || N >= (1ll << 31)) return false;
   // sample every stride-th tile; keep at least 4k bins so the k-th largest bin max is a tight bound
+  const long long full_tiles = N / TILE_N;  // the zero-padded last tile is never sampled (its 0 scores are not candidates)
+  if (full_tiles < 1) return false;
   pl.stride = MAX_SAMPLE_STRIDE;
-  while (pl.stride > 1 && 2 * ceil_div(pl.n_tiles, pl.stride) < 4ll * k) pl.stride >>= 1;
-  pl.n_sample = (int)ceil_div(pl.n_tiles, pl.stride);
+  while (pl.stride > 1 && 2 * ceil_div(full_tiles, pl.stride) < 4ll * k) pl.stride >>= 1;
+  pl.n_sample = (int)ceil_div(full_tiles, pl.stride);
   pl.n_bins = pl.n_sample * 2;
   pl.bins_ld = (pl.n_bins + 3) / 4 * 4;
   if (pl.n_bins < 4 * k) return false;  // too few bins for a useful threshold -> caller uses the exact path
@@ -745,7 +757,7 @@ extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, 
     static bool attr = false;
     if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
     tc_finalize_kernel<<<(unsigned)Q, 256, smem, st>>>(q, corpus, d, k, index_offset, count, cand, pl.parts_full, pl.cap_part,
-                                                     cut, ovf, out_scores, (long long*)out_idx);
+                                                     cut, thr, N, ovf, out_scores, (long long*)out_idx);
     TFRS_LAUNCH_CHECK();
   }
   // (4) exact fallback for overflowed queries (CTAs of non-flagged queries exit immediately)
