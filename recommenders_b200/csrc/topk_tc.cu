@@ -3,9 +3,9 @@
 // Replaces  scores = matmul(q, c^T); top_k(scores, k)  (layers/factorized_top_k.py:603-605) for large
 // corpora.  The [Q,N] score matrix never exists in HBM:
 //
-//   index time   tfrs_index_build : corpus fp32 -> bf16 image, pre-tiled as 128-row UMMA SWIZZLE_128B
-//                K-major tiles (one contiguous 16 KB block per 64-wide K slab), + max row norm.
-//   query time   (0) tc_qprep    : queries -> the same bf16 tile image; per-query error margin
+//   index time   tfrs_index_build : corpus fp32 -> fp16 image (exact 2^e rescale), pre-tiled as 128-row UMMA SWIZZLE_128B
+//                K-major tiles (one contiguous 16 KB block per 64-wide K slab), + max row norm / max |element|.
+//   query time   (0) q stats/image: queries -> the same fp16 tile image; per-query error margin
 //                (1) tc_scan<SAMPLE> : screening GEMM over every 4th corpus tile; epilogue keeps only the
 //                    per-(query, 64-column bin) max  -> K-th largest bin max = a valid lower bound L_q of
 //                    the K-th best screening score (K distinct bins hold K distinct candidates >= it)
@@ -17,19 +17,19 @@
 //                    sorted by (score desc, index asc) -> bit-identical to the exact CUDA-core path.
 //                (4) overflow fallback (list capacity exceeded; adversarial inputs only): exact scan.
 //
-// Why the result is exact: |screen(q,c) - exact(q,c)| <= eps_q = E_REL*|q|*max|c| (bf16 rounding of both
-// operands: (2u+u^2) sum|q_k c_k| with u = 2^-8, plus accumulation slack; Cauchy-Schwarz).  Any member
+// Why the result is exact: |screen(q,c) - exact(q,c)| <= eps_q = E_REL*|q|*max|c| (fp16 rounding of both
+// operands: (2u+u^2) sum|q_k c_k| with u = 2^-11, plus accumulation slack; Cauchy-Schwarz).  Any member
 // of the exact top-K has screening score >= tau - 2*eps_q >= L_q - 2*eps_q, so it is in the list and in
 // the re-scored band.
 //
 // Kernel shape (per CTA, 1 CTA / SM, 384 threads): 256 queries (two 128-row A blocks, resident in smem)
 // x a contiguous range of 128-row corpus tiles streamed through a 4-6 stage bulk-TMA ring; warp 0 = TMA
-// producer, warp 1 = MMA issuer (one thread, tcgen05.mma M=128 N=128 K=16, bf16 -> fp32 in TMEM),
+// producer, warp 1 = MMA issuer (one thread, tcgen05.mma M=128 N=128 K=16, fp16 -> fp32 in TMEM),
 // warp 2 = TMEM allocator, warps 4-11 = epilogue (one query row per thread, tcgen05.ld 32x32b.x32).
 // TMEM holds 2 A-blocks x 2 buffers x 128 columns = all 512 columns, so tile t+1's MMAs overlap tile
 // t's epilogue.  Each B tile feeds two MMAs (both A blocks): 16 KB of L2->smem traffic per 512
 // tensor-core cycles keeps the chip under the ~6.3 KB/clk L2 fabric limit.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "rowselect.cuh"
 
@@ -39,19 +39,30 @@ namespace tc {
 constexpr int TILE_N = 128;          // corpus rows per B tile
 constexpr int TILE_M = 128;          // query rows per A block
 constexpr int QBLK = 256;            // queries per CTA (2 A blocks)
-constexpr int KSLAB = 64;            // bf16 elements per 128-byte swizzle row
+constexpr int KSLAB = 64;            // fp16 elements per 128-byte swizzle row
 constexpr int SLAB_BYTES = TILE_N * 128;  // 16 KB: 128 rows x 128 B
 constexpr int HEADER_BYTES = 1024;
 constexpr int THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int CAND_CAP = 2048;       // survivors kept per query
 constexpr int MAX_SAMPLE_STRIDE = 4;
-constexpr float E_REL = 0.0083f;     // see header comment
-constexpr float E_ACC = 0.0010f;     // run-to-run accumulation slack between the two passes
+// Screening error model (operands: fp16 after an exact power-of-two rescale of each side so that the
+// largest magnitude lands in [2^14, 2^15); accumulate: fp32 in TMEM):
+//   |x^ - x| <= 2^-11 |x| (+2^-25 absolute below the fp16 normal range, negligible after the rescale)
+//   => |screen - exact| <= (2^-10 + 2^-22) sum|q_k c_k|  + accumulation slack (budget 2^-14) + fmaf-chain 2^-16
+//   <= E_REL * |q| * |c|   (Cauchy-Schwarz), E_REL = 0.00108 including the 0.1 % norm inflation.
+constexpr float E_REL = 0.00108f;
+constexpr float E_ACC = 0.00013f;    // run-to-run slack between the two passes (they are bit-identical in practice)
 
+struct SideStats {              // per operand side (corpus at index time, queries per call)
+  unsigned int max_norm2_bits;  // max_i |x_i|^2   (float bits; non-negative so uint order == float order)
+  unsigned int amax_bits;       // max_ij |x_ij|
+  int exp;                      // rescale exponent e: x * 2^e has its largest magnitude in [2^14, 2^15)
+  int pad;
+};
 struct IndexHeader {
-  unsigned int max_norm2_bits;  // max_i |c_i|^2 (float bits; non-negative so uint order == float order)
-  int d, d_pad, kb;
+  SideStats st;
+  int d, d_pad, kb, pad;
   long long n, n_tiles;
 };
 
@@ -96,8 +107,8 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, M=128, N=128, K=16
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate, M=128, N=128, K=16
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -105,25 +116,38 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+// 64 consecutive fp32 accumulator columns of this thread's row (TMEM lane) -> 64 registers
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+        "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+        "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
+        "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
+        "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
       : "r"(taddr));
 }
-// tcgen05.wait::ld, with the 32 destination registers threaded through as in/out operands so the
-// compiler cannot schedule a use of the loaded values above the wait.
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+// tcgen05.wait::ld.  The loaded registers are threaded through as in/out operands (in two statements:
+// inline asm has an operand limit) so the compiler cannot schedule a use of the values above the wait.
+__device__ __forceinline__ void tmem_ld_wait64(uint32_t (&r)[64]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
                  "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
                  "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
                  "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+  asm volatile(""
+               : "+r"(r[32]), "+r"(r[33]), "+r"(r[34]), "+r"(r[35]), "+r"(r[36]), "+r"(r[37]), "+r"(r[38]), "+r"(r[39]),
+                 "+r"(r[40]), "+r"(r[41]), "+r"(r[42]), "+r"(r[43]), "+r"(r[44]), "+r"(r[45]), "+r"(r[46]), "+r"(r[47]),
+                 "+r"(r[48]), "+r"(r[49]), "+r"(r[50]), "+r"(r[51]), "+r"(r[52]), "+r"(r[53]), "+r"(r[54]), "+r"(r[55]),
+                 "+r"(r[56]), "+r"(r[57]), "+r"(r[58]), "+r"(r[59]), "+r"(r[60]), "+r"(r[61]), "+r"(r[62]), "+r"(r[63])
                :: "memory");
 }
 
@@ -131,18 +155,19 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both, N=128, M=128
-constexpr uint32_t IDESC_BF16_M128_N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: D=f32 (bits 4-5 = 1), A=B=f16 (bits 7-9, 10-12 = 0), K-major both, N=128, M=128
+constexpr uint32_t IDESC_F16_M128_N128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
 // ------------------------------------------------------------------------------------------------
-// image builders: fp32 [rows, d] -> bf16 128-row tiles, each K slab of 64 as one swizzled 16 KB block
+// image builders: fp32 [rows, d] -> fp16 128-row tiles, each K slab of 64 as one swizzled 16 KB block
 //   byte offset of element (r, k) inside a tile = (k/64)*16384 + r*128 + (((k%64)/8) ^ (r%8))*16 + (k%8)*2
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 tile_image_kernel(const float* __restrict__ src, long long rows, int d, int kb, long long n_tiles,
-                  unsigned char* __restrict__ img) {
+                  const SideStats* __restrict__ st, unsigned char* __restrict__ img) {
+  const int e = st->exp;
   const long long total = n_tiles * TILE_N * (long long)kb * 8;  // 16-byte chunks
   for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
     int chunk = (int)(e % (kb * 8));
@@ -151,36 +176,51 @@ tile_image_kernel(const float* __restrict__ src, long long rows, int d, int kb, 
     int r = (int)(row % TILE_N);
     long long tile = row / TILE_N;
     int k0 = slab * KSLAB + cj * 8;
-    __align__(16) __nv_bfloat16 v[8];
+    __align__(16) __half v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float f = (row < rows && k0 + j < d) ? src[row * d + k0 + j] : 0.f;
-      v[j] = __float2bfloat16_rn(f);
+      v[j] = __float2half_rn(ldexpf(f, e));  // exact power-of-two rescale, then one rounding to fp16
     }
     unsigned char* dst = img + tile * ((long long)kb * SLAB_BYTES) + (long long)slab * SLAB_BYTES + r * 128 + ((cj ^ (r & 7)) * 16);
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
   }
 }
 
+// max row norm^2 and max |element| of a [rows, d] matrix (one warp per row -> coalesced)
 __global__ void __launch_bounds__(256)
-max_norm_kernel(const float* __restrict__ src, long long rows, int d, unsigned int* __restrict__ max_bits) {
-  long long row = (long long)blockIdx.x * 256 + threadIdx.x;
-  float n2 = 0.f;
-  if (row < rows) {
+side_stats_kernel(const float* __restrict__ src, long long rows, int d, SideStats* __restrict__ st) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * 256) >> 5;
+  float best_n2 = 0.f, best_a = 0.f;
+  for (long long row = warp; row < rows; row += nwarps) {
     const float* p = src + row * d;
-    for (int k = 0; k < d; ++k) n2 = fmaf(p[k], p[k], n2);
-  }
+    float n2 = 0.f, a = 0.f;
+    for (int k = lane; k < d; k += 32) { float x = p[k]; n2 = fmaf(x, x, n2); a = fmaxf(a, fabsf(x)); }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) n2 = fmaxf(n2, __shfl_xor_sync(0xffffffffu, n2, o));
-  if ((threadIdx.x & 31) == 0 && n2 > 0.f) atomicMax(max_bits, __float_as_uint(n2));
+    for (int o = 16; o > 0; o >>= 1) { n2 += __shfl_xor_sync(0xffffffffu, n2, o); a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o)); }
+    best_n2 = fmaxf(best_n2, n2); best_a = fmaxf(best_a, a);
+  }
+  if (lane == 0) {
+    if (best_n2 > 0.f) atomicMax(&st->max_norm2_bits, __float_as_uint(best_n2 * 1.0001f));  // slack for the tree order
+    if (best_a > 0.f) atomicMax(&st->amax_bits, __float_as_uint(best_a));
+  }
+}
+__global__ void side_exp_kernel(SideStats* st) {
+  const float amax = __uint_as_float(st->amax_bits);
+  int x = 0;
+  if (amax > 0.f && amax < INFINITY) (void)frexpf(amax, &x);  // amax = m * 2^x, m in [0.5, 1)
+  st->exp = (amax > 0.f && amax < INFINITY) ? (15 - x) : 0;      // amax * 2^exp in [2^14, 2^15)
 }
 
 __global__ void header_kernel(IndexHeader* dst, IndexHeader h) { *dst = h; }
 
-// per-query margins from |q| and the corpus max norm
+// per-query margins from |q| and the corpus max norm, expressed in SCREENING units (scores scaled by
+// 2^(exp_q + exp_c), an exact power of two)
 __global__ void __launch_bounds__(256)
 qmargin_kernel(const float* __restrict__ q, long long Q, long long Qp, int d, const IndexHeader* __restrict__ hdr,
-               float* __restrict__ margin, float* __restrict__ cut) {
+               const SideStats* __restrict__ qst, float* __restrict__ margin, float* __restrict__ cut) {
   long long row = (long long)blockIdx.x * 256 + threadIdx.x;
   if (row >= Qp) return;
   float n2 = 0.f;
@@ -188,10 +228,11 @@ qmargin_kernel(const float* __restrict__ q, long long Q, long long Qp, int d, co
     const float* p = q + row * d;
     for (int k = 0; k < d; ++k) n2 = fmaf(p[k], p[k], n2);
   }
-  float cn = sqrtf(__uint_as_float(hdr->max_norm2_bits)) * 1.001f;
-  float qn = sqrtf(n2) * 1.001f;
-  float e = E_REL * qn * cn + 1e-30f;
-  margin[row] = 2.f * e + E_ACC * qn * cn;
+  const float cn = sqrtf(__uint_as_float(hdr->st.max_norm2_bits)) * 1.001f;
+  const float qn = sqrtf(n2) * 1.001f;
+  const int se = hdr->st.exp + qst->exp;
+  const float e = ldexpf(E_REL * qn * cn, se) + 1e-30f;
+  margin[row] = 2.f * e + ldexpf(E_ACC * qn * cn, se);
   cut[row] = 2.f * e;
 }
 
@@ -283,8 +324,8 @@ tc_scan_kernel(const ScanParams p) {
             const uint64_t a_desc = make_smem_desc(smem_u32(sA + (ab * KB + kb) * SLAB_BYTES));
             const uint64_t b_desc = make_smem_desc(smem_u32(sB + (stage * KB + kb) * SLAB_BYTES));
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)  // 4 x (K=16 bf16 = 32 B) inside the 128-byte swizzle row
-              umma_bf16(d_tmem, a_desc + (uint64_t)(k4 * 2), b_desc + (uint64_t)(k4 * 2), IDESC_BF16_M128_N128,
+            for (int k4 = 0; k4 < 4; ++k4)  // 4 x (K=16 fp16 = 32 B) inside the 128-byte swizzle row
+              umma_f16(d_tmem, a_desc + (uint64_t)(k4 * 2), b_desc + (uint64_t)(k4 * 2), IDESC_F16_M128_N128,
                         (uint32_t)((kb | k4) != 0));
           }
         }
@@ -315,57 +356,60 @@ tc_scan_kernel(const ScanParams p) {
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ab * 2 + buf) * TILE_N);
       float binm[2] = {-INFINITY, -INFINITY};
-      uint32_t rbuf[2][32];
-      if (MODE != MODE_DBG_NOLD) tmem_ld32(taddr, rbuf[0]);
-#pragma unroll 2   // two chunk bodies (register buffers 0/1), executed twice: keeps the code inside the I-cache
-      for (int c = 0; c < 4; ++c) {
-        uint32_t (&r)[32] = rbuf[c & 1];
+#pragma unroll 1   // two halves of 64 columns; one body in the I-cache
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r[64];
         if (MODE != MODE_DBG_NOLD) {
-          tmem_ld_wait(r);                                         // chunk c has landed
-          if (c < 3) tmem_ld32(taddr + (c + 1) * 32, rbuf[(c + 1) & 1]);  // prefetch chunk c+1 under the math
+          tmem_ld64(taddr + h * 64, r);
+          tmem_ld_wait64(r);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = (uint32_t)(it * 131 + j * 7 + c + lane);
+          for (int j = 0; j < 64; ++j) r[j] = (uint32_t)(it * 131 + j * 7 + h + lane);
         }
-        if (MODE == MODE_DBG_LDONLY) { binm[c >> 1] = fmaxf(binm[c >> 1], __uint_as_float(r[0] ^ r[31])); continue; }
-        float v[32];
+        if (h == 1) {
+          // every TMEM read of this accumulator buffer has completed: hand it back to the MMA warp before the math
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[buf]);
+        }
+        if (MODE == MODE_DBG_LDONLY) { binm[h] = fmaxf(binm[h], __uint_as_float(r[0] ^ r[63])); continue; }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        // 8 group maxima of 4, then their max
-        float g[8];
+        for (int c2 = 0; c2 < 2; ++c2) {
+          float v[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = fmaxf(max3(v[4 * i], v[4 * i + 1], v[4 * i + 2]), v[4 * i + 3]);
-        const float m = fmaxf(max3(g[0], g[1], g[2]), fmaxf(max3(g[3], g[4], g[5]), fmaxf(g[6], g[7])));
-        if (MODE != MODE_FILTER) {
-          binm[c >> 1] = fmaxf(binm[c >> 1], m);
-        } else {
-          // Survivors are rare.  Every branch below is WARP-UNIFORM: one vote on the chunk max, then one
-          // REDUX.OR of the per-lane 8-bit group mask; the per-lane work is predicated stores only.
-          if (__any_sync(0xffffffffu, m >= thr)) {
-            unsigned int gmask = 0;
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c2 * 32 + j]);
+          // 8 group maxima of 4, then their max
+          float g[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) gmask |= (g[i] >= thr) ? (1u << i) : 0u;
-            const unsigned int umask = __reduce_or_sync(0xffffffffu, gmask);
-            const unsigned int idx0 = (unsigned int)(col0 + c * 32);
+          for (int i = 0; i < 8; ++i) g[i] = fmaxf(max3(v[4 * i], v[4 * i + 1], v[4 * i + 2]), v[4 * i + 3]);
+          const float m = fmaxf(max3(g[0], g[1], g[2]), fmaxf(max3(g[3], g[4], g[5]), fmaxf(g[6], g[7])));
+          if (MODE != MODE_FILTER) {
+            binm[h] = fmaxf(binm[h], m);
+          } else {
+            // Survivors are rare.  Every branch below is WARP-UNIFORM: one vote on the chunk max, then one
+            // REDUX.OR of the per-lane 8-bit group mask; the per-lane work is predicated stores only.
+            if (__any_sync(0xffffffffu, m >= thr)) {
+              unsigned int gmask = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (umask & (1u << i)) {
+              for (int i = 0; i < 8; ++i) gmask |= (g[i] >= thr) ? (1u << i) : 0u;
+              const unsigned int umask = __reduce_or_sync(0xffffffffu, gmask);
+              const unsigned int idx0 = (unsigned int)(col0 + h * 64 + c2 * 32);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float sc = v[4 * i + j];
-                  const bool hit = sc >= thr;
-                  if (hit && my_cnt < cap) my_list[my_cnt] = make_uint2(__float_as_uint(sc), idx0 + 4 * i + j);
-                  my_cnt += hit ? 1u : 0u;
+              for (int i = 0; i < 8; ++i) {
+                if (umask & (1u << i)) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float sc = v[4 * i + j];
+                    const bool hit = sc >= thr;
+                    if (hit && my_cnt < cap) my_list[my_cnt] = make_uint2(__float_as_uint(sc), idx0 + 4 * i + j);
+                    my_cnt += hit ? 1u : 0u;
+                  }
                 }
               }
             }
           }
         }
       }
-      // all TMEM reads of this buffer are complete (wait::ld above): hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[buf]);
       if (MODE != MODE_FILTER && row_ok)
         *reinterpret_cast<float2*>(p.binmax + row * p.bins_ld + 2 * u) = make_float2(binm[0], binm[1]);
     }
@@ -582,7 +626,7 @@ struct Plan {
   int stride, n_sample, n_bins, bins_ld, parts_sample, parts_full, cap_part;
   size_t smem;
   // workspace offsets
-  size_t o_qimg, o_margin, o_cut, o_thr, o_count, o_ovf, o_binmax, o_cand, total;
+  size_t o_qstats, o_qimg, o_margin, o_cut, o_thr, o_count, o_ovf, o_binmax, o_cand, total;
 };
 
 static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
@@ -615,6 +659,7 @@ static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
   pl.smem = (size_t)(2 + pl.stages) * pl.kb * SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 1024); return r; };
+  pl.o_qstats = take(sizeof(SideStats));
   pl.o_qimg = take((size_t)pl.nqb * 2 * pl.kb * SLAB_BYTES);
   pl.o_margin = take((size_t)pl.Qp * 4);
   pl.o_cut = take((size_t)pl.Qp * 4);
@@ -684,15 +729,17 @@ extern "C" int tfrs_index_build(const float* corpus, int64_t N, int d, void* ind
   cudaStream_t st = (cudaStream_t)stream;
   IndexHeader h{};
   h.d = d; h.kb = (d + KSLAB - 1) / KSLAB; h.d_pad = h.kb * KSLAB; h.n = N; h.n_tiles = ceil_div(N, TILE_N);
-  h.max_norm2_bits = 0;
   TFRS_CUDA(cudaMemsetAsync(index_buf, 0, HEADER_BYTES, st));
   header_kernel<<<1, 1, 0, st>>>(reinterpret_cast<IndexHeader*>(index_buf), h);
   TFRS_LAUNCH_CHECK();
-  max_norm_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(corpus, N, d, reinterpret_cast<unsigned int*>(index_buf));
+  SideStats* cst = &reinterpret_cast<IndexHeader*>(index_buf)->st;
+  side_stats_kernel<<<(unsigned)(148 * 8), 256, 0, st>>>(corpus, N, d, cst);
+  TFRS_LAUNCH_CHECK();
+  side_exp_kernel<<<1, 1, 0, st>>>(cst);
   TFRS_LAUNCH_CHECK();
   long long chunks = h.n_tiles * TILE_N * (long long)h.kb * 8;
   unsigned blocks = (unsigned)(ceil_div(chunks, 256) < (1 << 20) ? ceil_div(chunks, 256) : (1 << 20));
-  tile_image_kernel<<<blocks, 256, 0, st>>>(corpus, N, d, h.kb, h.n_tiles, (unsigned char*)index_buf + HEADER_BYTES);
+  tile_image_kernel<<<blocks, 256, 0, st>>>(corpus, N, d, h.kb, h.n_tiles, cst, (unsigned char*)index_buf + HEADER_BYTES);
   TFRS_LAUNCH_CHECK();
   return TFRS_OK;
 }
@@ -729,12 +776,18 @@ extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, 
   const unsigned char* cimg = (const unsigned char*)index_buf + HEADER_BYTES;
 
   prof_mark(st, 0);
-  // (0) query image + margins
+  // (0) query statistics, image and margins
   {
-    long long chunks = (long long)pl.nqb * 2 * TILE_N * pl.kb * 8;
-    tile_image_kernel<<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(q, Q, d, pl.kb, (long long)pl.nqb * 2, qimg);
+    SideStats* qst = (SideStats*)(w + pl.o_qstats);
+    TFRS_CUDA(cudaMemsetAsync(qst, 0, sizeof(SideStats), st));
+    side_stats_kernel<<<(unsigned)ceil_div(Q * 32, 256), 256, 0, st>>>(q, Q, d, qst);
     TFRS_LAUNCH_CHECK();
-    qmargin_kernel<<<(unsigned)ceil_div(pl.Qp, 256), 256, 0, st>>>(q, Q, pl.Qp, d, hdr, margin, cut);
+    side_exp_kernel<<<1, 1, 0, st>>>(qst);
+    TFRS_LAUNCH_CHECK();
+    long long chunks = (long long)pl.nqb * 2 * TILE_N * pl.kb * 8;
+    tile_image_kernel<<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(q, Q, d, pl.kb, (long long)pl.nqb * 2, qst, qimg);
+    TFRS_LAUNCH_CHECK();
+    qmargin_kernel<<<(unsigned)ceil_div(pl.Qp, 256), 256, 0, st>>>(q, Q, pl.Qp, d, hdr, qst, margin, cut);
     TFRS_LAUNCH_CHECK();
   }
   ScanParams sp{};
