@@ -68,12 +68,14 @@ int tfrs_gather_f32(const float* const* tables, const int64_t* rows, const int32
  * k <= 2048.
  *
  * tfrs_topk_scan_f32      exact fp32 CUDA-core path (any N, d; used for small corpora/chunks).
- * tfrs_index_*            builds the tensor-core screening image of a corpus (bf16, UMMA
- *                         SWIZZLE_128B K-major tiles + row-norm bound); done once at index() time
- *                         (BruteForce.index, factorized_top_k.py:540-584).
- * tfrs_topk_tc_f32        tcgen05 screening GEMM (bf16 in / fp32 accumulate in TMEM) with a fused
+ * tfrs_index_*            builds the tensor-core screening image of a corpus (fp16 after an exact
+ *                         power-of-two rescale, UMMA SWIZZLE_128B K-major tiles + row-norm bound);
+ *                         done once at index() time (BruteForce.index, factorized_top_k.py:540-584).
+ * tfrs_topk_tc_f32        tcgen05 screening GEMM (fp16 in / fp32 accumulate in TMEM) with a fused
  *                         threshold filter, then exact fp32 rescoring of the survivors -- same
- *                         bit-exact result as tfrs_topk_scan_f32.  Needs N >= 4096 and k <= 512.
+ *                         bit-exact result as tfrs_topk_scan_f32.  Needs d <= 128, k <= 512 and a
+ *                         corpus of at least ~256*k rows (tfrs_topk_tc_workspace_bytes returns 0
+ *                         outside the supported range; callers then use tfrs_topk_scan_f32).
  * ------------------------------------------------------------------------------------------- */
 size_t tfrs_topk_scan_workspace_bytes(int64_t Q, int64_t N, int d, int k);
 int tfrs_topk_scan_f32(const float* q, int64_t Q, const float* corpus, int64_t N, int d, int k,
@@ -88,6 +90,12 @@ size_t tfrs_topk_tc_workspace_bytes(int64_t Q, int64_t N, int d, int k);
 int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, const void* index_buf, int64_t N,
                      int d, int k, int64_t index_offset, float* out_scores, int64_t* out_idx, void* ws,
                      size_t ws_bytes, void* stream);
+
+/* Test/debug introspection of tfrs_topk_tc_f32's workspace: out8 = {count offset, fallback-flag offset,
+ * threshold offset, survivor-list offset, parts, cap_part, padded Q, cut offset} (byte offsets from the
+ * 16-byte-aligned workspace base).  Lets the tests assert that the exact fallback was NOT what produced a
+ * result. */
+int tfrs_topk_tc_layout(int64_t Q, int64_t N, int d, int k, int64_t* out8);
 
 /* Optional per-stage device timing of tfrs_topk_tc_f32 (CUDA events on the launch stream; used by
  * bench.py for the roofline figure).  tfrs_profile_read synchronises the device and returns the summed

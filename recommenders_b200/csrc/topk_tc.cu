@@ -30,6 +30,7 @@
 // t's epilogue.  Each B tile feeds two MMAs (both A blocks): 16 KB of L2->smem traffic per 512
 // tensor-core cycles keeps the chip under the ~6.3 KB/clk L2 fabric limit.
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 #include "rowselect.cuh"
 
@@ -53,6 +54,14 @@ constexpr int MAX_SAMPLE_STRIDE = 4;
 //   <= E_REL * |q| * |c|   (Cauchy-Schwarz), E_REL = 0.00108 including the 0.1 % norm inflation.
 constexpr float E_REL = 0.00108f;
 constexpr float E_ACC = 0.00013f;    // run-to-run slack between the two passes (they are bit-identical in practice)
+
+// Debug A/B switch (env TFRS_TC_BF16=1): screen with unscaled bf16 operands instead of scaled fp16.
+static int use_bf16() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TFRS_TC_BF16"); v = (e && atoi(e)) ? 1 : 0; }
+  return v;
+}
+constexpr float E_REL_BF16 = 0.0083f;
 
 struct SideStats {              // per operand side (corpus at index time, queries per call)
   unsigned int max_norm2_bits;  // max_i |x_i|^2   (float bits; non-negative so uint order == float order)
@@ -166,8 +175,8 @@ __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 tile_image_kernel(const float* __restrict__ src, long long rows, int d, int kb, long long n_tiles,
-                  const SideStats* __restrict__ st, unsigned char* __restrict__ img) {
-  const int e = st->exp;
+                  const SideStats* __restrict__ st, int bf16, unsigned char* __restrict__ img) {
+  const int scale_exp = bf16 ? 0 : st->exp;
   const long long total = n_tiles * TILE_N * (long long)kb * 8;  // 16-byte chunks
   for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
     int chunk = (int)(e % (kb * 8));
@@ -180,7 +189,8 @@ tile_image_kernel(const float* __restrict__ src, long long rows, int d, int kb, 
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float f = (row < rows && k0 + j < d) ? src[row * d + k0 + j] : 0.f;
-      v[j] = __float2half_rn(ldexpf(f, e));  // exact power-of-two rescale, then one rounding to fp16
+      v[j] = __float2half_rn(ldexpf(f, scale_exp));  // exact power-of-two rescale, then one rounding to fp16
+      if (bf16) { __nv_bfloat16 b = __float2bfloat16_rn(f); v[j] = *reinterpret_cast<__half*>(&b); }
     }
     unsigned char* dst = img + tile * ((long long)kb * SLAB_BYTES) + (long long)slab * SLAB_BYTES + r * 128 + ((cj ^ (r & 7)) * 16);
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
@@ -207,11 +217,16 @@ side_stats_kernel(const float* __restrict__ src, long long rows, int d, SideStat
     if (best_a > 0.f) atomicMax(&st->amax_bits, __float_as_uint(best_a));
   }
 }
-__global__ void side_exp_kernel(SideStats* st) {
+__global__ void side_exp_kernel(SideStats* st, int target) {
   const float amax = __uint_as_float(st->amax_bits);
   int x = 0;
   if (amax > 0.f && amax < INFINITY) (void)frexpf(amax, &x);  // amax = m * 2^x, m in [0.5, 1)
-  st->exp = (amax > 0.f && amax < INFINITY) ? (15 - x) : 0;      // amax * 2^exp in [2^14, 2^15)
+  st->exp = (amax > 0.f && amax < INFINITY) ? (target - x) : 0;  // amax * 2^exp in [2^(target-1), 2^target)
+}
+static int fp16_target() {
+  static int v = -100;
+  if (v == -100) { const char* e = getenv("TFRS_TC_FP16_TARGET"); v = e ? atoi(e) : 15; }
+  return v;
 }
 
 __global__ void header_kernel(IndexHeader* dst, IndexHeader h) { *dst = h; }
@@ -220,7 +235,7 @@ __global__ void header_kernel(IndexHeader* dst, IndexHeader h) { *dst = h; }
 // 2^(exp_q + exp_c), an exact power of two)
 __global__ void __launch_bounds__(256)
 qmargin_kernel(const float* __restrict__ q, long long Q, long long Qp, int d, const IndexHeader* __restrict__ hdr,
-               const SideStats* __restrict__ qst, float* __restrict__ margin, float* __restrict__ cut) {
+               const SideStats* __restrict__ qst, int bf16, float* __restrict__ margin, float* __restrict__ cut) {
   long long row = (long long)blockIdx.x * 256 + threadIdx.x;
   if (row >= Qp) return;
   float n2 = 0.f;
@@ -230,8 +245,8 @@ qmargin_kernel(const float* __restrict__ q, long long Q, long long Qp, int d, co
   }
   const float cn = sqrtf(__uint_as_float(hdr->st.max_norm2_bits)) * 1.001f;
   const float qn = sqrtf(n2) * 1.001f;
-  const int se = hdr->st.exp + qst->exp;
-  const float e = ldexpf(E_REL * qn * cn, se) + 1e-30f;
+  const int se = bf16 ? 0 : (hdr->st.exp + qst->exp);
+  const float e = ldexpf((bf16 ? E_REL_BF16 : E_REL) * qn * cn, se) + 1e-30f;
   margin[row] = 2.f * e + ldexpf(E_ACC * qn * cn, se);
   cut[row] = 2.f * e;
 }
@@ -254,6 +269,7 @@ struct ScanParams {
   unsigned int* count;            // [Qp, parts]   survivors found by each (query, corpus part)
   uint2* cand;                    // [Qp, parts, cap_part] (score bits, local index): one private segment per
   int cap_part;                   //   (query row, part) => appended by its single owner thread, no atomics
+  uint32_t idesc;
 };
 
 template <int KB, int STAGES, int MODE>
@@ -325,7 +341,7 @@ tc_scan_kernel(const ScanParams p) {
             const uint64_t b_desc = make_smem_desc(smem_u32(sB + (stage * KB + kb) * SLAB_BYTES));
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4)  // 4 x (K=16 fp16 = 32 B) inside the 128-byte swizzle row
-              umma_f16(d_tmem, a_desc + (uint64_t)(k4 * 2), b_desc + (uint64_t)(k4 * 2), IDESC_F16_M128_N128,
+              umma_f16(d_tmem, a_desc + (uint64_t)(k4 * 2), b_desc + (uint64_t)(k4 * 2), p.idesc,
                         (uint32_t)((kb | k4) != 0));
           }
         }
@@ -735,11 +751,11 @@ extern "C" int tfrs_index_build(const float* corpus, int64_t N, int d, void* ind
   SideStats* cst = &reinterpret_cast<IndexHeader*>(index_buf)->st;
   side_stats_kernel<<<(unsigned)(148 * 8), 256, 0, st>>>(corpus, N, d, cst);
   TFRS_LAUNCH_CHECK();
-  side_exp_kernel<<<1, 1, 0, st>>>(cst);
+  side_exp_kernel<<<1, 1, 0, st>>>(cst, fp16_target());
   TFRS_LAUNCH_CHECK();
   long long chunks = h.n_tiles * TILE_N * (long long)h.kb * 8;
   unsigned blocks = (unsigned)(ceil_div(chunks, 256) < (1 << 20) ? ceil_div(chunks, 256) : (1 << 20));
-  tile_image_kernel<<<blocks, 256, 0, st>>>(corpus, N, d, h.kb, h.n_tiles, cst, (unsigned char*)index_buf + HEADER_BYTES);
+  tile_image_kernel<<<blocks, 256, 0, st>>>(corpus, N, d, h.kb, h.n_tiles, cst, use_bf16(), (unsigned char*)index_buf + HEADER_BYTES);
   TFRS_LAUNCH_CHECK();
   return TFRS_OK;
 }
@@ -782,17 +798,18 @@ extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, 
     TFRS_CUDA(cudaMemsetAsync(qst, 0, sizeof(SideStats), st));
     side_stats_kernel<<<(unsigned)ceil_div(Q * 32, 256), 256, 0, st>>>(q, Q, d, qst);
     TFRS_LAUNCH_CHECK();
-    side_exp_kernel<<<1, 1, 0, st>>>(qst);
+    side_exp_kernel<<<1, 1, 0, st>>>(qst, fp16_target());
     TFRS_LAUNCH_CHECK();
     long long chunks = (long long)pl.nqb * 2 * TILE_N * pl.kb * 8;
-    tile_image_kernel<<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(q, Q, d, pl.kb, (long long)pl.nqb * 2, qst, qimg);
+    tile_image_kernel<<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(q, Q, d, pl.kb, (long long)pl.nqb * 2, qst, use_bf16(), qimg);
     TFRS_LAUNCH_CHECK();
-    qmargin_kernel<<<(unsigned)ceil_div(pl.Qp, 256), 256, 0, st>>>(q, Q, pl.Qp, d, hdr, qst, margin, cut);
+    qmargin_kernel<<<(unsigned)ceil_div(pl.Qp, 256), 256, 0, st>>>(q, Q, pl.Qp, d, hdr, qst, use_bf16(), margin, cut);
     TFRS_LAUNCH_CHECK();
   }
   ScanParams sp{};
   sp.qimg = qimg; sp.cimg = cimg; sp.Q = Q; sp.N = N; sp.nqb = pl.nqb; sp.n_tiles = pl.n_tiles;
   sp.binmax = binmax; sp.bins_ld = pl.bins_ld; sp.thr = thr; sp.count = count; sp.cand = cand; sp.cap_part = pl.cap_part;
+  sp.idesc = IDESC_F16_M128_N128 | (use_bf16() ? ((1u << 7) | (1u << 10)) : 0u);
   prof_mark(st, 1);
   // (1) sampled pass -> bin maxima -> k-th largest -> threshold
   int rc = launch_scan_mode(pl, sp, st, MODE_SAMPLE);
@@ -824,6 +841,17 @@ extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, 
     TFRS_LAUNCH_CHECK();
   }
   prof_mark(st, 4);
+  return TFRS_OK;
+}
+
+// Debug/test introspection: where the per-query survivor counts / fallback flags of the last call live
+// inside the caller's workspace (byte offsets from the 16-byte-aligned workspace base).
+extern "C" int tfrs_topk_tc_layout(int64_t Q, int64_t N, int d, int k, int64_t* out8) {
+  TFRS_CHECK_ARG(out8, "topk_tc_layout: NULL pointer");
+  Plan pl;
+  if (!make_plan(Q, N, d, k, pl)) { set_error("topk_tc_layout: unsupported shape"); return TFRS_ERR_UNSUPPORTED; }
+  out8[0] = (int64_t)pl.o_count; out8[1] = (int64_t)pl.o_ovf; out8[2] = (int64_t)pl.o_thr; out8[3] = (int64_t)pl.o_cand;
+  out8[4] = pl.parts_full; out8[5] = pl.cap_part; out8[6] = pl.Qp; out8[7] = (int64_t)pl.o_cut;
   return TFRS_OK;
 }
 

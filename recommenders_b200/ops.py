@@ -120,6 +120,25 @@ def tc_supported(Q: int, N: int, d: int, k: int) -> bool:
   return lib().tfrs_topk_tc_workspace_bytes(Q, N, d, k) > 0
 
 
+def tc_last_call_stats(Q: int, N: int, d: int, k: int, device=None) -> dict:
+  """Survivor / fallback statistics of the most recent topk_tc call with this shape (reads the cached
+  workspace; synchronises).  Used by tests to prove the tensor-core path -- not the exact fallback --
+  produced the result."""
+  out = (ctypes.c_int64 * 8)()
+  check(lib().tfrs_topk_tc_layout(Q, N, d, k, out), "topk_tc_layout")
+  o_count, o_ovf, o_thr, o_cand, parts, cap, Qp, o_cut = [int(x) for x in out]
+  dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+  ws = workspace(0, dev, "tc")
+  base = (-ws.data_ptr()) % 16
+  torch.cuda.synchronize()
+  counts = ws[base + o_count: base + o_count + Qp * parts * 4].view(torch.int32).view(Qp, parts)[:Q]
+  ovf = ws[base + o_ovf: base + o_ovf + Q * 4].view(torch.int32)
+  per_query = counts.sum(1)
+  return {"fallback_queries": int((ovf != 0).sum()), "survivors_mean": float(per_query.float().mean()),
+          "survivors_max": int(per_query.max()), "parts": parts, "cap_part": cap,
+          "part_max": int(counts.max())}
+
+
 def profile_enable(on: bool) -> None:
   check(lib().tfrs_profile_enable(int(on)), "profile_enable")
 

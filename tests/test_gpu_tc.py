@@ -20,10 +20,15 @@ def _rand(shape, seed, scale=1.0):
   return torch.randn(shape, generator=g, device="cuda") * scale
 
 
-def _check(ops, q, c, k, offset=0, oracle_rows=32):
+def _check(ops, q, c, k, offset=0, oracle_rows=32, max_fallback=0):
   idx = ops.index_build(c)
   assert ops.tc_supported(q.shape[0], c.shape[0], c.shape[1], k)
   s, i = ops.topk_tc(q, c, idx, k, index_offset=offset)
+  if max_fallback is not None:
+    # the tensor-core path itself -- not the exact fallback that backs it up -- must have produced the result
+    st = ops.tc_last_call_stats(q.shape[0], c.shape[0], c.shape[1], k)
+    assert st["fallback_queries"] <= max_fallback, st
+    assert st["survivors_mean"] >= k, st
   es, ei = ops.topk_scan(q, c, k, index_offset=offset)
   assert torch.equal(i, ei) and torch.equal(s, es), "tensor-core path differs from the exact CUDA-core path"
   r = min(oracle_rows, q.shape[0])
@@ -43,25 +48,26 @@ def test_tc_index_offset_and_negative_scores(ops):
   # all scores negative and N not a multiple of 128: zero-padded rows must never be returned
   c = torch.rand((50001, 64), device="cuda") + 0.1
   q = -(torch.rand((64, 64), device="cuda") + 0.1)
-  s, i = _check(ops, q, c, 20, offset=123456789)
+  s, i = _check(ops, q, c, 20, offset=123456789, max_fallback=None)  # narrow score spread: wide band, fallback allowed
   assert int(i.min()) >= 123456789 and int(i.max()) < 123456789 + 50001 and float(s.max()) < 0
 
 
 def test_tc_ties_overflow_fallback(ops):
   # every candidate identical -> every screening score ties -> survivor lists overflow -> exact fallback
   c = torch.ones((40000, 64), device="cuda"); q = _rand((40, 64), 3)
-  s, i = _check(ops, q, c, 10)
+  s, i = _check(ops, q, c, 10, max_fallback=None)  # every query must take the exact fallback here
+  assert ops.tc_last_call_stats(40, 40000, 64, 10)["fallback_queries"] == 40
   assert torch.equal(i, torch.arange(10, device="cuda").expand(40, 10))
   # duplicated corpus blocks: exact duplicates across tiles, lowest index must win
   base = _rand((20000, 64), 4)
-  _check(ops, _rand((100, 64), 5), torch.cat([base, base, base], 0), 30)
+  _check(ops, _rand((100, 64), 5), torch.cat([base, base, base], 0), 30, max_fallback=None)
 
 
 def test_tc_scaled_inputs(ops):
   # large dynamic range: margins scale with |q| * max|c|
   _check(ops, _rand((128, 64), 6, 1e3), _rand((60000, 64), 7, 1e-3), 25)
   c = _rand((60000, 64), 8); c[12345] *= 1000.0   # one huge-norm row inflates the bound -> more survivors, same answer
-  _check(ops, _rand((64, 64), 9), c, 10)
+  _check(ops, _rand((64, 64), 9), c, 10, max_fallback=None)
 
 
 def test_tc_full_size_properties(ops):
@@ -71,6 +77,8 @@ def test_tc_full_size_properties(ops):
   c = _rand((N, d), 1); q = _rand((Q, d), 2)
   idx = ops.index_build(c)
   s, i = ops.topk_tc(q, c, idx, k)
+  st = ops.tc_last_call_stats(Q, N, d, k)
+  assert st["fallback_queries"] == 0 and st["survivors_mean"] >= k, st
   assert bool((s[:, :-1] >= s[:, 1:]).all()), "scores must be sorted descending"
   assert int(i.min()) >= 0 and int(i.max()) < N
   assert all(len(set(r)) == k for r in i[:64].cpu().tolist()), "indices must be distinct"
