@@ -97,6 +97,10 @@ int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, const void*
  * result. */
 int tfrs_topk_tc_layout(int64_t Q, int64_t N, int d, int k, int64_t* out8);
 
+/* Hardware probe (tools/probe_f16acc.py): one 128x128x64 UMMA tile with a caller-chosen instruction
+ * descriptor, raw TMEM dump.  Not on any product path. */
+int tfrs_debug_umma_probe(const void* a_img, const void* b_img, uint32_t idesc, int n_cols, uint32_t* out, void* stream);
+
 /* Optional per-stage device timing of tfrs_topk_tc_f32 (CUDA events on the launch stream; used by
  * bench.py for the roofline figure).  tfrs_profile_read synchronises the device and returns the summed
  * times in ms of stage 0 = query image, 1 = sampled pass + threshold, 2 = full filter pass (the

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "tfrs_topk_tc_workspace_bytes": (c_sz, [c_l, c_l, c_i, c_i]),
     "tfrs_topk_tc_f32": (c_i, [c_p, c_l, c_p, c_p, c_l, c_i, c_i, c_l, c_p, c_p, c_p, c_sz, c_p]),
     "tfrs_topk_tc_layout": (c_i, [c_l, c_l, c_i, c_i, c_p]),
+    "tfrs_debug_umma_probe": (c_i, [c_p, c_p, ctypes.c_uint32, c_i, c_p, c_p]),
     "tfrs_profile_enable": (c_i, [c_i]),
     "tfrs_profile_read": (c_i, [c_p, c_p]),
     "tfrs_topk_merge": (c_i, [c_p, c_p, c_i, c_l, c_i, c_i, c_p, c_p, c_p]),

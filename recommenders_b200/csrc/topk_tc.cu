@@ -33,6 +33,7 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 #include "rowselect.cuh"
+#include "tc_ptx.cuh"
 
 namespace tfrs {
 namespace tc {
@@ -43,7 +44,8 @@ constexpr int QBLK = 256;            // queries per CTA (2 A blocks)
 constexpr int KSLAB = 64;            // fp16 elements per 128-byte swizzle row
 constexpr int SLAB_BYTES = TILE_N * 128;  // 16 KB: 128 rows x 128 B
 constexpr int HEADER_BYTES = 1024;
-constexpr int THREADS = 384;
+constexpr int THREADS = 640;      // 4 control warps + 16 epilogue warps (4 per SM sub-partition)
+constexpr int EPI_WARPS = 16;
 constexpr int EPI_WARP0 = 4;
 constexpr int CAND_CAP = 2048;       // survivors kept per query
 constexpr int MAX_SAMPLE_STRIDE = 4;
@@ -74,100 +76,6 @@ struct IndexHeader {
   int d, d_pad, kb, pad;
   long long n, n_tiles;
 };
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate, M=128, N=128, K=16
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// 64 consecutive fp32 accumulator columns of this thread's row (TMEM lane) -> 64 registers
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
-        "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
-        "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
-        "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
-        "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
-      : "r"(taddr));
-}
-// tcgen05.wait::ld.  The loaded registers are threaded through as in/out operands (in two statements:
-// inline asm has an operand limit) so the compiler cannot schedule a use of the values above the wait.
-__device__ __forceinline__ void tmem_ld_wait64(uint32_t (&r)[64]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-               :: "memory");
-  asm volatile(""
-               : "+r"(r[32]), "+r"(r[33]), "+r"(r[34]), "+r"(r[35]), "+r"(r[36]), "+r"(r[37]), "+r"(r[38]), "+r"(r[39]),
-                 "+r"(r[40]), "+r"(r[41]), "+r"(r[42]), "+r"(r[43]), "+r"(r[44]), "+r"(r[45]), "+r"(r[46]), "+r"(r[47]),
-                 "+r"(r[48]), "+r"(r[49]), "+r"(r[50]), "+r"(r[51]), "+r"(r[52]), "+r"(r[53]), "+r"(r[54]), "+r"(r[55]),
-                 "+r"(r[56]), "+r"(r[57]), "+r"(r[58]), "+r"(r[59]), "+r"(r[60]), "+r"(r[61]), "+r"(r[62]), "+r"(r[63])
-               :: "memory");
-}
-
-// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor: D=f32 (bits 4-5 = 1), A=B=f16 (bits 7-9, 10-12 = 0), K-major both, N=128, M=128
-constexpr uint32_t IDESC_F16_M128_N128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-
-__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
 // ------------------------------------------------------------------------------------------------
 // image builders: fp32 [rows, d] -> fp16 128-row tiles, each K slab of 64 as one swizzled 16 KB block
@@ -297,7 +205,7 @@ tc_scan_kernel(const ScanParams p) {
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(a_full, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -352,15 +260,17 @@ tc_scan_kernel(const ScanParams p) {
     }
   } else if (warp >= EPI_WARP0) {
     // ===== epilogue: one query row per thread =====
-    const int ew = warp - EPI_WARP0;       // 0..7
-    const int ab = ew >> 2, quad = ew & 3; // TMEM lane quadrant == warp % 4
+    // 16 epilogue warps: (column half, A block, TMEM lane quadrant); a thread owns one query row x 64 columns of
+    // every tile, so four warps per scheduler overlap their TMEM-load latency with each other's math.
+    const int ew = warp - EPI_WARP0;       // 0..15
+    const int half = ew >> 3, ab = (ew >> 2) & 1, quad = ew & 3;  // TMEM lane quadrant == warp % 4
     const long long row = (long long)qb * QBLK + ab * TILE_M + quad * 32 + lane;
     const bool row_ok = row < p.Q;
     float thr = INFINITY;
     if (MODE == MODE_FILTER && row_ok) thr = p.thr[row];
     uint2* my_list = nullptr;
     unsigned int my_cnt = 0;
-    if (MODE == MODE_FILTER) my_list = p.cand + ((long long)row * p.parts + part) * p.cap_part;
+    if (MODE == MODE_FILTER) my_list = p.cand + (((long long)row * p.parts + part) * 2 + half) * p.cap_part;
     const unsigned int cap = (unsigned int)p.cap_part;
     for (int it = 0; it < n_iter; ++it) {
       const int buf = it & 1;
@@ -371,9 +281,9 @@ tc_scan_kernel(const ScanParams p) {
       mbar_wait(&t_full[buf], tphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ab * 2 + buf) * TILE_N);
-      float binm[2] = {-INFINITY, -INFINITY};
-#pragma unroll 1   // two halves of 64 columns; one body in the I-cache
-      for (int h = 0; h < 2; ++h) {
+      float binm = -INFINITY;
+      {
+        const int h = half;
         uint32_t r[64];
         if (MODE != MODE_DBG_NOLD) {
           tmem_ld64(taddr + h * 64, r);
@@ -382,13 +292,12 @@ tc_scan_kernel(const ScanParams p) {
 #pragma unroll
           for (int j = 0; j < 64; ++j) r[j] = (uint32_t)(it * 131 + j * 7 + h + lane);
         }
-        if (h == 1) {
-          // every TMEM read of this accumulator buffer has completed: hand it back to the MMA warp before the math
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&t_empty[buf]);
-        }
-        if (MODE == MODE_DBG_LDONLY) { binm[h] = fmaxf(binm[h], __uint_as_float(r[0] ^ r[63])); continue; }
+        // this warp's TMEM reads of the accumulator buffer are complete: release it before the math
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[buf]);
+        if (MODE == MODE_DBG_LDONLY) binm = fmaxf(binm, __uint_as_float(r[0] ^ r[63]));
+        else {
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
           float v[32];
@@ -400,7 +309,7 @@ tc_scan_kernel(const ScanParams p) {
           for (int i = 0; i < 8; ++i) g[i] = fmaxf(max3(v[4 * i], v[4 * i + 1], v[4 * i + 2]), v[4 * i + 3]);
           const float m = fmaxf(max3(g[0], g[1], g[2]), fmaxf(max3(g[3], g[4], g[5]), fmaxf(g[6], g[7])));
           if (MODE != MODE_FILTER) {
-            binm[h] = fmaxf(binm[h], m);
+            binm = fmaxf(binm, m);
           } else {
             // Survivors are rare.  Every branch below is WARP-UNIFORM: one vote on the chunk max, then one
             // REDUX.OR of the per-lane 8-bit group mask; the per-lane work is predicated stores only.
@@ -425,11 +334,11 @@ tc_scan_kernel(const ScanParams p) {
             }
           }
         }
+        }
       }
-      if (MODE != MODE_FILTER && row_ok)
-        *reinterpret_cast<float2*>(p.binmax + row * p.bins_ld + 2 * u) = make_float2(binm[0], binm[1]);
+      if (MODE != MODE_FILTER && row_ok) p.binmax[row * p.bins_ld + 2 * u + half] = binm;
     }
-    if (MODE == MODE_FILTER) p.count[(long long)row * p.parts + part] = my_cnt;
+    if (MODE == MODE_FILTER) p.count[((long long)row * p.parts + part) * 2 + half] = my_cnt;
   }
 
   tc_fence_before();
@@ -496,15 +405,25 @@ __device__ unsigned int block_kth_largest(KeyAt key_at, int n, int k, unsigned i
   return prefix;
 }
 
-// k-th largest bin maximum of the sampled pass -> filter threshold T = L - margin
+// k-th largest bin maximum of the sampled pass -> filter threshold T = L - margin.
+// The row of bin maxima is staged once in shared memory (when it fits) and radix-selected there.
+constexpr int THR_SMEM_BINS = 12288;
 __global__ void __launch_bounds__(256)
 tc_threshold_kernel(const float* __restrict__ binmax, int bins_ld, int n_bins, int k, const float* __restrict__ margin,
                     float* __restrict__ thr, unsigned int* __restrict__ overflow) {
+  extern __shared__ unsigned int thr_keys[];
   __shared__ unsigned int hist[256];
   __shared__ unsigned int bcast[2];
   const int row = blockIdx.x;
   const float* src = binmax + (long long)row * bins_ld;
-  const unsigned int kth = block_kth_largest([&](int i) { return f2key(__ldg(src + i)); }, n_bins, k, hist, bcast);
+  unsigned int kth;
+  if (n_bins <= THR_SMEM_BINS) {
+    for (int i = threadIdx.x; i < n_bins; i += 256) thr_keys[i] = f2key(__ldg(src + i));
+    __syncthreads();
+    kth = block_kth_largest([&](int i) { return thr_keys[i]; }, n_bins, k, hist, bcast);
+  } else {
+    kth = block_kth_largest([&](int i) { return f2key(__ldg(src + i)); }, n_bins, k, hist, bcast);
+  }
   if (threadIdx.x == 0) { thr[row] = key2f(kth) - margin[row]; overflow[row] = 0; }
 }
 
@@ -668,7 +587,7 @@ static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
   pl.parts_sample = parts < pl.n_sample ? parts : pl.n_sample;
   pl.parts_full = (long long)parts < pl.n_tiles ? parts : (int)pl.n_tiles;
   {
-    int cp = 2 * CAND_CAP / pl.parts_full;  // segments add up to ~2x the per-query capacity
+    int cp = 2 * CAND_CAP / (pl.parts_full * 2);  // (part, column-half) segments add up to ~2x the per-query capacity
     int p2 = 32; while (p2 * 2 <= cp && p2 < CAND_CAP) p2 <<= 1;
     pl.cap_part = p2;
   }
@@ -680,10 +599,10 @@ static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
   pl.o_margin = take((size_t)pl.Qp * 4);
   pl.o_cut = take((size_t)pl.Qp * 4);
   pl.o_thr = take((size_t)pl.Qp * 4);
-  pl.o_count = take((size_t)pl.Qp * pl.parts_full * 4);
+  pl.o_count = take((size_t)pl.Qp * pl.parts_full * 2 * 4);
   pl.o_ovf = take((size_t)pl.Qp * 4);
   pl.o_binmax = take((size_t)pl.Qp * pl.bins_ld * 4);
-  pl.o_cand = take((size_t)pl.Qp * pl.parts_full * pl.cap_part * 8);
+  pl.o_cand = take((size_t)pl.Qp * pl.parts_full * 2 * pl.cap_part * 8);
   pl.total = o;
   return true;
 }
@@ -814,7 +733,12 @@ extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, 
   // (1) sampled pass -> bin maxima -> k-th largest -> threshold
   int rc = launch_scan_mode(pl, sp, st, MODE_SAMPLE);
   if (rc) return rc;
-  tc_threshold_kernel<<<(unsigned)Q, 256, 0, st>>>(binmax, pl.bins_ld, pl.n_bins, k, margin, thr, ovf);
+  {
+    size_t smem = pl.n_bins <= THR_SMEM_BINS ? (size_t)pl.n_bins * 4 : 0;
+    static bool attr = false;
+    if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(tc_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, THR_SMEM_BINS * 4)); attr = true; }
+    tc_threshold_kernel<<<(unsigned)Q, 256, smem, st>>>(binmax, pl.bins_ld, pl.n_bins, k, margin, thr, ovf);
+  }
   TFRS_LAUNCH_CHECK();
   prof_mark(st, 2);
   // (2) full pass with the fused threshold filter
@@ -826,7 +750,7 @@ extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, 
     size_t smem = (size_t)FIN_MAXM * 12 + (size_t)CAND_CAP * 8 + (size_t)d * 4 + 16;
     static bool attr = false;
     if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
-    tc_finalize_kernel<<<(unsigned)Q, 256, smem, st>>>(q, corpus, d, k, index_offset, count, cand, pl.parts_full, pl.cap_part,
+    tc_finalize_kernel<<<(unsigned)Q, 256, smem, st>>>(q, corpus, d, k, index_offset, count, cand, pl.parts_full * 2, pl.cap_part,
                                                      cut, thr, N, ovf, out_scores, (long long*)out_idx);
     TFRS_LAUNCH_CHECK();
   }
@@ -851,7 +775,7 @@ extern "C" int tfrs_topk_tc_layout(int64_t Q, int64_t N, int d, int k, int64_t* 
   Plan pl;
   if (!make_plan(Q, N, d, k, pl)) { set_error("topk_tc_layout: unsupported shape"); return TFRS_ERR_UNSUPPORTED; }
   out8[0] = (int64_t)pl.o_count; out8[1] = (int64_t)pl.o_ovf; out8[2] = (int64_t)pl.o_thr; out8[3] = (int64_t)pl.o_cand;
-  out8[4] = pl.parts_full; out8[5] = pl.cap_part; out8[6] = pl.Qp; out8[7] = (int64_t)pl.o_cut;
+  out8[4] = pl.parts_full * 2; out8[5] = pl.cap_part; out8[6] = pl.Qp; out8[7] = (int64_t)pl.o_cut;
   return TFRS_OK;
 }
 

@@ -1,0 +1,120 @@
+"""Secondary measurements for BASELINE.md §4 (configs 3 and 5): embedding gather GB/s, sparse Adagrad,
+in-batch softmax step, Cross layer.  CUDA events, warm-up, inputs larger than L2 or rotated between
+iterations.  Prints one JSON object.   usage: python tools/bench_kernels.py [--quick]"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from recommenders_b200 import ops
+
+dev = torch.device("cuda", 0)
+quick = "--quick" in sys.argv
+peaks = {}
+try:
+  peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+except Exception:
+  pass
+HBM = peaks.get("hbm_gbs", 6650.0)
+
+
+def timeit(fn, iters=20, warm=5):
+  for _ in range(warm):
+    fn()
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(iters):
+    fn()
+  e1.record()
+  torch.cuda.synchronize()
+  return e0.elapsed_time(e1) / iters * 1e-3
+
+
+out = {"hbm_peak_gbs": HBM}
+g = torch.Generator(device=dev); g.manual_seed(7)
+
+# ---- config 5 gather: 26 tables 1M x 32, 65536 ids each -> [65536, 26*32 (+13 dense, ld 848)]
+F, V, D, B = (26, 1_000_000, 32, 65536) if not quick else (26, 100_000, 32, 8192)
+tables = [torch.rand((V, D), generator=g, device=dev) - 0.5 for _ in range(F)]
+ids_sets = [[torch.randint(0, V, (B,), generator=g, device=dev, dtype=torch.int32) for _ in range(F)] for _ in range(4)]
+act = torch.zeros((B, 848), device=dev)
+state = {"i": 0}
+
+
+def gather5():
+  ops.gather(tables, ids_sets[state["i"] % 4], out=act); state["i"] += 1
+
+
+t = timeit(gather5)
+bytes5 = B * F * D * 4 * 2 + B * F * 4
+out["cfg5_gather"] = {"seconds": t, "algorithmic_bytes": bytes5, "GBps": bytes5 / t / 1e9, "frac_of_hbm": bytes5 / t / 1e9 / HBM,
+                      "shape": f"{F} tables {V}x{D}, batch {B}, ids int32"}
+
+# ---- config 5 Cross: B=65536, D=845 (ld 848 padded activations -> use D=848 contiguous here), 3 layers fwd
+Dc = 845
+x0 = torch.rand((B, Dc), generator=g, device=dev)
+Ws = [torch.randn((Dc, Dc), generator=g, device=dev) * 0.05 for _ in range(3)]
+bs = [torch.zeros((Dc,), device=dev) for _ in range(3)]
+
+
+def cross3():
+  x = x0
+  for W, b in zip(Ws, bs):
+    x = ops.cross(x0, x, W, b, 0.0)
+  return x
+
+
+with torch.no_grad():
+  t = timeit(cross3, iters=5 if not quick else 3, warm=2)
+flops = 3 * 2.0 * B * Dc * Dc
+out["cfg5_cross_fwd_3layers"] = {"seconds": t, "TFLOPs": flops / t / 1e12, "flops": flops, "path": "exact fp32 CUDA-core SGEMM + fused epilogue"}
+del tables, ids_sets, act, x0, Ws
+
+# ---- config 3: two-tower step pieces, 10M users / 1M items, d=64, batch 16384
+U, I, d, Bt = (10_000_000, 1_000_000, 64, 16384) if not quick else (1_000_000, 100_000, 64, 4096)
+ut = (torch.rand((U, d), generator=g, device=dev) - 0.5) * 0.1
+it = (torch.rand((I, d), generator=g, device=dev) - 0.5) * 0.1
+uacc = torch.full_like(ut, 0.1); iacc = torch.full_like(it, 0.1)
+uid = [torch.randint(0, U, (Bt,), generator=g, device=dev) for _ in range(4)]
+iid = [torch.randint(0, I, (Bt,), generator=g, device=dev) for _ in range(4)]
+state["i"] = 0
+
+
+def gather3():
+  k = state["i"] % 4; state["i"] += 1
+  return ops.gather([ut], [uid[k]]), ops.gather([it], [iid[k]])
+
+
+t = timeit(gather3)
+bytes3 = 2 * Bt * d * 4 * 2 + 2 * Bt * 8
+out["cfg3_gather_2tables"] = {"seconds": t, "algorithmic_bytes": bytes3, "GBps": bytes3 / t / 1e9, "frac_of_hbm": bytes3 / t / 1e9 / HBM,
+                              "note": "2 launches of 4 MB each: launch-latency bound at this size"}
+qe, ce = gather3()
+qe = qe.requires_grad_(True); ce = ce.requires_grad_(True)
+
+
+def softmax_fwd_bwd():
+  qe.grad = None; ce.grad = None
+  loss = ops.inbatch_softmax_loss(qe, ce)
+  loss.backward()
+  return loss
+
+
+t = timeit(softmax_fwd_bwd, iters=5 if not quick else 3, warm=2)
+out["cfg3_inbatch_softmax_fwd_bwd"] = {"seconds": t, "TFLOPs": 8.0 * Bt * Bt * d / t / 1e12, "flops": 8.0 * Bt * Bt * d,
+                                       "path": "exact fp32 CUDA-core SGEMM, L2-resident row blocks"}
+gq = qe.grad.detach().clone()
+
+
+def adagrad3():
+  k = state["i"] % 4; state["i"] += 1
+  ops.sparse_adagrad_(ut, uacc, uid[k], gq, 0.5)
+
+
+t = timeit(adagrad3)
+out["cfg3_sparse_adagrad_user_table"] = {"seconds": t, "rows": Bt, "GBps_algorithmic": (Bt * d * 4 * 5) / t / 1e9}
+print(json.dumps(out))

@@ -15,7 +15,7 @@ print("tc_supported:", ops.tc_supported(Q, N, d, k), flush=True)
 t0 = time.time(); idx = ops.index_build(c); torch.cuda.synchronize(); print("index_build ok %.3fs" % (time.time() - t0), flush=True)
 s, i = ops.topk_tc(q, c, idx, k); torch.cuda.synchronize(); print("topk_tc ok", flush=True)
 print("stats:", ops.tc_last_call_stats(Q, N, d, k))
-Qc = min(Q, 512)
+Qc = min(Q, 128)
 es, ei = ops.topk_scan(q[:Qc], c, k); torch.cuda.synchronize()
 print("stats:", ops.tc_last_call_stats(Q, N, d, k))
 print("ids equal:", bool((i[:Qc] == ei).all()), " scores equal:", bool((s[:Qc] == es).all()))
