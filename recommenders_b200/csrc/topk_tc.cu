@@ -49,6 +49,7 @@ constexpr int EPI_WARPS = 16;
 constexpr int EPI_WARP0 = 4;
 constexpr int CAND_CAP = 2048;       // survivors kept per query
 constexpr int MAX_SAMPLE_STRIDE = 4;
+constexpr int FIN_MAX_PARTS = 2 * 148;  // survivor-list segments per query: (corpus part, column half)
 // Screening error model (operands: fp16 after an exact power-of-two rescale of each side so that the
 // largest magnitude lands in [2^14, 2^15); accumulate: fp32 in TMEM):
 //   |x^ - x| <= 2^-11 |x| (+2^-25 absolute below the fp16 normal range, negligible after the rescale)
@@ -444,30 +445,37 @@ tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus
   __shared__ unsigned int bcast[2];
   __shared__ int m_sh;
   const int row = blockIdx.x, tid = threadIdx.x;
-  // gather this query's per-part segments (all threads walk the same part loop: uniform control flow)
-  unsigned int n_raw = 0; bool part_ovf = false;
-  for (int pt = 0; pt < parts; ++pt) {
+  // gather this query's per-(part, half) segments: counts -> exclusive prefix (parts <= 296, one thread each)
+  __shared__ int seg_off[FIN_MAX_PARTS + 1];
+  __shared__ int seg_bad;
+  if (tid == 0) seg_bad = 0;
+  __syncthreads();
+  for (int pt = tid; pt < parts; pt += 256) {
     unsigned int c = count[(long long)row * parts + pt];
-    part_ovf |= c > (unsigned)cap_part;
-    n_raw += c;
+    if (c > (unsigned)cap_part) { seg_bad = 1; c = 0; }
+    seg_off[pt + 1] = (int)c;
   }
-  if (part_ovf || n_raw > (unsigned)CAND_CAP || n_raw < (unsigned)k) {  // overflow (or impossible underflow): exact fallback
+  if (tid == 0) seg_off[0] = 0;
+  __syncthreads();
+  if (tid == 0) { int a = 0; for (int pt = 1; pt <= parts; ++pt) { a += seg_off[pt]; seg_off[pt] = a; } }
+  __syncthreads();
+  const unsigned int n_raw = (unsigned int)seg_off[parts];
+  if (seg_bad || n_raw > (unsigned)CAND_CAP || n_raw < (unsigned)k) {  // overflow (or impossible underflow): exact fallback
     if (tid == 0) overflow[row] = 1;
     return;
   }
   const int n = (int)n_raw;
   for (int t = tid; t < d; t += 256) qs[t] = q[(long long)row * d + t];
-  int base = 0;
-  for (int pt = 0; pt < parts; ++pt) {
-    const int c = (int)count[(long long)row * parts + pt];
+  // one warp per segment: coalesced copies
+  for (int pt = tid >> 5; pt < parts; pt += 8) {
+    const int b0 = seg_off[pt], c = seg_off[pt + 1] - b0;
     const uint2* seg = cand + ((long long)row * parts + pt) * cap_part;
-    for (int t = tid; t < c; t += 256) {
+    for (int t = tid & 31; t < c; t += 32) {
       uint2 e = seg[t];
       // rows of the zero-padded last tile are not candidates: sink them below everything
-      as[base + t] = (e.y < (unsigned long long)N) ? __uint_as_float(e.x) : -INFINITY;
-      ai[base + t] = e.y;
+      as[b0 + t] = (e.y < (unsigned long long)N) ? __uint_as_float(e.x) : -INFINITY;
+      ai[b0 + t] = e.y;
     }
-    base += c;
   }
   if (tid == 0) m_sh = 0;
   __syncthreads();
@@ -496,7 +504,16 @@ tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus
   for (int t = tid; t < m; t += 256) {
     const float* c = corpus + ei[t] * d;
     float acc = 0.f;
-    if ((d & 3) == 0) {
+    if (d == 64) {  // all 16 loads in flight, then the canonical chain
+      float4 cv[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) cv[u] = __ldg(reinterpret_cast<const float4*>(c) + u);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        acc = fmaf(qs[4 * u], cv[u].x, acc); acc = fmaf(qs[4 * u + 1], cv[u].y, acc);
+        acc = fmaf(qs[4 * u + 2], cv[u].z, acc); acc = fmaf(qs[4 * u + 3], cv[u].w, acc);
+      }
+    } else if ((d & 3) == 0) {
       for (int kk = 0; kk < d; kk += 4) {
         float4 cv = __ldg(reinterpret_cast<const float4*>(c + kk));
         acc = fmaf(qs[kk], cv.x, acc); acc = fmaf(qs[kk + 1], cv.y, acc);
@@ -577,13 +594,18 @@ static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
   const long long full_tiles = N / TILE_N;  // the zero-padded last tile is never sampled (its 0 scores are not candidates)
   if (full_tiles < 1) return false;
   pl.stride = MAX_SAMPLE_STRIDE;
+  {
+    static int ov = -1;
+    if (ov < 0) { const char* e = getenv("TFRS_TC_SAMPLE_STRIDE"); ov = e ? atoi(e) : 0; }
+    if (ov >= 1 && ov <= 16) pl.stride = ov;
+  }
   while (pl.stride > 1 && 2 * ceil_div(full_tiles, pl.stride) < 4ll * k) pl.stride >>= 1;
   pl.n_sample = (int)ceil_div(full_tiles, pl.stride);
   pl.n_bins = pl.n_sample * 2;
   pl.bins_ld = (pl.n_bins + 3) / 4 * 4;
   if (pl.n_bins < 4 * k) return false;  // too few bins for a useful threshold -> caller uses the exact path
   const int sms = sm_count();
-  int parts = sms / pl.nqb; if (parts < 1) parts = 1;
+  int parts = sms / pl.nqb; if (parts < 1) parts = 1; if (parts > FIN_MAX_PARTS / 2) parts = FIN_MAX_PARTS / 2;
   pl.parts_sample = parts < pl.n_sample ? parts : pl.n_sample;
   pl.parts_full = (long long)parts < pl.n_tiles ? parts : (int)pl.n_tiles;
   {
