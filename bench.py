@@ -283,12 +283,12 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32 (bf16 tcgen05 screening + exact fp32 re-scoring)" if used_tc else "f32",
+        "dtype": "f32 (fp16 tcgen05 screening, fp32 accumulate + exact fp32 re-scoring)" if used_tc else "f32",
         "data": "synthetic",
         "config": {"workload": f"{args.workload}: BruteForce top-{k}, {Q} queries x {N}x{d} corpus (N(0,1), seeds 1/2), "
                                f"row-sharded over {world} GPU(s)",
                    "path": "tcgen05 screening + exact rescoring" if used_tc else "exact CUDA-core scan",
-                   "l2": "inputs (bf16 image 128 MB + fp32 corpus 256 MB per 1M rows) exceed the 126 MB L2 between steps",
+                   "l2": "inputs (fp16 image 128 MB + fp32 corpus 256 MB per 1M rows) exceed the 126 MB L2 between steps",
                    "parallelism": f"corpus-shard x{world}"},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": Q * d * 4, "d2h_bytes_per_step": Q * k * 8,

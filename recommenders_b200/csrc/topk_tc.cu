@@ -176,8 +176,12 @@ struct ScanParams {
   // FILTER
   const float* thr;               // [Qp]
   unsigned int* count;            // [Qp, parts]   survivors found by each (query, corpus part)
-  uint2* cand;                    // [Qp, parts, cap_part] (score bits, local index): one private segment per
-  int cap_part;                   //   (query row, part) => appended by its single owner thread, no atomics
+  // Survivor RECORDS: when any of 8 consecutive columns of a row passes the threshold, the whole octet is
+  // appended (two 16-byte stores + the index of its first column); finalize drops the non-survivors.
+  // One private segment per (query row, corpus part, column half): a single writer thread, no atomics.
+  float* cand_s;                  // [Qp, parts, 2, cap_part, 8] screening scores of the octet
+  unsigned int* cand_i;           // [Qp, parts, 2, cap_part]    local index of the octet's first column
+  int cap_part;                   // records per segment
   uint32_t idesc;
 };
 
@@ -269,10 +273,13 @@ tc_scan_kernel(const ScanParams p) {
     const bool row_ok = row < p.Q;
     float thr = INFINITY;
     if (MODE == MODE_FILTER && row_ok) thr = p.thr[row];
-    uint2* my_list = nullptr;
-    unsigned int my_cnt = 0;
-    if (MODE == MODE_FILTER) my_list = p.cand + (((long long)row * p.parts + part) * 2 + half) * p.cap_part;
+    float* my_s = nullptr; unsigned int* my_i = nullptr;
+    unsigned int my_cnt = 0, my_ovf = 0;
     const unsigned int cap = (unsigned int)p.cap_part;
+    if (MODE == MODE_FILTER) {
+      const long long seg = (((long long)row * p.parts + part) * 2 + half) * p.cap_part;
+      my_s = p.cand_s + seg * 8; my_i = p.cand_i + seg;
+    }
     for (int it = 0; it < n_iter; ++it) {
       const int buf = it & 1;
       const uint32_t tphase = (it >> 1) & 1;
@@ -304,31 +311,35 @@ tc_scan_kernel(const ScanParams p) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c2 * 32 + j]);
-          // 8 group maxima of 4, then their max
-          float g[8];
+          // 4 quarter maxima of 8, then their max (FMNMX3 trees)
+          float qmx[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] = fmaxf(max3(v[4 * i], v[4 * i + 1], v[4 * i + 2]), v[4 * i + 3]);
-          const float m = fmaxf(max3(g[0], g[1], g[2]), fmaxf(max3(g[3], g[4], g[5]), fmaxf(g[6], g[7])));
+          for (int i = 0; i < 4; ++i)
+            qmx[i] = max3(max3(v[8 * i], v[8 * i + 1], v[8 * i + 2]), max3(v[8 * i + 3], v[8 * i + 4], v[8 * i + 5]),
+                          fmaxf(v[8 * i + 6], v[8 * i + 7]));
+          const float m = fmaxf(max3(qmx[0], qmx[1], qmx[2]), qmx[3]);
           if (MODE != MODE_FILTER) {
             binm = fmaxf(binm, m);
           } else {
             // Survivors are rare.  Every branch below is WARP-UNIFORM: one vote on the chunk max, then one
-            // REDUX.OR of the per-lane 8-bit group mask; the per-lane work is predicated stores only.
+            // REDUX.OR of the per-lane 4-bit quarter mask; the per-lane work is predicated stores only.
             if (__any_sync(0xffffffffu, m >= thr)) {
-              unsigned int gmask = 0;
+              unsigned int qmask = 0;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) gmask |= (g[i] >= thr) ? (1u << i) : 0u;
-              const unsigned int umask = __reduce_or_sync(0xffffffffu, gmask);
+              for (int i = 0; i < 4; ++i) qmask |= (qmx[i] >= thr) ? (1u << i) : 0u;
+              const unsigned int umask = __reduce_or_sync(0xffffffffu, qmask);
+              const bool room = my_cnt + 4u <= cap;    // worst case of this visit (4 octets) fits
+              my_ovf |= (!room && m >= thr) ? 1u : 0u;
               const unsigned int idx0 = (unsigned int)(col0 + h * 64 + c2 * 32);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (umask & (1u << i)) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float sc = v[4 * i + j];
-                    const bool hit = sc >= thr;
-                    if (hit && my_cnt < cap) my_list[my_cnt] = make_uint2(__float_as_uint(sc), idx0 + 4 * i + j);
-                    my_cnt += hit ? 1u : 0u;
+              for (int i = 0; i < 4; ++i) {
+                if (umask & (1u << i)) {             // uniform: some lane's octet i has a survivor
+                  if (room && qmx[i] >= thr) {       // per lane: append my whole octet (predicated, no loop)
+                    float4* dst = reinterpret_cast<float4*>(my_s + (size_t)my_cnt * 8);
+                    dst[0] = make_float4(v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3]);
+                    dst[1] = make_float4(v[8 * i + 4], v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
+                    my_i[my_cnt] = idx0 + 8 * i;
+                    ++my_cnt;
                   }
                 }
               }
@@ -339,7 +350,7 @@ tc_scan_kernel(const ScanParams p) {
       }
       if (MODE != MODE_FILTER && row_ok) p.binmax[row * p.bins_ld + 2 * u + half] = binm;
     }
-    if (MODE == MODE_FILTER) p.count[((long long)row * p.parts + part) * 2 + half] = my_cnt;
+    if (MODE == MODE_FILTER) p.count[((long long)row * p.parts + part) * 2 + half] = my_ovf ? (cap + 1u) : my_cnt;
   }
 
   tc_fence_before();
@@ -432,7 +443,8 @@ constexpr int FIN_MAXM = 1024;  // survivors re-scored exactly per query (band a
 
 __global__ void __launch_bounds__(256)
 tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus, int d, int k, long long index_offset,
-                   const unsigned int* __restrict__ count, const uint2* __restrict__ cand, int parts, int cap_part,
+                   const unsigned int* __restrict__ count, const float* __restrict__ cand_s,
+                   const unsigned int* __restrict__ cand_i, int parts, int cap_part,
                    const float* __restrict__ cut, const float* __restrict__ thr, long long N,
                    unsigned int* __restrict__ overflow, float* __restrict__ out_s, long long* __restrict__ out_i) {
   extern __shared__ __align__(16) unsigned char fsm[];
@@ -459,23 +471,33 @@ tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus
   __syncthreads();
   if (tid == 0) { int a = 0; for (int pt = 1; pt <= parts; ++pt) { a += seg_off[pt]; seg_off[pt] = a; } }
   __syncthreads();
-  const unsigned int n_raw = (unsigned int)seg_off[parts];
-  if (seg_bad || n_raw > (unsigned)CAND_CAP || n_raw < (unsigned)k) {  // overflow (or impossible underflow): exact fallback
+  if (seg_bad) {  // a segment overflowed: exact fallback
     if (tid == 0) overflow[row] = 1;
     return;
   }
-  const int n = (int)n_raw;
   for (int t = tid; t < d; t += 256) qs[t] = q[(long long)row * d + t];
-  // one warp per segment: coalesced copies
+  // one warp per segment: read its octet records, keep the true survivors (>= the filter threshold, real row)
+  __shared__ int n_sh;
+  if (tid == 0) n_sh = 0;
+  __syncthreads();
+  const float thr_row = thr[row];
   for (int pt = tid >> 5; pt < parts; pt += 8) {
-    const int b0 = seg_off[pt], c = seg_off[pt + 1] - b0;
-    const uint2* seg = cand + ((long long)row * parts + pt) * cap_part;
-    for (int t = tid & 31; t < c; t += 32) {
-      uint2 e = seg[t];
-      // rows of the zero-padded last tile are not candidates: sink them below everything
-      as[b0 + t] = (e.y < (unsigned long long)N) ? __uint_as_float(e.x) : -INFINITY;
-      ai[b0 + t] = e.y;
+    const int c = seg_off[pt + 1] - seg_off[pt];
+    const long long seg = ((long long)row * parts + pt) * cap_part;
+    for (int t = tid & 31; t < c * 8; t += 32) {
+      const float sc = cand_s[seg * 8 + t];
+      const unsigned int ix = cand_i[seg + (t >> 3)] + (unsigned int)(t & 7);
+      if (sc >= thr_row && ix < (unsigned long long)N) {
+        const int pos = atomicAdd(&n_sh, 1);
+        if (pos < CAND_CAP) { as[pos] = sc; ai[pos] = ix; }
+      }
     }
+  }
+  __syncthreads();
+  const int n = n_sh;
+  if (n > CAND_CAP || n < k) {
+    if (tid == 0) overflow[row] = 1;
+    return;
   }
   if (tid == 0) m_sh = 0;
   __syncthreads();
@@ -523,6 +545,21 @@ tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus
       for (int kk = 0; kk < d; ++kk) acc = fmaf(qs[kk], __ldg(c + kk), acc);
     }
     es[t] = acc;
+  }
+  __syncthreads();
+  if (m <= 512) {
+    // rank sort: the band is small, so each thread ranks its entry against all others (broadcast reads, no
+    // barriers) and writes it straight to its output slot.  Ranks are unique: (score, index) is a total order.
+    for (int t = tid; t < m; t += 256) {
+      const float s_t = es[t]; const long long i_t = ei[t];
+      int rank = 0;
+      for (int j = 0; j < m; ++j) rank += better(es[j], ei[j], s_t, i_t) ? 1 : 0;
+      if (rank < k) {
+        out_s[(long long)row * k + rank] = s_t;
+        out_i[(long long)row * k + rank] = i_t + index_offset;
+      }
+    }
+    return;
   }
   int P2 = 2; while (P2 < m) P2 <<= 1;
   for (int t = m + tid; t < P2; t += 256) { es[t] = -INFINITY; ei[t] = LLONG_MAX; }
@@ -609,7 +646,7 @@ static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
   pl.parts_sample = parts < pl.n_sample ? parts : pl.n_sample;
   pl.parts_full = (long long)parts < pl.n_tiles ? parts : (int)pl.n_tiles;
   {
-    int cp = 2 * CAND_CAP / (pl.parts_full * 2);  // (part, column-half) segments add up to ~2x the per-query capacity
+    int cp = 2 * CAND_CAP / (pl.parts_full * 2);  // octet records: (part, column-half) segments add up to ~2x the per-query capacity
     int p2 = 32; while (p2 * 2 <= cp && p2 < CAND_CAP) p2 <<= 1;
     pl.cap_part = p2;
   }
@@ -624,7 +661,7 @@ static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
   pl.o_count = take((size_t)pl.Qp * pl.parts_full * 2 * 4);
   pl.o_ovf = take((size_t)pl.Qp * 4);
   pl.o_binmax = take((size_t)pl.Qp * pl.bins_ld * 4);
-  pl.o_cand = take((size_t)pl.Qp * pl.parts_full * 2 * pl.cap_part * 8);
+  pl.o_cand = take((size_t)pl.Qp * pl.parts_full * 2 * pl.cap_part * (8 * 4 + 4));
   pl.total = o;
   return true;
 }
@@ -728,7 +765,8 @@ extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, 
   unsigned int* count = (unsigned int*)(w + pl.o_count);
   unsigned int* ovf = (unsigned int*)(w + pl.o_ovf);
   float* binmax = (float*)(w + pl.o_binmax);
-  uint2* cand = (uint2*)(w + pl.o_cand);
+  float* cand_s = (float*)(w + pl.o_cand);
+  unsigned int* cand_i = (unsigned int*)(w + pl.o_cand + (size_t)pl.Qp * pl.parts_full * 2 * pl.cap_part * 32);
   const IndexHeader* hdr = (const IndexHeader*)index_buf;
   const unsigned char* cimg = (const unsigned char*)index_buf + HEADER_BYTES;
 
@@ -749,7 +787,7 @@ extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, 
   }
   ScanParams sp{};
   sp.qimg = qimg; sp.cimg = cimg; sp.Q = Q; sp.N = N; sp.nqb = pl.nqb; sp.n_tiles = pl.n_tiles;
-  sp.binmax = binmax; sp.bins_ld = pl.bins_ld; sp.thr = thr; sp.count = count; sp.cand = cand; sp.cap_part = pl.cap_part;
+  sp.binmax = binmax; sp.bins_ld = pl.bins_ld; sp.thr = thr; sp.count = count; sp.cand_s = cand_s; sp.cand_i = cand_i; sp.cap_part = pl.cap_part;
   sp.idesc = IDESC_F16_M128_N128 | (use_bf16() ? ((1u << 7) | (1u << 10)) : 0u);
   prof_mark(st, 1);
   // (1) sampled pass -> bin maxima -> k-th largest -> threshold
@@ -772,7 +810,7 @@ extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, 
     size_t smem = (size_t)FIN_MAXM * 12 + (size_t)CAND_CAP * 8 + (size_t)d * 4 + 16;
     static bool attr = false;
     if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
-    tc_finalize_kernel<<<(unsigned)Q, 256, smem, st>>>(q, corpus, d, k, index_offset, count, cand, pl.parts_full * 2, pl.cap_part,
+    tc_finalize_kernel<<<(unsigned)Q, 256, smem, st>>>(q, corpus, d, k, index_offset, count, cand_s, cand_i, pl.parts_full * 2, pl.cap_part,
                                                      cut, thr, N, ovf, out_scores, (long long*)out_idx);
     TFRS_LAUNCH_CHECK();
   }
