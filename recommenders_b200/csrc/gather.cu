@@ -28,6 +28,7 @@ gather_kernel(GatherParams p, long long n, float* __restrict__ out, long long ou
   const long long rows = p.rows[t];
   const int dim = p.dim[t];
   const int lanes = VEC ? dim / 4 : dim;  // work items per row
+  const int lane_shift = (lanes & (lanes - 1)) == 0 ? (31 - __clz(lanes)) : -1;
   const long long total = n * lanes;
   const long long stride = (long long)gridDim.x * GT_THREADS;
   long long w = (long long)blockIdx.x * GT_THREADS + threadIdx.x;
@@ -40,7 +41,10 @@ gather_kernel(GatherParams p, long long n, float* __restrict__ out, long long ou
       long long e = w + u * stride;
       dst[u] = -1;
       if (e < total) {
-        long long i = e / lanes; int l = (int)(e - i * lanes);
+        long long i; int l;
+        if (lane_shift >= 0) { i = e >> lane_shift; l = (int)(e & (lanes - 1)); }   // lanes is a power of two: no division
+        else if (total < (1ll << 32)) { unsigned int e32 = (unsigned int)e; i = e32 / (unsigned int)lanes; l = (int)(e32 - (unsigned int)i * lanes); }
+        else { i = e / lanes; l = (int)(e - i * lanes); }
         long long r = (long long)ids[i];
         bool ok = (r >= 0 && r < rows);
         if (VEC) {

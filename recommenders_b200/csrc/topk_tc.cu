@@ -441,7 +441,7 @@ tc_threshold_kernel(const float* __restrict__ binmax, int bins_ld, int n_bins, i
 
 constexpr int FIN_MAXM = 1024;  // survivors re-scored exactly per query (band around tau)
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus, int d, int k, long long index_offset,
                    const unsigned int* __restrict__ count, const float* __restrict__ cand_s,
                    const unsigned int* __restrict__ cand_i, int parts, int cap_part,
@@ -526,14 +526,16 @@ tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus
   for (int t = tid; t < m; t += 256) {
     const float* c = corpus + ei[t] * d;
     float acc = 0.f;
-    if (d == 64) {  // all 16 loads in flight, then the canonical chain
-      float4 cv[16];
+    if ((d & 31) == 0) {  // 8 loads (128 B) in flight per step, then the canonical chain on them
+      for (int kk = 0; kk < d; kk += 32) {
+        float4 cv[8];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) cv[u] = __ldg(reinterpret_cast<const float4*>(c) + u);
+        for (int u = 0; u < 8; ++u) cv[u] = __ldg(reinterpret_cast<const float4*>(c + kk) + u);
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        acc = fmaf(qs[4 * u], cv[u].x, acc); acc = fmaf(qs[4 * u + 1], cv[u].y, acc);
-        acc = fmaf(qs[4 * u + 2], cv[u].z, acc); acc = fmaf(qs[4 * u + 3], cv[u].w, acc);
+        for (int u = 0; u < 8; ++u) {
+          acc = fmaf(qs[kk + 4 * u], cv[u].x, acc); acc = fmaf(qs[kk + 4 * u + 1], cv[u].y, acc);
+          acc = fmaf(qs[kk + 4 * u + 2], cv[u].z, acc); acc = fmaf(qs[kk + 4 * u + 3], cv[u].w, acc);
+        }
       }
     } else if ((d & 3) == 0) {
       for (int kk = 0; kk < d; kk += 4) {
