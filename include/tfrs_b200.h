@@ -114,6 +114,12 @@ int tfrs_profile_read(float* stage_ms, int* calls);
 int tfrs_topk_merge(const float* scores, const int64_t* idx, int n_lists, int64_t Q, int k_in, int k_out,
                     float* out_scores, int64_t* out_idx, void* stream);
 
+/* Same merge for lists that sit `list_stride_*` elements apart (e.g. the receive buffer of the single
+ * all-gather, where every rank's block is [scores | indices]). */
+int tfrs_topk_merge_strided(const float* scores, const int64_t* idx, int64_t list_stride_scores,
+                            int64_t list_stride_idx, int n_lists, int64_t Q, int k_in, int k_out,
+                            float* out_scores, int64_t* out_idx, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Score helpers (exact fp32, canonical fmaf chain, one owner thread per output).
  * tfrs_sgemm_f32: C[M,N] (+)= opA(A) . opB(B); opA(m,k) = transA ? A[k*lda+m] : A[m*lda+k],
@@ -169,6 +175,18 @@ size_t tfrs_cross_bwd_workspace_bytes(int64_t B, int D);
 int tfrs_cross_bwd_f32(const float* x0, const float* x, const float* W, const float* prod, const float* dout,
                        int64_t B, int D, int64_t ld, float diag_scale, float* dx0, float* dx, float* dW,
                        float* dbias, void* ws, size_t ws_bytes, void* stream);
+
+/* K5 on the tensor cores (forward): the same cross formula as tfrs_cross_fwd_f32, computed as one tcgen05
+ * GEMM on exactly-rescaled fp16 hi/lo splits of x and W (3 MMAs per K step, fp32 accumulation in TMEM;
+ * ~2^-21 relative error, inside the 1e-5 bar) with the formula fused in the epilogue.
+ * tfrs_cross_tc_weight_build turns W [D,D] ([in,out]) into the K-major image of W^T; rebuild it whenever
+ * W changes.  `ws` holds the per-call image of x. */
+size_t tfrs_cross_tc_weight_bytes(int D);
+int tfrs_cross_tc_weight_build(const float* W, int D, void* wbuf, size_t bytes, void* stream);
+size_t tfrs_cross_tc_workspace_bytes(int64_t B, int D);
+int tfrs_cross_tc_fwd_f32(const float* x0, const float* x, const void* wbuf, const float* bias, int64_t B, int D,
+                          int64_t ld, float diag_scale, float* out, float* prod, void* ws, size_t ws_bytes,
+                          void* stream);
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,7 @@ _SIGNATURES = {
     "tfrs_profile_enable": (c_i, [c_i]),
     "tfrs_profile_read": (c_i, [c_p, c_p]),
     "tfrs_topk_merge": (c_i, [c_p, c_p, c_i, c_l, c_i, c_i, c_p, c_p, c_p]),
+    "tfrs_topk_merge_strided": (c_i, [c_p, c_p, c_l, c_l, c_i, c_l, c_i, c_i, c_p, c_p, c_p]),
     "tfrs_sgemm_f32": (c_i, [c_i, c_i, c_l, c_l, c_l, c_p, c_l, c_p, c_l, c_p, c_l, c_i, c_p]),
     "tfrs_rowwise_dot_f32": (c_i, [c_p, c_p, c_l, c_i, c_p, c_p]),
     "tfrs_inbatch_softmax_workspace_bytes": (c_sz, [c_l, c_l, c_i]),
@@ -47,6 +48,10 @@ _SIGNATURES = {
     "tfrs_sparse_adagrad_workspace_bytes": (c_sz, [c_l, c_i]),
     "tfrs_sparse_adagrad_f32": (c_i, [c_p, c_p, c_l, c_i, c_p, c_i, c_l, c_p, c_f, c_f, c_i, c_p, c_sz, c_p]),
     "tfrs_cross_fwd_f32": (c_i, [c_p, c_p, c_p, c_p, c_l, c_i, c_l, c_f, c_p, c_p, c_p]),
+    "tfrs_cross_tc_weight_bytes": (c_sz, [c_i]),
+    "tfrs_cross_tc_weight_build": (c_i, [c_p, c_i, c_p, c_sz, c_p]),
+    "tfrs_cross_tc_workspace_bytes": (c_sz, [c_l, c_i]),
+    "tfrs_cross_tc_fwd_f32": (c_i, [c_p, c_p, c_p, c_p, c_l, c_i, c_l, c_f, c_p, c_p, c_p, c_sz, c_p]),
     "tfrs_cross_bwd_workspace_bytes": (c_sz, [c_l, c_i]),
     "tfrs_cross_bwd_f32": (c_i, [c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_l, c_f, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
 }

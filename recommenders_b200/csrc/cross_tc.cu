@@ -1,0 +1,306 @@
+// cross_tc.cu -- K5 on the tensor cores: DCN-v2 cross layer forward (layers/feature_interaction/dcn.py:176-186)
+//   out = x0 * (x . W + bias + diag_scale * x) + x        W [D,D] in Keras [in,out] layout
+// as ONE tcgen05 GEMM with the whole cross formula in the epilogue.
+//
+// fp32 parity on fp16 tensor cores: each operand is rescaled by an exact power of two and split into
+//   v = hi + lo,  hi = fp16(v), lo = fp16(v - hi)            (|v - hi - lo| <= 2^-22 |v|)
+// and the product is accumulated in fp32 (TMEM) as  hi_x*hi_w + lo_x*hi_w + hi_x*lo_w  (the dropped
+// lo*lo term is 2^-22 relative), i.e. 3 MMAs per K step -- ~2^-21 relative error, inside the 1e-5 bar.
+//
+// Layout: x (per call) and W^T (once per weight version) are turned into UMMA SWIZZLE_128B K-major tile
+// images, 128 rows x 64 K-elements per 16 KB block, hi block then lo block per K slab (32 KB per slab).
+// Kernel: persistent CTAs (1/SM, 640 threads) over (256-row block, 128-column tile) pairs; per K slab a
+// bulk-TMA stage brings 2x(hi,lo) A blocks + (hi,lo) of W^T (96 KB); 24 MMAs (2 A blocks x 3 products x 4
+// K16 steps) accumulate into a 128-column TMEM buffer per A block (2 buffers -> next tile's MMAs overlap the
+// epilogue).  16 epilogue warps read 64 columns of one row each, fetch x0 / x / bias, apply the formula and
+// store fp32.
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace tfrs {
+namespace tc {
+
+constexpr int CX_THREADS = 640;
+constexpr int CX_STAGES = 2;
+constexpr int CX_STAGE_BYTES = 6 * 16384;  // A: 2 blocks x (hi, lo); B: (hi, lo)
+constexpr int CX_TARGET_EXP = 14;
+
+struct CxStats { unsigned int amax_bits; int exp; int pad0, pad1; };
+
+// max |element| of a [rows, D] matrix with row stride ld
+__global__ void __launch_bounds__(256)
+cx_amax_kernel(const float* __restrict__ src, long long rows, int D, long long ld, CxStats* __restrict__ st) {
+  const long long total = rows * D;
+  float a = 0.f;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    long long r = e / D; int c = (int)(e - r * D);
+    a = fmaxf(a, fabsf(src[r * ld + c]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+  if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(&st->amax_bits, __float_as_uint(a));
+}
+__global__ void cx_exp_kernel(CxStats* st) {
+  const float amax = __uint_as_float(st->amax_bits);
+  int x = 0;
+  const bool ok = amax > 0.f && amax < INFINITY;
+  if (ok) (void)frexpf(amax, &x);
+  st->exp = ok ? (CX_TARGET_EXP - x) : 0;
+}
+
+// fp32 [rows, D] (row stride ld; or its transpose when TRANSPOSED) -> hi/lo fp16 tile image:
+//   tile t (128 rows) : slab s (64 K) : {hi, lo} : 128 rows x 128 B, 16-byte chunk j of row r at chunk j ^ (r & 7)
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(256)
+cx_split_image_kernel(const float* __restrict__ src, long long rows, int K, long long ld, int kb, long long n_tiles,
+                      const CxStats* __restrict__ st, unsigned char* __restrict__ img) {
+  const int sexp = st->exp;
+  const long long total = n_tiles * 128 * (long long)kb * 8;
+  for (long long w = (long long)blockIdx.x * 256 + threadIdx.x; w < total; w += (long long)gridDim.x * 256) {
+    const int chunk = (int)(w % (kb * 8));
+    const long long row = w / (kb * 8);
+    const int slab = chunk / 8, cj = chunk % 8;
+    const int r = (int)(row % 128);
+    const long long tile = row / 128;
+    const int k0 = slab * 64 + cj * 8;
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float f = 0.f;
+      if (row < rows && k0 + j < K) f = TRANSPOSED ? src[(long long)(k0 + j) * ld + row] : src[row * ld + k0 + j];
+      const float v = ldexpf(f, sexp);
+      const __half h = __float2half_rn(v);
+      hi[j] = h;
+      lo[j] = __float2half_rn(v - __half2float(h));
+    }
+    unsigned char* dst = img + (tile * kb + slab) * 32768 + r * 128 + ((cj ^ (r & 7)) * 16);
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(dst + 16384) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+struct CrossParams {
+  const unsigned char* ximg;  // [n_mtiles128][kb][hi|lo][16 KB]
+  const unsigned char* wimg;  // [n_ntiles128][kb][hi|lo][16 KB]   (W^T: rows = output column)
+  const CxStats* xst; const CxStats* wst;
+  const float* x0; const float* x; const float* bias; float diag;
+  float* out; float* prod;
+  long long B; int D; long long ld;
+  int kb, n_mb, n_nt;
+};
+
+__global__ void __launch_bounds__(CX_THREADS, 1)
+cross_tc_kernel(const CrossParams p) {
+  extern __shared__ __align__(1024) unsigned char cx_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cx_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CX_STAGES * CX_STAGE_BYTES);
+  uint64_t* full = bars;                  // [CX_STAGES]
+  uint64_t* empty = bars + CX_STAGES;     // [CX_STAGES]
+  uint64_t* t_full = empty + CX_STAGES;   // [2]
+  uint64_t* t_empty = t_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long n_tiles = (long long)p.n_mb * p.n_nt;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < CX_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 16); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const long long mb = t / p.n_nt; const int nt = (int)(t % p.n_nt);
+        for (int ks = 0; ks < p.kb; ++ks) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], CX_STAGE_BYTES);
+          unsigned char* s = smem + stage * CX_STAGE_BYTES;
+          bulk_g2s(s, p.ximg + ((mb * 2 + 0) * p.kb + ks) * 32768, 32768, &full[stage]);
+          bulk_g2s(s + 32768, p.ximg + ((mb * 2 + 1) * p.kb + ks) * 32768, 32768, &full[stage]);
+          bulk_g2s(s + 65536, p.wimg + ((long long)nt * p.kb + ks) * 32768, 32768, &full[stage]);
+          if (++stage == CX_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t tphase = (it >> 1) & 1;
+        mbar_wait(&t_empty[buf], tphase ^ 1);
+        for (int ks = 0; ks < p.kb; ++ks) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(smem + stage * CX_STAGE_BYTES);
+          const uint64_t b_hi = make_smem_desc(sb + 65536), b_lo = make_smem_desc(sb + 65536 + 16384);
+#pragma unroll
+          for (int ab = 0; ab < 2; ++ab) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)((ab * 2 + buf) * 128);
+            const uint64_t a_hi = make_smem_desc(sb + ab * 32768), a_lo = make_smem_desc(sb + ab * 32768 + 16384);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t o = (uint64_t)(k4 * 2);
+              umma_f16(d_tmem, a_hi + o, b_hi + o, IDESC_F16_M128_N128, (uint32_t)((ks | k4) != 0));
+              umma_f16(d_tmem, a_lo + o, b_hi + o, IDESC_F16_M128_N128, 1u);
+              umma_f16(d_tmem, a_hi + o, b_lo + o, IDESC_F16_M128_N128, 1u);
+            }
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == CX_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&t_full[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int half = ew >> 3, ab = (ew >> 2) & 1, quad = ew & 3;
+    const float unscale = ldexpf(1.0f, -(p.xst->exp + p.wst->exp));
+    const bool vec_ok = (p.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.x0) |
+                                            reinterpret_cast<uintptr_t>(p.out)) % 16 == 0) &&
+                        (!p.prod || reinterpret_cast<uintptr_t>(p.prod) % 16 == 0);
+    int it = 0;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t tphase = (it >> 1) & 1;
+      const long long mb = t / p.n_nt; const int nt = (int)(t % p.n_nt);
+      const long long row = mb * 256 + ab * 128 + quad * 32 + lane;
+      const int n0 = nt * 128 + half * 64;
+      mbar_wait(&t_full[buf], tphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ab * 2 + buf) * 128 + half * 64);
+      uint32_t r[64];
+      tmem_ld64(taddr, r);
+      tmem_ld_wait64(r);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[buf]);
+      if (row < p.B && n0 < p.D) {
+        const long long o = row * p.ld + n0;
+        if (vec_ok && n0 + 64 <= p.D) {
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            const float4 xv = *reinterpret_cast<const float4*>(p.x + o + j);
+            const float4 x0v = *reinterpret_cast<const float4*>(p.x0 + o + j);
+            float4 pv;
+            pv.x = __uint_as_float(r[j]) * unscale; pv.y = __uint_as_float(r[j + 1]) * unscale;
+            pv.z = __uint_as_float(r[j + 2]) * unscale; pv.w = __uint_as_float(r[j + 3]) * unscale;
+            if (p.bias) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              pv.x += bv.x; pv.y += bv.y; pv.z += bv.z; pv.w += bv.w;
+            }
+            if (p.diag != 0.f) { pv.x += p.diag * xv.x; pv.y += p.diag * xv.y; pv.z += p.diag * xv.z; pv.w += p.diag * xv.w; }
+            if (p.prod) *reinterpret_cast<float4*>(p.prod + o + j) = pv;
+            float4 ov;
+            ov.x = x0v.x * pv.x + xv.x; ov.y = x0v.y * pv.y + xv.y; ov.z = x0v.z * pv.z + xv.z; ov.w = x0v.w * pv.w + xv.w;
+            *reinterpret_cast<float4*>(p.out + o + j) = ov;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            if (n0 + j < p.D) {
+              const float xv = p.x[o + j];
+              float pv = __uint_as_float(r[j]) * unscale;
+              if (p.bias) pv += __ldg(p.bias + n0 + j);
+              if (p.diag != 0.f) pv += p.diag * xv;
+              if (p.prod) p.prod[o + j] = pv;
+              p.out[o + j] = p.x0[o + j] * pv + xv;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+static size_t cx_img_bytes(long long rows, int K) {
+  return (size_t)ceil_div(rows, 128) * ceil_div(K, 64) * 32768;
+}
+
+}  // namespace tc
+}  // namespace tfrs
+using namespace tfrs;
+using namespace tfrs::tc;
+
+// ---- W image (built once per weight version, by the caller) --------------------------------------------
+extern "C" size_t tfrs_cross_tc_weight_bytes(int D) {
+  if (D <= 0) return 0;
+  return 1024 + cx_img_bytes(D, D);
+}
+extern "C" int tfrs_cross_tc_weight_build(const float* W, int D, void* wbuf, size_t bytes, void* stream) {
+  TFRS_CHECK_ARG(W && wbuf && D > 0, "cross_tc_weight_build: bad arguments");
+  TFRS_CHECK_ARG(bytes >= tfrs_cross_tc_weight_bytes(D), "cross_tc_weight_build: buffer too small");
+  TFRS_CHECK_ARG((reinterpret_cast<uintptr_t>(wbuf) & 15) == 0, "cross_tc_weight_build: buffer must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  CxStats* ws = (CxStats*)wbuf;
+  TFRS_CUDA(cudaMemsetAsync(wbuf, 0, 1024, st));
+  cx_amax_kernel<<<64, 256, 0, st>>>(W, D, D, D, ws);
+  TFRS_LAUNCH_CHECK();
+  cx_exp_kernel<<<1, 1, 0, st>>>(ws);
+  TFRS_LAUNCH_CHECK();
+  const int kb = (int)ceil_div(D, 64);
+  const long long nt = ceil_div(D, 128);
+  const long long chunks = nt * 128 * kb * 8;
+  // rows of the image = output columns n; element (n, k) = W[k, n]  -> transposed read
+  cx_split_image_kernel<true><<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(W, D, D, D, kb, nt, ws, (unsigned char*)wbuf + 1024);
+  TFRS_LAUNCH_CHECK();
+  return TFRS_OK;
+}
+
+extern "C" size_t tfrs_cross_tc_workspace_bytes(int64_t B, int D) {
+  if (B <= 0 || D <= 0) return 0;
+  return 1024 + cx_img_bytes(ceil_div(B, 256) * 256, D);
+}
+
+extern "C" int tfrs_cross_tc_fwd_f32(const float* x0, const float* x, const void* wbuf, const float* bias, int64_t B, int D,
+                                     int64_t ld, float diag_scale, float* out, float* prod, void* ws, size_t ws_bytes,
+                                     void* stream) {
+  TFRS_CHECK_ARG(x0 && x && wbuf && out, "cross_tc_fwd: NULL pointer");
+  TFRS_CHECK_ARG(B > 0 && D > 0 && ld >= D, "cross_tc_fwd: bad shape");
+  TFRS_CHECK_ARG(diag_scale >= 0.f, "`diag_scale` should be non-negative. Got `diag_scale` = %g", diag_scale);
+  if (!ws || ws_bytes < tfrs_cross_tc_workspace_bytes(B, D)) { set_error("cross_tc_fwd: workspace too small"); return TFRS_ERR_WORKSPACE_TOO_SMALL; }
+  TFRS_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "cross_tc_fwd: workspace must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  CxStats* xs = (CxStats*)ws;
+  unsigned char* ximg = (unsigned char*)ws + 1024;
+  const int kb = (int)ceil_div(D, 64);
+  const int n_mb = (int)ceil_div(B, 256);
+  const int n_nt = (int)ceil_div(D, 128);
+  TFRS_CUDA(cudaMemsetAsync(ws, 0, 1024, st));
+  cx_amax_kernel<<<(unsigned)(148 * 8), 256, 0, st>>>(x, B, D, ld, xs);
+  TFRS_LAUNCH_CHECK();
+  cx_exp_kernel<<<1, 1, 0, st>>>(xs);
+  TFRS_LAUNCH_CHECK();
+  {
+    const long long chunks = (long long)n_mb * 2 * 128 * kb * 8;
+    unsigned blocks = (unsigned)(ceil_div(chunks, 256) < (1 << 20) ? ceil_div(chunks, 256) : (1 << 20));
+    cx_split_image_kernel<false><<<blocks, 256, 0, st>>>(x, B, D, ld, kb, (long long)n_mb * 2, xs, ximg);
+    TFRS_LAUNCH_CHECK();
+  }
+  CrossParams p{};
+  p.ximg = ximg; p.wimg = (const unsigned char*)wbuf + 1024; p.xst = xs; p.wst = (const CxStats*)wbuf;
+  p.x0 = x0; p.x = x; p.bias = bias; p.diag = diag_scale; p.out = out; p.prod = prod;
+  p.B = B; p.D = D; p.ld = ld; p.kb = kb; p.n_mb = n_mb; p.n_nt = n_nt;
+  const size_t smem = (size_t)CX_STAGES * CX_STAGE_BYTES + 1024 + 256;
+  static bool attr = false;
+  if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(cross_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  long long tiles = (long long)n_mb * n_nt;
+  int grid = sm_count(); if (grid > tiles) grid = (int)tiles;
+  cross_tc_kernel<<<grid, CX_THREADS, smem, st>>>(p);
+  TFRS_LAUNCH_CHECK();
+  return TFRS_OK;
+}

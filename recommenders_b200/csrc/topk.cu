@@ -22,12 +22,13 @@ struct ScanProvider {
 
 struct MergeProvider {
   const float* s; const long long* idx; int n_lists; long long Q; int k_in;
+  long long stride_s, stride_i;  // elements between consecutive lists
   __device__ void begin(int, void*) {}
   __device__ long long count(int) const { return (long long)n_lists * k_in; }
   __device__ void get(int row, long long t, float& sc, long long& i) const {
     int l = (int)(t / k_in), r = (int)(t % k_in);
-    long long o = ((long long)l * Q + row) * k_in + r;
-    sc = s[o]; i = idx[o];
+    long long o = (long long)row * k_in + r;
+    sc = s[(long long)l * stride_s + o]; i = idx[(long long)l * stride_i + o];
   }
 };
 
@@ -136,7 +137,20 @@ extern "C" int tfrs_topk_merge(const float* scores, const int64_t* idx, int n_li
   TFRS_CHECK_ARG(scores && idx && out_scores && out_idx, "topk_merge: NULL pointer");
   long long tot = (long long)n_lists * k_in;
   int ko = (int)(k_out < tot ? k_out : tot);
-  MergeProvider prov{scores, (const long long*)idx, n_lists, Q, k_in};
+  MergeProvider prov{scores, (const long long*)idx, n_lists, Q, k_in, Q * k_in, Q * k_in};
+  return launch_row_topk(prov, Q, ko, out_scores, (long long*)out_idx, k_out, (cudaStream_t)stream);
+}
+
+extern "C" int tfrs_topk_merge_strided(const float* scores, const int64_t* idx, int64_t list_stride_scores,
+                                       int64_t list_stride_idx, int n_lists, int64_t Q, int k_in, int k_out,
+                                       float* out_scores, int64_t* out_idx, void* stream) {
+  TFRS_CHECK_ARG(n_lists > 0 && Q >= 0 && k_in > 0 && k_out > 0 && k_out <= 2048, "topk_merge_strided: bad shape");
+  TFRS_CHECK_ARG(list_stride_scores >= Q * k_in && list_stride_idx >= Q * k_in, "topk_merge_strided: list strides overlap");
+  if (Q == 0) return TFRS_OK;
+  TFRS_CHECK_ARG(scores && idx && out_scores && out_idx, "topk_merge_strided: NULL pointer");
+  long long tot = (long long)n_lists * k_in;
+  int ko = (int)(k_out < tot ? k_out : tot);
+  MergeProvider prov{scores, (const long long*)idx, n_lists, Q, k_in, list_stride_scores, list_stride_idx};
   return launch_row_topk(prov, Q, ko, out_scores, (long long*)out_idx, k_out, (cudaStream_t)stream);
 }
 

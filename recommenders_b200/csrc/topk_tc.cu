@@ -476,20 +476,33 @@ tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus
     return;
   }
   for (int t = tid; t < d; t += 256) qs[t] = q[(long long)row * d + t];
-  // one warp per segment: read its octet records, keep the true survivors (>= the filter threshold, real row)
+  // All records of all segments as one flat list of 8*total values: every thread issues its loads in batches
+  // of four independent (index, score) pairs, then keeps the true survivors (>= filter threshold, real row).
   __shared__ int n_sh;
   if (tid == 0) n_sh = 0;
   __syncthreads();
   const float thr_row = thr[row];
-  for (int pt = tid >> 5; pt < parts; pt += 8) {
-    const int c = seg_off[pt + 1] - seg_off[pt];
-    const long long seg = ((long long)row * parts + pt) * cap_part;
-    for (int t = tid & 31; t < c * 8; t += 32) {
-      const float sc = cand_s[seg * 8 + t];
-      const unsigned int ix = cand_i[seg + (t >> 3)] + (unsigned int)(t & 7);
-      if (sc >= thr_row && ix < (unsigned long long)N) {
+  const int total_vals = seg_off[parts] * 8;
+  for (int v0 = tid; v0 < total_vals; v0 += 4 * 256) {
+    float sc[4]; unsigned int ix[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int v = v0 + u * 256;
+      sc[u] = -INFINITY; ix[u] = 0xffffffffu;
+      if (v < total_vals) {
+        const int rec = v >> 3;
+        int lo = 0, hi = parts;  // largest pt with seg_off[pt] <= rec
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_off[mid] <= rec) lo = mid; else hi = mid; }
+        const long long at = ((long long)row * parts + lo) * cap_part + (rec - seg_off[lo]);
+        ix[u] = __ldg(cand_i + at) + (unsigned int)(v & 7);
+        sc[u] = __ldg(cand_s + at * 8 + (v & 7));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (sc[u] >= thr_row && ix[u] < (unsigned long long)N) {
         const int pos = atomicAdd(&n_sh, 1);
-        if (pos < CAND_CAP) { as[pos] = sc; ai[pos] = ix; }
+        if (pos < CAND_CAP) { as[pos] = sc[u]; ai[pos] = ix[u]; }
       }
     }
   }

@@ -280,11 +280,11 @@ class BruteForce(TopK):
     if self.use_tensor_cores and cands.shape[0] >= ops.TC_MIN_N and cands.shape[1] <= 128:
       self._tc_index = ops.index_build(cands)
 
-  def _local_topk(self, queries: Tensor, k: int, offset: int):
+  def _local_topk(self, queries: Tensor, k: int, offset: int, out=None):
     if self._tc_index is not None and ops.tc_supported(queries.shape[0], self._candidates.shape[0],
                                                        self._candidates.shape[1], k):
-      return ops.topk_tc(queries, self._candidates, self._tc_index, k, index_offset=offset)
-    return ops.topk_scan(queries, self._candidates, k, index_offset=offset)
+      return ops.topk_tc(queries, self._candidates, self._tc_index, k, index_offset=offset, out=out)
+    return ops.topk_scan(queries, self._candidates, k, index_offset=offset, out=out)
 
   def call(self, queries, k: Optional[int] = None):
     k = k if k is not None else self._k
@@ -304,11 +304,26 @@ class BruteForce(TopK):
     return values, _gather_identifiers(self._identifiers, indices)
 
   def _sharded_topk(self, queries: Tensor, k: int):
+    """Local scan -> ONE all-gather of every rank's packed [scores | indices] block -> merge kernel reading the
+    receive buffer in place.  The local scan writes straight into the send block (no packing kernels)."""
+    import torch.distributed as dist
     offset, group = self._shard
+    world = dist.get_world_size(group)
+    Q = queries.shape[0]
     k_local = min(k, self._candidates.shape[0])
-    s, i = self._local_topk(queries, k_local, offset)
-    all_s, all_i = allgather_topk(s, i, k, group)
-    return ops.topk_merge(all_s, all_i, k)
+    if k_local < k:  # a shard smaller than k: rectangular lists via the generic (padding) path
+      s, i = self._local_topk(queries, k_local, offset)
+      all_s, all_i = allgather_topk(s, i, k, group)
+      return ops.topk_merge(all_s, all_i, k)
+    idx_off = (Q * k * 4 + 7) // 8 * 8
+    block = idx_off + Q * k * 8
+    send = torch.empty(block, dtype=torch.uint8, device=queries.device)
+    out_s = send[:Q * k * 4].view(torch.float32).view(Q, k)
+    out_i = send[idx_off:].view(torch.int64).view(Q, k)
+    self._local_topk(queries, k, offset, out=(out_s, out_i))
+    recv = torch.empty(world * block, dtype=torch.uint8, device=queries.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return ops.topk_merge_packed(recv, world, Q, k, k, idx_off, block)
 
   def is_exact(self) -> bool:
     return True

@@ -65,7 +65,8 @@ def gather(tables: Sequence[torch.Tensor], ids: Sequence[torch.Tensor], out: Opt
 # K2 top-k
 # ------------------------------------------------------------------------------------------------
 def topk_scan(q: torch.Tensor, corpus: torch.Tensor, k: int, index_offset: int = 0,
-              state: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+              state: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+              out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
   """Exact brute-force top-k (CUDA-core path) with optional carried state. Returns ([Q,k_out] f32, [Q,k_out] i64)."""
   q = f32c(q, "queries"); corpus = f32c(corpus, "candidates")
   if q.dim() != 2 or corpus.dim() != 2 or q.shape[1] != corpus.shape[1]:
@@ -76,8 +77,11 @@ def topk_scan(q: torch.Tensor, corpus: torch.Tensor, k: int, index_offset: int =
     st_s = f32c(state[0], "state scores"); st_i = require_cuda(state[1], "state idx").to(torch.int64).contiguous()
     st_k = st_s.shape[1]
   k_out = min(k, st_k + N)
-  out_s = torch.empty((Q, k), dtype=torch.float32, device=q.device)
-  out_i = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+  if out is None:
+    out_s = torch.empty((Q, k), dtype=torch.float32, device=q.device)
+    out_i = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+  else:
+    out_s, out_i = out  # contiguous [Q, k] f32 / i64 views supplied by the caller
   if Q == 0 or k_out == 0:
     return out_s[:, :0], out_i[:, :0]
   wsb = lib().tfrs_topk_scan_workspace_bytes(Q, N, d, k)
@@ -99,19 +103,36 @@ def index_build(corpus: torch.Tensor) -> torch.Tensor:
   return buf
 
 
-def topk_tc(q: torch.Tensor, corpus: torch.Tensor, index_buf: torch.Tensor, k: int, index_offset: int = 0
-            ) -> Tuple[torch.Tensor, torch.Tensor]:
+def topk_tc(q: torch.Tensor, corpus: torch.Tensor, index_buf: torch.Tensor, k: int, index_offset: int = 0,
+            out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
   """tcgen05 screening + exact rescoring; bit-identical to topk_scan."""
   q = f32c(q, "queries"); corpus = f32c(corpus, "candidates")
   Q, d = q.shape; N = corpus.shape[0]
-  out_s = torch.empty((Q, k), dtype=torch.float32, device=q.device)
-  out_i = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+  if out is None:
+    out_s = torch.empty((Q, k), dtype=torch.float32, device=q.device)
+    out_i = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+  else:
+    out_s, out_i = out
   if Q == 0:
     return out_s, out_i
   wsb = lib().tfrs_topk_tc_workspace_bytes(Q, N, d, k)
   ws = workspace(wsb, q.device, "tc")
   check(lib().tfrs_topk_tc_f32(ptr(q), Q, ptr(corpus), ptr(index_buf), N, d, k, index_offset, ptr(out_s),
                                ptr(out_i), ptr(ws), ws.numel(), stream()), "topk_tc")
+  return out_s, out_i
+
+
+def topk_merge_packed(gathered: torch.Tensor, n_lists: int, Q: int, k_in: int, k: int, idx_byte_offset: int,
+                      block_bytes: int) -> Tuple[torch.Tensor, torch.Tensor]:
+  """Merge the receive buffer of the sharded scan's single all-gather: `n_lists` blocks of `block_bytes`, each
+  [scores f32 [Q,k_in] | pad | indices i64 [Q,k_in] at idx_byte_offset]."""
+  k_out = min(k, n_lists * k_in)
+  out_s = torch.empty((Q, k_out), dtype=torch.float32, device=gathered.device)
+  out_i = torch.empty((Q, k_out), dtype=torch.int64, device=gathered.device)
+  base = gathered.data_ptr()
+  check(lib().tfrs_topk_merge_strided(ctypes.c_void_p(base), ctypes.c_void_p(base + idx_byte_offset), block_bytes // 4,
+                                      block_bytes // 8, n_lists, Q, k_in, k_out, ptr(out_s), ptr(out_i), stream()),
+        "topk_merge_strided")
   return out_s, out_i
 
 
@@ -294,6 +315,26 @@ def sparse_adagrad_(table: torch.Tensor, accum: torch.Tensor, ids: torch.Tensor,
 # ------------------------------------------------------------------------------------------------
 # K5 cross
 # ------------------------------------------------------------------------------------------------
+# Cross layers at least this large run their forward GEMM on the tensor cores (fp16 hi/lo split, fp32 accumulate).
+CROSS_TC_MIN_B = 1024
+CROSS_TC_MIN_D = 64
+_cross_w_cache = {}
+
+
+def cross_weight_image(W: torch.Tensor) -> torch.Tensor:
+  """K-major fp16 hi/lo image of W^T for the tensor-core Cross kernel; cached per (storage, version)."""
+  key = (W.data_ptr(), W._version, tuple(W.shape), W.device.index)
+  hit = _cross_w_cache.get(W.data_ptr())
+  if hit is not None and hit[0] == key:
+    return hit[1]
+  D = W.shape[0]
+  nb = lib().tfrs_cross_tc_weight_bytes(D)
+  buf = torch.empty(nb, dtype=torch.uint8, device=W.device)
+  check(lib().tfrs_cross_tc_weight_build(ptr(W), D, ptr(buf), nb, stream()), "cross_tc_weight_build")
+  _cross_w_cache[W.data_ptr()] = (key, buf)
+  return buf
+
+
 class _Cross(torch.autograd.Function):
 
   @staticmethod
@@ -304,8 +345,15 @@ class _Cross(torch.autograd.Function):
     out = torch.empty_like(x0)
     need_grad = any(ctx.needs_input_grad[:4])
     prod = torch.empty_like(x0) if need_grad else None
-    check(lib().tfrs_cross_fwd_f32(ptr(x0), ptr(x), ptr(W), ptr(b), B, D, D, c_f(diag_scale), ptr(out), ptr(prod),
-                                   stream()), "cross_fwd")
+    if B >= CROSS_TC_MIN_B and D >= CROSS_TC_MIN_D and W.shape == (D, D):
+      wimg = cross_weight_image(W)
+      wsb = lib().tfrs_cross_tc_workspace_bytes(B, D)
+      ws = workspace(wsb, x0.device, "cross_tc")
+      check(lib().tfrs_cross_tc_fwd_f32(ptr(x0), ptr(x), ptr(wimg), ptr(b), B, D, D, c_f(diag_scale), ptr(out), ptr(prod),
+                                        ptr(ws), ws.numel(), stream()), "cross_tc_fwd")
+    else:
+      check(lib().tfrs_cross_fwd_f32(ptr(x0), ptr(x), ptr(W), ptr(b), B, D, D, c_f(diag_scale), ptr(out), ptr(prod),
+                                     stream()), "cross_fwd")
     if need_grad:
       ctx.save_for_backward(x0, x, W, prod)
     ctx.diag = diag_scale

@@ -143,7 +143,8 @@ def test_inbatch_softmax_loss_and_grads(ops, B, C, d, temp, weighted):
     assert err <= 1e-5 * max(1.0, np.abs(ref).max())
 
 
-@pytest.mark.parametrize("B,D,diag,bias", [(1, 3, 0.0, False), (257, 845, 0.0, True), (100, 64, 1.0, True), (5000, 130, 0.5, False)])
+@pytest.mark.parametrize("B,D,diag,bias", [(1, 3, 0.0, False), (257, 845, 0.0, True), (100, 64, 1.0, True), (5000, 130, 0.5, False),
+                                           (4096, 845, 0.0, True), (1500, 64, 0.25, False), (2048, 200, 0.0, True)])
 def test_cross_fwd_bwd(ops, B, D, diag, bias):
   """1e-5 relative to the output scale (fp32 kernel vs float64 oracle)."""
   rng = np.random.RandomState(B + D)
@@ -168,3 +169,29 @@ def test_errors_cross_the_abi(ops):
     ops.topk_scan(cu(np.zeros((2, 4), np.float32)), cu(np.zeros((8, 4), np.float32)), 5000)
   with pytest.raises(RuntimeError):
     ops.topk_scan(torch.zeros((2, 4)), torch.zeros((8, 4)), 3)  # CPU tensors: no fallback
+
+
+def test_cross_tensor_core_matches_cuda_core(ops):
+  """The tcgen05 Cross forward (fp16 hi/lo split) against the exact CUDA-core kernel: 1e-5 of the output scale."""
+  rng = np.random.RandomState(0)
+  B, D = 8192, 845
+  x0 = cu(rng.uniform(size=(B, D)).astype(np.float32)); x = cu(rng.normal(size=(B, D)).astype(np.float32))
+  W = cu((rng.normal(size=(D, D)) * 0.05).astype(np.float32)); b = cu(rng.normal(size=(D,)).astype(np.float32))
+  tc = ops.cross(x0, x, W, b, 0.5)
+  old = ops.CROSS_TC_MIN_B
+  try:
+    ops.CROSS_TC_MIN_B = 1 << 60
+    ref = ops.cross(x0, x, W, b, 0.5)
+  finally:
+    ops.CROSS_TC_MIN_B = old
+  err = float((tc - ref).abs().max()); scale = float(ref.abs().max())
+  assert err <= 1e-5 * scale, (err, scale)
+  # weights updated in place -> the cached image must be rebuilt
+  W.mul_(2.0)
+  tc2 = ops.cross(x0, x, W, b, 0.5)
+  ops.CROSS_TC_MIN_B = 1 << 60
+  try:
+    ref2 = ops.cross(x0, x, W, b, 0.5)
+  finally:
+    ops.CROSS_TC_MIN_B = old
+  assert float((tc2 - ref2).abs().max()) <= 1e-5 * float(ref2.abs().max())
