@@ -28,18 +28,20 @@ constexpr int CX_TARGET_EXP = 14;
 
 struct CxStats { unsigned int amax_bits; int exp; int pad0, pad1; };
 
-// max |element| of a [rows, D] matrix with row stride ld
+// max |element| of a [rows, D] matrix with row stride ld (one warp per row: coalesced, no index division)
 __global__ void __launch_bounds__(256)
 cx_amax_kernel(const float* __restrict__ src, long long rows, int D, long long ld, CxStats* __restrict__ st) {
-  const long long total = rows * D;
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * 256) >> 5;
   float a = 0.f;
-  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
-    long long r = e / D; int c = (int)(e - r * D);
-    a = fmaxf(a, fabsf(src[r * ld + c]));
+  for (long long r = warp; r < rows; r += nwarps) {
+    const float* p = src + r * ld;
+    for (int c = lane; c < D; c += 32) a = fmaxf(a, fabsf(p[c]));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
-  if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(&st->amax_bits, __float_as_uint(a));
+  if (lane == 0 && a > 0.f) atomicMax(&st->amax_bits, __float_as_uint(a));
 }
 __global__ void cx_exp_kernel(CxStats* st) {
   const float amax = __uint_as_float(st->amax_bits);
@@ -57,9 +59,11 @@ cx_split_image_kernel(const float* __restrict__ src, long long rows, int K, long
                       const CxStats* __restrict__ st, unsigned char* __restrict__ img) {
   const int sexp = st->exp;
   const long long total = n_tiles * 128 * (long long)kb * 8;
+  const unsigned int cpr = (unsigned int)(kb * 8);  // 16-byte chunks per row
   for (long long w = (long long)blockIdx.x * 256 + threadIdx.x; w < total; w += (long long)gridDim.x * 256) {
-    const int chunk = (int)(w % (kb * 8));
-    const long long row = w / (kb * 8);
+    long long row; int chunk;
+    if (total < (1ll << 32)) { const unsigned int w32 = (unsigned int)w; const unsigned int r32 = w32 / cpr; row = r32; chunk = (int)(w32 - r32 * cpr); }
+    else { row = w / cpr; chunk = (int)(w - row * cpr); }
     const int slab = chunk / 8, cj = chunk % 8;
     const int r = (int)(row % 128);
     const long long tile = row / 128;

@@ -161,6 +161,16 @@ struct EpiStoreSplit {  // partial[z][m*ldc + n] = v   (deterministic split-K; r
   }
 };
 
+// out[e] (+)= sum_z partial[z][e]  (z ascending: deterministic split-K reduction)
+static __global__ void __launch_bounds__(256)
+reduce_splits_kernel(const float* __restrict__ partial, long long elems, int splits, float* __restrict__ out) {
+  long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (e >= elems) return;
+  float a = partial[e];
+  for (int z = 1; z < splits; ++z) a += partial[(long long)z * elems + e];
+  out[e] = a;
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // Host launcher.  splits > 1 => K is cut into `splits` ranges (multiple of 16), blockIdx.z = range.

@@ -68,19 +68,21 @@ __global__ void __launch_bounds__(1024) sm_reduce_loss(const float* __restrict__
   if (threadIdx.x == 0) loss[0] = (float)red[0];
 }
 
+// one CTA per row of the block: G = (exp(s - lse) - [j == i]) * w_i * grad_loss * invT, in place
 __global__ void __launch_bounds__(SM_THREADS)
 sm_make_grad(float* __restrict__ S, long long ldS, int C, int R, long long row0, float invT,
              const float* __restrict__ w, const float* __restrict__ lse, const float* __restrict__ grad_loss) {
-  const long long total = (long long)R * C;
+  const int r = blockIdx.x;
+  if (r >= R) return;
+  const long long gi = row0 + r;
   const float gl = grad_loss ? grad_loss[0] : 1.0f;
-  for (long long e = (long long)blockIdx.x * SM_THREADS + threadIdx.x; e < total; e += (long long)gridDim.x * SM_THREADS) {
-    int r = (int)(e / C); int j = (int)(e - (long long)r * C);
-    long long gi = row0 + r;
-    float s = S[(long long)r * ldS + j] * invT;
-    float p = expf(s - lse[gi]);
+  const float scale = (w ? w[gi] : 1.0f) * gl * invT;
+  const float l = lse[gi];
+  float* s = S + (long long)r * ldS;
+  for (int j = threadIdx.x; j < C; j += SM_THREADS) {
+    float p = expf(s[j] * invT - l);
     if (j == gi) p -= 1.0f;
-    float wi = w ? w[gi] : 1.0f;
-    S[(long long)r * ldS + j] = p * (wi * gl * invT);
+    s[j] = p * scale;
   }
 }
 
@@ -103,11 +105,12 @@ static long long sm_rows_per_block(long long B, long long C) {
 }  // namespace tfrs
 using namespace tfrs;
 
+constexpr int SM_DQ_SPLITS = 8;  // dq = G . c is skinny (N = d): split K = C so that all SMs have work
+
 extern "C" size_t tfrs_inbatch_softmax_workspace_bytes(int64_t B, int64_t C, int d) {
-  (void)d;
   if (B <= 0 || C <= 0) return 256;
   long long R = sm_rows_per_block(B, C);
-  return align_up((size_t)R * C * 4, 256) + align_up((size_t)B * 4, 256);
+  return align_up((size_t)R * C * 4, 256) + align_up((size_t)B * 4, 256) + align_up((size_t)SM_DQ_SPLITS * R * d * 4, 256);
 }
 
 static int sm_check(const float* q, const float* c, int64_t B, int64_t C, int d, void* ws, size_t ws_bytes) {
@@ -156,13 +159,19 @@ extern "C" int tfrs_inbatch_softmax_bwd(const float* q, const float* c, int64_t 
     int rows = (int)((B - r0) < R ? (B - r0) : R);
     rc = launch_sgemm<false, true>(q + r0 * d, d, c, d, rows, (int)C, d, 1, EpiStore{S, C}, st);
     if (rc) return rc;
-    long long total = (long long)rows * C;
-    unsigned blocks = (unsigned)(ceil_div(total, SM_THREADS) < 148 * 16 ? ceil_div(total, SM_THREADS) : 148 * 16);
-    sm_make_grad<<<blocks, SM_THREADS, 0, st>>>(S, C, (int)C, rows, r0, inv_temperature, sample_weight, lse, grad_loss);
+    sm_make_grad<<<(unsigned)rows, SM_THREADS, 0, st>>>(S, C, (int)C, rows, r0, inv_temperature, sample_weight, lse, grad_loss);
     TFRS_LAUNCH_CHECK();
-    // dq[r0:r0+rows] = G . c      (M=rows, N=d, K=C; A=G row-major, B=c [C,d] not transposed)
-    rc = launch_sgemm<false, false>(S, C, c, d, rows, d, (int)C, 1, EpiStore{dq + r0 * d, d}, st);
-    if (rc) return rc;
+    // dq[r0:r0+rows] = G . c      (M=rows, N=d, K=C; A=G row-major, B=c [C,d] not transposed); deterministic split-K
+    {
+      float* part = (float*)((unsigned char*)ws + align_up((size_t)R * C * 4, 256) + align_up((size_t)B * 4, 256));
+      const long long elems = (long long)rows * d;
+      rc = launch_sgemm<false, false>(S, C, c, d, rows, d, (int)C, SM_DQ_SPLITS, EpiStoreSplit{part, d, elems}, st);
+      if (rc) return rc;
+      int kps = (int)(ceil_div(ceil_div(C, SM_DQ_SPLITS), SG_BK) * SG_BK);
+      int used = (int)ceil_div(C, kps);
+      reduce_splits_kernel<<<(unsigned)ceil_div(elems, 256), 256, 0, st>>>(part, elems, used, dq + r0 * d);
+      TFRS_LAUNCH_CHECK();
+    }
     // dc (+)= G^T . q_blk         (M=C, N=d, K=rows; A=G read transposed)
     rc = launch_sgemm<true, false>(S, C, q + r0 * d, d, (int)C, d, rows, 1, EpiAccum{dc, d, r0 > 0}, st);
     if (rc) return rc;

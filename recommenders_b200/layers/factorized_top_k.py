@@ -180,6 +180,7 @@ class Streaming(TopK):
     self._handle_incomplete_batches = handle_incomplete_batches
     self._num_parallel_calls = num_parallel_calls
     self._sorted = sorted_order
+    self._coalesce_rows = 65536
     self.register_buffer("_counter", torch.zeros((), dtype=torch.int32), persistent=False)
 
   def index_from_dataset(self, candidates) -> "TopK":
@@ -204,6 +205,19 @@ class Streaming(TopK):
     counter = 0
     id_chunks = []
     has_ids = False
+    pending, pending_rows = [], 0
+
+    def flush():
+      nonlocal state, counter, pending, pending_rows
+      if not pending:
+        return
+      emb = pending[0] if len(pending) == 1 else torch.cat(pending, 0)
+      # the scan kernel takes the carried state and numbers the rows with the running counter
+      # (enumerate_rows, :474-485); ties resolve to the lower running index == state first (:462-463).
+      state = ops.topk_scan(queries, emb, k, index_offset=counter, state=state)
+      counter += int(emb.shape[0])
+      pending, pending_rows = [], 0
+
     for el in self._candidates:
       _check_candidates_with_identifiers(el)
       if isinstance(el, tuple):
@@ -214,10 +228,12 @@ class Streaming(TopK):
         emb = el
       if not self._handle_incomplete_batches and emb.shape[0] < k:
         raise _wrap_batch_too_small_error(k)
-      # the scan kernel takes the carried state and numbers the chunk's rows with the running counter
-      # (enumerate_rows, :474-485); ties resolve to the lower running index == state first (:462-463).
-      state = ops.topk_scan(queries, emb, k, index_offset=counter, state=state)
-      counter += int(emb.shape[0])
+      # Dataset batches are tiny (README uses 128): coalesce them into >= 64K-row scans.  The result is the
+      # same as merging per batch -- indices are the running row numbers either way.
+      pending.append(emb); pending_rows += int(emb.shape[0])
+      if pending_rows >= self._coalesce_rows:
+        flush()
+    flush()
     self._counter.fill_(counter)
     scores, idx = state
     if has_ids:

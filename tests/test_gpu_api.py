@@ -300,3 +300,22 @@ def test_two_tower_model_trains(tfrs):
   assert "loss" in ev
   with pytest.raises(NotImplementedError):
     tfrs.Model().compute_loss(None)
+
+
+def test_streaming_carried_state_across_scans(tfrs):
+  """Streaming.call (factorized_top_k.py:404-509): many small batches, several coalesced scans, carried [Q,k] state;
+  the result must equal one brute-force scan, with and without identifiers."""
+  rng = np.random.RandomState(3)
+  cand = rng.normal(size=(5000, 16)).astype(np.float32); q = rng.normal(size=(33, 16)).astype(np.float32)
+  es, ei = orc.topk_scan(q, cand, 50)
+  ds = tfrs.data.Dataset.from_tensor_slices(cu(cand)).batch(37)
+  layer = tfrs.layers.factorized_top_k.Streaming(k=50).index_from_dataset(ds)
+  layer._coalesce_rows = 300   # ~17 scans with carried state
+  s, i = layer(cu(q))
+  np.testing.assert_array_equal(i.cpu().numpy(), ei.astype(np.int32)); np.testing.assert_array_equal(s.cpu().numpy(), es)
+  ids = (np.arange(5000) * 7 + 3).astype(np.int64)
+  ds2 = tfrs.data.Dataset.from_tensor_slices((cu(ids), cu(cand))).batch(41)
+  layer2 = tfrs.layers.factorized_top_k.Streaming(k=50).index_from_dataset(ds2)
+  layer2._coalesce_rows = 1
+  s2, i2 = layer2(cu(q))
+  np.testing.assert_array_equal(i2.cpu().numpy(), ids[ei]); np.testing.assert_array_equal(s2.cpu().numpy(), es)

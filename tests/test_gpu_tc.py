@@ -108,3 +108,23 @@ def test_bruteforce_layer_uses_tc_and_shards(ops):
     parts.append(l._local_topk(q, 50, lo))
   ms, mi = ops.topk_merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), 50)
   assert torch.equal(mi, ei) and torch.equal(ms, es)
+
+
+def test_packed_allgather_block_merge(ops):
+  """The merge kernel reads the all-gather receive buffer in place: blocks of [scores f32 | pad | indices i64]."""
+  import recommenders_b200 as tfrs
+  c = _rand((90000, 64), 21); q = _rand((333, 64), 22); k = 100
+  es, ei = ops.topk_scan(q, c, k)
+  Q = q.shape[0]
+  idx_off = (Q * k * 4 + 7) // 8 * 8
+  block = idx_off + Q * k * 8
+  world = 3
+  recv = torch.empty(world * block, dtype=torch.uint8, device="cuda")
+  for r in range(world):
+    lo, hi = tfrs.layers.factorized_top_k.shard_bounds(90000, r, world)
+    blk = recv[r * block:(r + 1) * block]
+    out_s = blk[:Q * k * 4].view(torch.float32).view(Q, k); out_i = blk[idx_off:].view(torch.int64).view(Q, k)
+    layer = tfrs.layers.factorized_top_k.BruteForce(k=k).index(c[lo:hi])
+    layer._local_topk(q, k, lo, out=(out_s, out_i))
+  ms, mi = ops.topk_merge_packed(recv, world, Q, k, k, idx_off, block)
+  assert torch.equal(mi, ei) and torch.equal(ms, es)
