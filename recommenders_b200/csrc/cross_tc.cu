@@ -171,15 +171,11 @@ cross_tc_kernel(const CrossParams p) {
     const int ew = warp - 4;
     const int half = ew >> 3, ab = (ew >> 2) & 1, quad = ew & 3;
     const float unscale = ldexpf(1.0f, -(p.xst->exp + p.wst->exp));
-    const bool vec_ok = (p.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.x0) |
-                                            reinterpret_cast<uintptr_t>(p.out)) % 16 == 0) &&
-                        (!p.prod || reinterpret_cast<uintptr_t>(p.prod) % 16 == 0);
     int it = 0;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t tphase = (it >> 1) & 1;
       const long long mb = t / p.n_nt; const int nt = (int)(t % p.n_nt);
-      const long long row = mb * 256 + ab * 128 + quad * 32 + lane;
       const int n0 = nt * 128 + half * 64;
       mbar_wait(&t_full[buf], tphase);
       tc_fence_after();
@@ -190,36 +186,41 @@ cross_tc_kernel(const CrossParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[buf]);
-      if (row < p.B && n0 < p.D) {
-        const long long o = row * p.ld + n0;
-        if (vec_ok && n0 + 64 <= p.D) {
+      // The accumulators arrive one ROW per lane (32 rows x 64 columns per warp).  Global memory wants the other
+      // orientation, so each 32x32 block is transposed in registers (5 butterfly stages of shfl.xor): afterwards
+      // lane l holds COLUMN l of the 32 rows and every x / x0 / out access of the warp is one contiguous 128-byte
+      // segment of a row (row-per-lane accesses would touch 32 DRAM pages per instruction).
+      const long long row_base = mb * 256 + ab * 128 + quad * 32;
 #pragma unroll
-          for (int j = 0; j < 64; j += 4) {
-            const float4 xv = *reinterpret_cast<const float4*>(p.x + o + j);
-            const float4 x0v = *reinterpret_cast<const float4*>(p.x0 + o + j);
-            float4 pv;
-            pv.x = __uint_as_float(r[j]) * unscale; pv.y = __uint_as_float(r[j + 1]) * unscale;
-            pv.z = __uint_as_float(r[j + 2]) * unscale; pv.w = __uint_as_float(r[j + 3]) * unscale;
-            if (p.bias) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              pv.x += bv.x; pv.y += bv.y; pv.z += bv.z; pv.w += bv.w;
+      for (int blk = 0; blk < 2; ++blk) {
+        // transposed in place inside r[blk*32 .. blk*32+31] (raw bits; unscaled when used)
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+          const bool upper = (lane & s) != 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if ((i & s) == 0) {
+              const uint32_t lo_v = r[blk * 32 + i], hi_v = r[blk * 32 + (i | s)];
+              const uint32_t recv = __shfl_xor_sync(0xffffffffu, upper ? lo_v : hi_v, s);
+              r[blk * 32 + i] = upper ? recv : lo_v;
+              r[blk * 32 + (i | s)] = upper ? hi_v : recv;
             }
-            if (p.diag != 0.f) { pv.x += p.diag * xv.x; pv.y += p.diag * xv.y; pv.z += p.diag * xv.z; pv.w += p.diag * xv.w; }
-            if (p.prod) *reinterpret_cast<float4*>(p.prod + o + j) = pv;
-            float4 ov;
-            ov.x = x0v.x * pv.x + xv.x; ov.y = x0v.y * pv.y + xv.y; ov.z = x0v.z * pv.z + xv.z; ov.w = x0v.w * pv.w + xv.w;
-            *reinterpret_cast<float4*>(p.out + o + j) = ov;
           }
-        } else {
+        }
+        // now a[j] = accumulator of row (row_base + j), column (n0 + blk*32 + lane)
+        const int col = n0 + blk * 32 + lane;
+        if (col < p.D) {
+          const float bcol = p.bias ? __ldg(p.bias + col) : 0.f;
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            if (n0 + j < p.D) {
-              const float xv = p.x[o + j];
-              float pv = __uint_as_float(r[j]) * unscale;
-              if (p.bias) pv += __ldg(p.bias + n0 + j);
+          for (int j = 0; j < 32; ++j) {
+            const long long rr = row_base + j;
+            if (rr < p.B) {
+              const long long o = rr * p.ld + col;
+              const float xv = p.x[o];
+              float pv = __uint_as_float(r[blk * 32 + j]) * unscale + bcol;
               if (p.diag != 0.f) pv += p.diag * xv;
-              if (p.prod) p.prod[o + j] = pv;
-              p.out[o + j] = p.x0[o + j] * pv + xv;
+              if (p.prod) p.prod[o] = pv;
+              p.out[o] = p.x0[o] * pv + xv;
             }
           }
         }

@@ -9,7 +9,7 @@ namespace tfrs {
 
 constexpr int GT_MAX_TABLES = 32;
 constexpr int GT_THREADS = 256;
-constexpr int GT_ROWS_PER_THREAD = 8;  // independent loads in flight per thread
+constexpr int GT_ROWS_PER_THREAD = 4;  // independent loads in flight per thread
 
 struct GatherParams {
   const float* table[GT_MAX_TABLES];

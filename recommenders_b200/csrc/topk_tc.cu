@@ -379,9 +379,22 @@ __device__ unsigned int block_kth_largest(KeyAt key_at, int n, int k, unsigned i
   for (int shift = 24; shift >= 0; shift -= 8) {
     for (int t = threadIdx.x; t < 256; t += blockDim.x) hist[t] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      unsigned int key = key_at(i);
-      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    for (int ib = 0; ib < n; ib += blockDim.x) {  // block-uniform trip count (warp votes inside)
+      const int i = ib + threadIdx.x;
+      unsigned int key = 0; bool in = false;
+      if (i < n) { key = key_at(i); in = (key & mask) == prefix; }
+      const unsigned int bin = (key >> shift) & 255u;
+      // scores cluster: in the high-byte passes a whole warp usually lands in ONE bin -> one atomic, not 32 serialised
+      const unsigned int vote = __ballot_sync(0xffffffffu, in);
+      if (vote) {
+        const int leader = __ffs(vote) - 1;
+        const unsigned int bin0 = __shfl_sync(0xffffffffu, bin, leader);
+        if (__all_sync(0xffffffffu, !in || bin == bin0)) {
+          if ((threadIdx.x & 31) == leader) atomicAdd(&hist[bin0], (unsigned int)__popc(vote));
+        } else if (in) {
+          atomicAdd(&hist[bin], 1u);
+        }
+      }
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -483,11 +496,11 @@ tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus
   __syncthreads();
   const float thr_row = thr[row];
   const int total_vals = seg_off[parts] * 8;
-  for (int v0 = tid; v0 < total_vals; v0 += 4 * 256) {
+  for (int vb = 0; vb < total_vals; vb += 4 * 256) {  // block-uniform trip count (warp votes inside)
     float sc[4]; unsigned int ix[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int v = v0 + u * 256;
+      const int v = vb + tid + u * 256;
       sc[u] = -INFINITY; ix[u] = 0xffffffffu;
       if (v < total_vals) {
         const int rec = v >> 3;
@@ -500,9 +513,15 @@ tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (sc[u] >= thr_row && ix[u] < (unsigned long long)N) {
-        const int pos = atomicAdd(&n_sh, 1);
-        if (pos < CAND_CAP) { as[pos] = sc[u]; ai[pos] = ix[u]; }
+      // warp-aggregated append: one shared-memory atomic per warp instead of one per survivor
+      const bool keep = sc[u] >= thr_row && ix[u] < (unsigned long long)N;
+      const unsigned int vote = __ballot_sync(0xffffffffu, keep);
+      if (vote) {
+        int base = 0;
+        if ((tid & 31) == 0) base = atomicAdd(&n_sh, __popc(vote));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const int pos = base + __popc(vote & ((1u << (tid & 31)) - 1u));
+        if (keep && pos < CAND_CAP) { as[pos] = sc[u]; ai[pos] = ix[u]; }
       }
     }
   }
@@ -523,10 +542,16 @@ tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus
     if (tid == 0) overflow[row] = 1;
     return;
   }
-  for (int t = tid; t < n; t += 256) {
-    if (as[t] >= lim) {
-      int pos = atomicAdd(&m_sh, 1);
-      if (pos < FIN_MAXM) ei[pos] = (long long)ai[t];
+  for (int tb = 0; tb < n; tb += 256) {
+    const int t = tb + tid;
+    const bool keep = t < n && as[t] >= lim;
+    const unsigned int vote = __ballot_sync(0xffffffffu, keep);
+    if (vote) {
+      int base = 0;
+      if ((tid & 31) == 0) base = atomicAdd(&m_sh, __popc(vote));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const int pos = base + __popc(vote & ((1u << (tid & 31)) - 1u));
+      if (keep && pos < FIN_MAXM) ei[pos] = (long long)ai[t];
     }
   }
   __syncthreads();
