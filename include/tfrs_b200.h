@@ -73,7 +73,7 @@ int tfrs_gather_f32(const float* const* tables, const int64_t* rows, const int32
  *                         done once at index() time (BruteForce.index, factorized_top_k.py:540-584).
  * tfrs_topk_tc_f32        tcgen05 screening GEMM (fp16 in / fp32 accumulate in TMEM) with a fused
  *                         threshold filter, then exact fp32 rescoring of the survivors -- same
- *                         bit-exact result as tfrs_topk_scan_f32.  Needs d <= 128, k <= 512 and a
+ *                         bit-exact result as tfrs_topk_scan_f32.  Needs d <= 128, k <= 256 and a
  *                         corpus of at least ~256*k rows (tfrs_topk_tc_workspace_bytes returns 0
  *                         outside the supported range; callers then use tfrs_topk_scan_f32).
  * ------------------------------------------------------------------------------------------- */

@@ -211,16 +211,29 @@ cross_tc_kernel(const CrossParams p) {
         const int col = n0 + blk * 32 + lane;
         if (col < p.D) {
           const float bcol = p.bias ? __ldg(p.bias + col) : 0.f;
+          // rows in batches of 4: all 8 loads are issued before the first store (out may alias x for the
+          // compiler, so it would otherwise serialise load -> store -> load per row)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const long long rr = row_base + j;
-            if (rr < p.B) {
+          for (int j0 = 0; j0 < 32; j0 += 4) {
+            float xv[4], x0v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const long long rr = row_base + j0 + u;
+              const bool ok = rr < p.B;
               const long long o = rr * p.ld + col;
-              const float xv = p.x[o];
-              float pv = __uint_as_float(r[blk * 32 + j]) * unscale + bcol;
-              if (p.diag != 0.f) pv += p.diag * xv;
-              if (p.prod) p.prod[o] = pv;
-              p.out[o] = p.x0[o] * pv + xv;
+              xv[u] = ok ? __ldg(p.x + o) : 0.f;
+              x0v[u] = ok ? __ldg(p.x0 + o) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const long long rr = row_base + j0 + u;
+              if (rr < p.B) {
+                const long long o = rr * p.ld + col;
+                float pv = __uint_as_float(r[blk * 32 + j0 + u]) * unscale + bcol;
+                if (p.diag != 0.f) pv += p.diag * xv[u];
+                if (p.prod) p.prod[o] = pv;
+                p.out[o] = x0v[u] * pv + xv[u];
+              }
             }
           }
         }

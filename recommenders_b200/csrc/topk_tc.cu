@@ -379,22 +379,9 @@ __device__ unsigned int block_kth_largest(KeyAt key_at, int n, int k, unsigned i
   for (int shift = 24; shift >= 0; shift -= 8) {
     for (int t = threadIdx.x; t < 256; t += blockDim.x) hist[t] = 0;
     __syncthreads();
-    for (int ib = 0; ib < n; ib += blockDim.x) {  // block-uniform trip count (warp votes inside)
-      const int i = ib + threadIdx.x;
-      unsigned int key = 0; bool in = false;
-      if (i < n) { key = key_at(i); in = (key & mask) == prefix; }
-      const unsigned int bin = (key >> shift) & 255u;
-      // scores cluster: in the high-byte passes a whole warp usually lands in ONE bin -> one atomic, not 32 serialised
-      const unsigned int vote = __ballot_sync(0xffffffffu, in);
-      if (vote) {
-        const int leader = __ffs(vote) - 1;
-        const unsigned int bin0 = __shfl_sync(0xffffffffu, bin, leader);
-        if (__all_sync(0xffffffffu, !in || bin == bin0)) {
-          if ((threadIdx.x & 31) == leader) atomicAdd(&hist[bin0], (unsigned int)__popc(vote));
-        } else if (in) {
-          atomicAdd(&hist[bin], 1u);
-        }
-      }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      unsigned int key = key_at(i);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -666,7 +653,7 @@ static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
   pl.nqb = (int)ceil_div(Q, QBLK);
   pl.Qp = (long long)pl.nqb * QBLK;
   if (pl.kb > 2) return false;          // d > 128: smem budget (A blocks + ring) not laid out yet
-  if (k > 512 || N >= (1ll << 31)) return false;
+  if (k > 256 || N >= (1ll << 31)) return false;   // survivor capacity (CAND_CAP) is sized for ~4k + band entries per query
   // sample every stride-th tile; keep at least 4k bins so the k-th largest bin max is a tight bound
   const long long full_tiles = N / TILE_N;  // the zero-padded last tile is never sampled (its 0 scores are not candidates)
   if (full_tiles < 1) return false;

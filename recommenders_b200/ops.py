@@ -15,7 +15,7 @@ from ._ffi import c_f, c_i, c_l, c_sz, check, f32c, lib, ptr, require_cuda, stre
 
 # Corpora at least this large go through the tensor-core screening path when an index image exists.
 TC_MIN_N = 16384
-TC_MAX_K = 512
+TC_MAX_K = 256
 
 
 # ------------------------------------------------------------------------------------------------

@@ -39,7 +39,8 @@ def _check(ops, q, c, k, offset=0, oracle_rows=32, max_fallback=0):
 
 
 @pytest.mark.parametrize("Q,N,d,k", [(300, 40000, 64, 100), (256, 32768, 64, 100), (1000, 200000, 128, 10),
-                                     (17, 65537, 33, 50), (513, 100001, 100, 128), (4096, 131072, 64, 100)])
+                                     (17, 65537, 33, 50), (513, 100001, 100, 128), (4096, 131072, 64, 100),
+                                     (1, 300000, 64, 1), (700, 400000, 64, 256)])
 def test_tc_matches_exact(ops, Q, N, d, k):
   _check(ops, _rand((Q, d), 2), _rand((N, d), 1), k)
 
