@@ -476,39 +476,43 @@ tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus
     return;
   }
   for (int t = tid; t < d; t += 256) qs[t] = q[(long long)row * d + t];
-  // All records of all segments as one flat list of 8*total values: every thread issues its loads in batches
-  // of four independent (index, score) pairs, then keeps the true survivors (>= filter threshold, real row).
+  // All octet records of all segments as one flat list: a thread takes a record (one segment lookup, one index
+  // load, two 16-byte score loads), keeps the true survivors (>= filter threshold, real row) and the warp
+  // reserves its output slots with a shuffle prefix sum + ONE shared atomic.
   __shared__ int n_sh;
   if (tid == 0) n_sh = 0;
   __syncthreads();
   const float thr_row = thr[row];
-  const int total_vals = seg_off[parts] * 8;
-  for (int vb = 0; vb < total_vals; vb += 4 * 256) {  // block-uniform trip count (warp votes inside)
-    float sc[4]; unsigned int ix[4];
+  const int total_rec = seg_off[parts];
+  const int lane_id = tid & 31;
+  for (int rb = 0; rb < total_rec; rb += 256) {  // block-uniform trip count (warp shuffles inside)
+    const int rec = rb + tid;
+    float sc[8]; unsigned int ix0 = 0; int cnt = 0; unsigned int keep = 0;
+    if (rec < total_rec) {
+      int lo = 0, hi = parts;  // largest pt with seg_off[pt] <= rec
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_off[mid] <= rec) lo = mid; else hi = mid; }
+      const long long at = ((long long)row * parts + lo) * cap_part + (rec - seg_off[lo]);
+      ix0 = __ldg(cand_i + at);
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(cand_s + at * 8));
+      const float4 s1 = __ldg(reinterpret_cast<const float4*>(cand_s + at * 8) + 1);
+      sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int v = vb + tid + u * 256;
-      sc[u] = -INFINITY; ix[u] = 0xffffffffu;
-      if (v < total_vals) {
-        const int rec = v >> 3;
-        int lo = 0, hi = parts;  // largest pt with seg_off[pt] <= rec
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_off[mid] <= rec) lo = mid; else hi = mid; }
-        const long long at = ((long long)row * parts + lo) * cap_part + (rec - seg_off[lo]);
-        ix[u] = __ldg(cand_i + at) + (unsigned int)(v & 7);
-        sc[u] = __ldg(cand_s + at * 8 + (v & 7));
-      }
+      for (int j = 0; j < 8; ++j)
+        if (sc[j] >= thr_row && (unsigned long long)(ix0 + j) < (unsigned long long)N) { keep |= 1u << j; ++cnt; }
     }
+    int incl = cnt;  // warp inclusive prefix sum of the per-lane survivor counts
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      // warp-aggregated append: one shared-memory atomic per warp instead of one per survivor
-      const bool keep = sc[u] >= thr_row && ix[u] < (unsigned long long)N;
-      const unsigned int vote = __ballot_sync(0xffffffffu, keep);
-      if (vote) {
-        int base = 0;
-        if ((tid & 31) == 0) base = atomicAdd(&n_sh, __popc(vote));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const int pos = base + __popc(vote & ((1u << (tid & 31)) - 1u));
-        if (keep && pos < CAND_CAP) { as[pos] = sc[u]; ai[pos] = ix[u]; }
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane_id >= o) incl += v; }
+    const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane_id == 0 && warp_total) base = atomicAdd(&n_sh, warp_total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    int pos = base + incl - cnt;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (keep & (1u << j)) {
+        if (pos < CAND_CAP) { as[pos] = sc[j]; ai[pos] = ix0 + j; }
+        ++pos;
       }
     }
   }

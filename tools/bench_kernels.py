@@ -71,7 +71,7 @@ def cross3():
 with torch.no_grad():
   t = timeit(cross3, iters=5 if not quick else 3, warm=2)
 flops = 3 * 2.0 * B * Dc * Dc
-out["cfg5_cross_fwd_3layers"] = {"seconds": t, "TFLOPs": flops / t / 1e12, "flops": flops, "path": "exact fp32 CUDA-core SGEMM + fused epilogue"}
+out["cfg5_cross_fwd_3layers"] = {"seconds": t, "TFLOPs": flops / t / 1e12, "flops": flops, "path": "tcgen05 fp16 hi/lo split GEMM + fused epilogue (B>=1024), exact CUDA-core SGEMM otherwise"}
 del tables, ids_sets, act, x0, Ws
 
 # ---- config 3: two-tower step pieces, 10M users / 1M items, d=64, batch 16384
