@@ -195,3 +195,18 @@ def test_cross_tensor_core_matches_cuda_core(ops):
   finally:
     ops.CROSS_TC_MIN_B = old
   assert float((tc2 - ref2).abs().max()) <= 1e-5 * float(ref2.abs().max())
+
+
+@pytest.mark.parametrize("idt", [np.int32, np.int64])
+def test_gather_uniform_tables_fast_path(ops, idt):
+  """All tables the same width (the DCN-v2 / two-tower shape): table-fastest kernel, concatenated output with padding."""
+  rng = np.random.RandomState(9)
+  T, V, D, n = 5, 3000, 32, 1234
+  tabs = [rng.normal(size=(V, D)).astype(np.float32) for _ in range(T)]
+  ids = [rng.randint(0, V, size=n).astype(idt) for _ in range(T)]
+  ids[2][7] = V; ids[4][0] = -3   # out of range -> zero rows
+  exp = np.concatenate([orc.gather(t, i) for t, i in zip(tabs, ids)], 1)
+  out = torch.full((n, T * D + 8), -7.0, device=dev())
+  ops.gather([cu(t) for t in tabs], [cu(i) for i in ids], out=out)
+  np.testing.assert_array_equal(out[:, :T * D].cpu().numpy(), exp)
+  assert float((out[:, T * D:] + 7.0).abs().sum()) == 0.0   # padding columns untouched
