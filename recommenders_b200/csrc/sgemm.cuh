@@ -15,24 +15,25 @@ namespace tfrs {
 
 constexpr int SG_BM = 128, SG_BN = 128, SG_BK = 16, SG_THREADS = 256;
 
-template <bool TA, bool TB, class Epi>
+template <bool TA, bool TB, int BN, class Epi>
 __global__ void __launch_bounds__(SG_THREADS)
 sgemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb,
              int M, int N, int K, int k_per_split, bool vecA, bool vecB, Epi epi) {
   __shared__ __align__(16) float As[SG_BK][SG_BM + 4];
-  __shared__ __align__(16) float Bs[SG_BK][SG_BN + 4];
+  constexpr int TN = BN / 16;  // columns per thread (8 for BN=128, 4 for the skinny BN=64 variant)
+  __shared__ __align__(16) float Bs[SG_BK][BN + 4];
 
   const int tid = threadIdx.x;
-  const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+  const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * BN;
   const int k_begin = blockIdx.z * k_per_split;
   const int k_end = min(K, k_begin + k_per_split);
   const int tx = tid % 16, ty = tid / 16;
 
-  float acc[8][8];
+  float acc[8][TN];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
 
   for (int k0 = k_begin; k0 < k_end; k0 += SG_BK) {
     const int kmax = min(SG_BK, k_end - k0);
@@ -76,7 +77,7 @@ sgemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict
     if (TB) {
       if (vecB) {
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
+        for (int it = 0; it < BN / 64; ++it) {
           int f = tid + it * SG_THREADS;
           int n = f / 4, kq = (f % 4) * 4;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -92,7 +93,7 @@ sgemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict
         }
       } else {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
+        for (int it = 0; it < BN / 16; ++it) {
           int e = tid + it * SG_THREADS;
           int n = e / SG_BK, kk = e % SG_BK;
           int gn = n0 + n, gk = k0 + kk;
@@ -101,9 +102,9 @@ sgemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict
       }
     } else {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
+      for (int it = 0; it < BN / 16; ++it) {
         int e = tid + it * SG_THREADS;
-        int kk = e / SG_BN, n = e % SG_BN;
+        int kk = e / BN, n = e % BN;
         int gn = n0 + n, gk = k0 + kk;
         Bs[kk][n] = (gn < N && gk < k_end) ? B[(long long)gk * ldb + gn] : 0.f;
       }
@@ -113,25 +114,27 @@ sgemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict
     if (kmax == SG_BK) {
 #pragma unroll
       for (int kk = 0; kk < SG_BK; ++kk) {
-        float a[8], b[8];
+        float a[8], b[TN];
         *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
         *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
-        *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8]);
-        *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8 + 4]);
+        *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN]);
+        if (TN == 8) *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN + 4]);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
       }
     } else {
       for (int kk = 0; kk < kmax; ++kk) {
-        float a[8], b[8];
+        float a[8], b[TN];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { a[i] = As[kk][ty * 8 + i]; b[i] = Bs[kk][tx * 8 + i]; }
+        for (int i = 0; i < 8; ++i) a[i] = As[kk][ty * 8 + i];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
       }
     }
     __syncthreads();
@@ -142,8 +145,8 @@ sgemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict
     int gm = m0 + ty * 8 + i;
     if (gm >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int gn = n0 + tx * 8 + j;
+    for (int j = 0; j < TN; ++j) {
+      int gn = n0 + tx * TN + j;
       if (gn < N) epi(gm, gn, acc[i][j], (int)blockIdx.z);
     }
   }
@@ -184,9 +187,11 @@ static inline int launch_sgemm(const float* A, long long lda, const float* B, lo
   if (kps <= 0) kps = SG_BK;
   bool vecA = !TA && (lda % 4 == 0) && aligned16(A);
   bool vecB = TB && (ldb % 4 == 0) && aligned16(B);
-  dim3 grid((unsigned)ceil_div(N, SG_BN), (unsigned)ceil_div(M, SG_BM), (unsigned)splits);
+  const bool skinny = N <= 64;  // 64-column tiles: no half-empty tiles for the [*, d] outputs of the backward passes
+  dim3 grid((unsigned)ceil_div(N, skinny ? 64 : SG_BN), (unsigned)ceil_div(M, SG_BM), (unsigned)splits);
   if (grid.y > 65535) { set_error("sgemm: M too large (%d)", M); return TFRS_ERR_UNSUPPORTED; }
-  sgemm_kernel<TA, TB, Epi><<<grid, SG_THREADS, 0, st>>>(A, lda, B, ldb, M, N, K, kps, vecA, vecB, epi);
+  if (skinny) sgemm_kernel<TA, TB, 64, Epi><<<grid, SG_THREADS, 0, st>>>(A, lda, B, ldb, M, N, K, kps, vecA, vecB, epi);
+  else sgemm_kernel<TA, TB, SG_BN, Epi><<<grid, SG_THREADS, 0, st>>>(A, lda, B, ldb, M, N, K, kps, vecA, vecB, epi);
   TFRS_LAUNCH_CHECK();
   return TFRS_OK;
 }

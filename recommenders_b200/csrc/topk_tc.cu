@@ -678,7 +678,7 @@ static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
   pl.parts_full = (long long)parts < pl.n_tiles ? parts : (int)pl.n_tiles;
   {
     int cp = 2 * CAND_CAP / (pl.parts_full * 2);  // octet records: (part, column-half) segments add up to ~2x the per-query capacity
-    int p2 = 32; while (p2 * 2 <= cp && p2 < CAND_CAP) p2 <<= 1;
+    int p2 = 32; while (p2 * 2 <= cp && p2 < 512) p2 <<= 1;   // 32..512 records per segment
     pl.cap_part = p2;
   }
   pl.smem = (size_t)(2 + pl.stages) * pl.kb * SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;

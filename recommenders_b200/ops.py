@@ -16,6 +16,7 @@ from ._ffi import c_f, c_i, c_l, c_sz, check, f32c, lib, ptr, require_cuda, stre
 # Corpora at least this large go through the tensor-core screening path when an index image exists.
 TC_MIN_N = 16384
 TC_MAX_K = 256
+TC_MAX_Q_PER_CALL = 8192
 
 
 # ------------------------------------------------------------------------------------------------
@@ -114,6 +115,11 @@ def topk_tc(q: torch.Tensor, corpus: torch.Tensor, index_buf: torch.Tensor, k: i
   else:
     out_s, out_i = out
   if Q == 0:
+    return out_s, out_i
+  if Q > TC_MAX_Q_PER_CALL:  # bound the workspace (bin maxima + survivor records scale with Q): query chunks
+    for lo in range(0, Q, TC_MAX_Q_PER_CALL):
+      hi = min(Q, lo + TC_MAX_Q_PER_CALL)
+      topk_tc(q[lo:hi], corpus, index_buf, k, index_offset, out=(out_s[lo:hi], out_i[lo:hi]))
     return out_s, out_i
   wsb = lib().tfrs_topk_tc_workspace_bytes(Q, N, d, k)
   ws = workspace(wsb, q.device, "tc")

@@ -129,3 +129,14 @@ def test_packed_allgather_block_merge(ops):
     layer._local_topk(q, k, lo, out=(out_s, out_i))
   ms, mi = ops.topk_merge_packed(recv, world, Q, k, k, idx_off, block)
   assert torch.equal(mi, ei) and torch.equal(ms, es)
+
+
+def test_tc_query_chunking(ops):
+  """More queries than TC_MAX_Q_PER_CALL: the wrapper runs query chunks into slices of one output."""
+  c = _rand((40000, 64), 31); q = _rand((9001, 64), 32)
+  idx = ops.index_build(c)
+  s, i = ops.topk_tc(q, c, idx, 10)
+  es, ei = ops.topk_scan(q[-300:], c, 10)
+  assert torch.equal(i[-300:], ei) and torch.equal(s[-300:], es)
+  es, ei = ops.topk_scan(q[8000:8300], c, 10)
+  assert torch.equal(i[8000:8300], ei) and torch.equal(s[8000:8300], es)
