@@ -108,7 +108,8 @@ tile_image_kernel(const float* __restrict__ src, long long rows, int d, int kb, 
 
 // max row norm^2 and max |element| of a [rows, d] matrix (one warp per row -> coalesced)
 __global__ void __launch_bounds__(256)
-side_stats_kernel(const float* __restrict__ src, long long rows, int d, SideStats* __restrict__ st) {
+side_stats_kernel(const float* __restrict__ src, long long rows, int d, SideStats* __restrict__ st,
+                  float* __restrict__ row_n2 /* nullable: per-row |x|^2 */) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * 256) >> 5;
@@ -120,6 +121,7 @@ side_stats_kernel(const float* __restrict__ src, long long rows, int d, SideStat
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { n2 += __shfl_xor_sync(0xffffffffu, n2, o); a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o)); }
     best_n2 = fmaxf(best_n2, n2); best_a = fmaxf(best_a, a);
+    if (row_n2 && lane == 0) row_n2[row] = n2;
   }
   if (lane == 0) {
     if (best_n2 > 0.f) atomicMax(&st->max_norm2_bits, __float_as_uint(best_n2 * 1.0001f));  // slack for the tree order
@@ -143,15 +145,11 @@ __global__ void header_kernel(IndexHeader* dst, IndexHeader h) { *dst = h; }
 // per-query margins from |q| and the corpus max norm, expressed in SCREENING units (scores scaled by
 // 2^(exp_q + exp_c), an exact power of two)
 __global__ void __launch_bounds__(256)
-qmargin_kernel(const float* __restrict__ q, long long Q, long long Qp, int d, const IndexHeader* __restrict__ hdr,
-               const SideStats* __restrict__ qst, int bf16, float* __restrict__ margin, float* __restrict__ cut) {
+qmargin_kernel(long long Q, long long Qp, const IndexHeader* __restrict__ hdr, const SideStats* __restrict__ qst, int bf16,
+               float* __restrict__ margin /* in: |q|^2 per row (rows < Q); out: filter margin */, float* __restrict__ cut) {
   long long row = (long long)blockIdx.x * 256 + threadIdx.x;
   if (row >= Qp) return;
-  float n2 = 0.f;
-  if (row < Q) {
-    const float* p = q + row * d;
-    for (int k = 0; k < d; ++k) n2 = fmaf(p[k], p[k], n2);
-  }
+  const float n2 = row < Q ? margin[row] * 1.0001f : 0.f;  // slack for the tree-order norm
   const float cn = sqrtf(__uint_as_float(hdr->st.max_norm2_bits)) * 1.001f;
   const float qn = sqrtf(n2) * 1.001f;
   const int se = bf16 ? 0 : (hdr->st.exp + qst->exp);
@@ -758,7 +756,7 @@ extern "C" int tfrs_index_build(const float* corpus, int64_t N, int d, void* ind
   header_kernel<<<1, 1, 0, st>>>(reinterpret_cast<IndexHeader*>(index_buf), h);
   TFRS_LAUNCH_CHECK();
   SideStats* cst = &reinterpret_cast<IndexHeader*>(index_buf)->st;
-  side_stats_kernel<<<(unsigned)(148 * 8), 256, 0, st>>>(corpus, N, d, cst);
+  side_stats_kernel<<<(unsigned)(148 * 8), 256, 0, st>>>(corpus, N, d, cst, nullptr);
   TFRS_LAUNCH_CHECK();
   side_exp_kernel<<<1, 1, 0, st>>>(cst, fp16_target());
   TFRS_LAUNCH_CHECK();
@@ -806,14 +804,14 @@ extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, 
   {
     SideStats* qst = (SideStats*)(w + pl.o_qstats);
     TFRS_CUDA(cudaMemsetAsync(qst, 0, sizeof(SideStats), st));
-    side_stats_kernel<<<(unsigned)ceil_div(Q * 32, 256), 256, 0, st>>>(q, Q, d, qst);
+    side_stats_kernel<<<(unsigned)ceil_div(Q * 32, 256), 256, 0, st>>>(q, Q, d, qst, margin /* scratch: |q|^2 per row */);
     TFRS_LAUNCH_CHECK();
     side_exp_kernel<<<1, 1, 0, st>>>(qst, fp16_target());
     TFRS_LAUNCH_CHECK();
     long long chunks = (long long)pl.nqb * 2 * TILE_N * pl.kb * 8;
     tile_image_kernel<<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(q, Q, d, pl.kb, (long long)pl.nqb * 2, qst, use_bf16(), qimg);
     TFRS_LAUNCH_CHECK();
-    qmargin_kernel<<<(unsigned)ceil_div(pl.Qp, 256), 256, 0, st>>>(q, Q, pl.Qp, d, hdr, qst, use_bf16(), margin, cut);
+    qmargin_kernel<<<(unsigned)ceil_div(pl.Qp, 256), 256, 0, st>>>(Q, pl.Qp, hdr, qst, use_bf16(), margin, cut);
     TFRS_LAUNCH_CHECK();
   }
   ScanParams sp{};
