@@ -78,6 +78,20 @@ gather_uniform_kernel(GatherParams p, int n_tables, long long n, int lanes, floa
   const int dim = lanes * 4;
   long long w = (long long)blockIdx.x * GT_THREADS + threadIdx.x;
   for (; w < total; w += stride * GT_ROWS_PER_THREAD) {
+    // software prefetch into L2 of the rows this thread will need in its NEXT trip (persistent grid): raises
+    // the number of random row fetches in flight beyond what the register-held loads allow
+    if ((w & (lanes - 1)) == 0) {  // one thread per row issues the prefetches (stride is a multiple of `lanes`)
+#pragma unroll
+      for (int u = 0; u < GT_ROWS_PER_THREAD; ++u) {
+        const long long en = w + stride * (GT_ROWS_PER_THREAD + u);
+        if (en < total) {
+          const long long itn = en >> lane_shift;
+          const long long in_ = itn / n_tables; const int tn = (int)(itn - in_ * n_tables);
+          const long long rn = (long long)reinterpret_cast<const IdT*>(p.ids[tn])[in_];
+          if (rn >= 0 && rn < p.rows[tn]) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.table[tn] + rn * dim));
+        }
+      }
+    }
     float4 v4[GT_ROWS_PER_THREAD];
     long long dst[GT_ROWS_PER_THREAD];
 #pragma unroll
@@ -136,7 +150,8 @@ extern "C" int tfrs_gather_f32(const float* const* tables, const int64_t* rows, 
       const int lanes = dims[t0] / 4;
       long long items_u = n * nt * lanes;
       long long blocks_u = ceil_div(items_u, (long long)GT_THREADS * GT_ROWS_PER_THREAD);
-      if (blocks_u > 1 << 20) blocks_u = 1 << 20;
+      const long long persistent = (long long)sm_count() * 8;  // persistent grid: several trips per thread -> prefetch distance
+      if (blocks_u > persistent) blocks_u = persistent;
       if (ids_dtype == TFRS_I32) gather_uniform_kernel<int32_t><<<(unsigned)blocks_u, GT_THREADS, 0, st>>>(p, nt, n, lanes, out, out_ld);
       else gather_uniform_kernel<int64_t><<<(unsigned)blocks_u, GT_THREADS, 0, st>>>(p, nt, n, lanes, out, out_ld);
       TFRS_LAUNCH_CHECK();
