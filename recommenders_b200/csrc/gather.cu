@@ -66,56 +66,6 @@ gather_kernel(GatherParams p, long long n, float* __restrict__ out, long long ou
   }
 }
 
-// Uniform-width fast path (all tables share `dim`, 16-byte lanes): the TABLE index varies fastest after the
-// lane, so consecutive warps write consecutive column blocks of the SAME output row -- the concatenated
-// activation is written in long contiguous runs (one DRAM page per row) while the row reads stay random.
-template <typename IdT>
-__global__ void __launch_bounds__(GT_THREADS)
-gather_uniform_kernel(GatherParams p, int n_tables, long long n, int lanes, float* __restrict__ out, long long out_ld) {
-  const long long total = n * n_tables * lanes;
-  const long long stride = (long long)gridDim.x * GT_THREADS;
-  const int lane_shift = 31 - __clz(lanes);  // lanes is a power of two on this path
-  const int dim = lanes * 4;
-  long long w = (long long)blockIdx.x * GT_THREADS + threadIdx.x;
-  for (; w < total; w += stride * GT_ROWS_PER_THREAD) {
-    // software prefetch into L2 of the rows this thread will need in its NEXT trip (persistent grid): raises
-    // the number of random row fetches in flight beyond what the register-held loads allow
-    if ((w & (lanes - 1)) == 0) {  // one thread per row issues the prefetches (stride is a multiple of `lanes`)
-#pragma unroll
-      for (int u = 0; u < GT_ROWS_PER_THREAD; ++u) {
-        const long long en = w + stride * (GT_ROWS_PER_THREAD + u);
-        if (en < total) {
-          const long long itn = en >> lane_shift;
-          const long long in_ = itn / n_tables; const int tn = (int)(itn - in_ * n_tables);
-          const long long rn = (long long)reinterpret_cast<const IdT*>(p.ids[tn])[in_];
-          if (rn >= 0 && rn < p.rows[tn]) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.table[tn] + rn * dim));
-        }
-      }
-    }
-    float4 v4[GT_ROWS_PER_THREAD];
-    long long dst[GT_ROWS_PER_THREAD];
-#pragma unroll
-    for (int u = 0; u < GT_ROWS_PER_THREAD; ++u) {
-      const long long e = w + u * stride;
-      dst[u] = -1;
-      if (e < total) {
-        const int l = (int)(e & (lanes - 1));
-        const long long it = e >> lane_shift;          // (i, t) pair index
-        long long i; int t;
-        if (it < (1ll << 32)) { const unsigned int it32 = (unsigned int)it; const unsigned int i32 = it32 / (unsigned int)n_tables; i = i32; t = (int)(it32 - i32 * (unsigned int)n_tables); }
-        else { i = it / n_tables; t = (int)(it - i * n_tables); }
-        const long long r = (long long)reinterpret_cast<const IdT*>(p.ids[t])[i];
-        const bool ok = (r >= 0 && r < p.rows[t]);
-        v4[u] = ok ? __ldg(reinterpret_cast<const float4*>(p.table[t] + r * dim) + l) : make_float4(0.f, 0.f, 0.f, 0.f);
-        dst[u] = i * out_ld + p.col_off[t] + l * 4;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < GT_ROWS_PER_THREAD; ++u)
-      if (dst[u] >= 0) *reinterpret_cast<float4*>(out + dst[u]) = v4[u];
-  }
-}
-
 }  // namespace tfrs
 using namespace tfrs;
 
@@ -142,20 +92,6 @@ extern "C" int tfrs_gather_f32(const float* const* tables, const int64_t* rows, 
       vec = vec && (dims[t0 + t] % 4 == 0) && (out_col_off[t0 + t] % 4 == 0) &&
             ((reinterpret_cast<uintptr_t>(tables[t0 + t]) & 15) == 0);
       if (dims[t0 + t] > max_dim) max_dim = dims[t0 + t];
-    }
-    bool uniform = vec && nt > 1;
-    for (int t = 0; t < nt; ++t) uniform = uniform && dims[t0 + t] == dims[t0];
-    if (uniform) { int ln = dims[t0] / 4; uniform = (ln & (ln - 1)) == 0; }
-    if (uniform) {
-      const int lanes = dims[t0] / 4;
-      long long items_u = n * nt * lanes;
-      long long blocks_u = ceil_div(items_u, (long long)GT_THREADS * GT_ROWS_PER_THREAD);
-      const long long persistent = (long long)sm_count() * 8;  // persistent grid: several trips per thread -> prefetch distance
-      if (blocks_u > persistent) blocks_u = persistent;
-      if (ids_dtype == TFRS_I32) gather_uniform_kernel<int32_t><<<(unsigned)blocks_u, GT_THREADS, 0, st>>>(p, nt, n, lanes, out, out_ld);
-      else gather_uniform_kernel<int64_t><<<(unsigned)blocks_u, GT_THREADS, 0, st>>>(p, nt, n, lanes, out, out_ld);
-      TFRS_LAUNCH_CHECK();
-      continue;
     }
     long long items = n * (vec ? max_dim / 4 : max_dim);
     long long blocks = ceil_div(items, (long long)GT_THREADS * GT_ROWS_PER_THREAD);
