@@ -249,7 +249,10 @@ def main():
     t_filter = stage_ms[2] / max(calls, 1) * 1e-3
     achieved = flops / t_filter / 1e12
     roofline = {"bound": "tensor", "kernel": "tc_scan_kernel<FILTER>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "peak_source": which, "traffic": None,
+                "frac": achieved / peak, "peak_source": which,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, from the committed ncu
+                # --set full capture (profiles/r01_tc_scan_v5_metrics.csv: 131.3 MB + 39.7 MB); only for that shape
+                "traffic": 170.9e6 if (args.workload == "cfg2" and world == 1) else None, "traffic_unit": "bytes/launch",
                 "stage_ms_per_call": {"qprep": stage_ms[0] / calls, "sample_pass+threshold": stage_ms[1] / calls,
                                       "filter_pass": stage_ms[2] / calls, "rescore+finalize": stage_ms[3] / calls}}
 
