@@ -149,6 +149,15 @@ int tfrs_inbatch_softmax_bwd(const float* q, const float* c, int64_t B, int64_t 
                              const float* grad_loss, float* dq, float* dc, void* ws, size_t ws_bytes,
                              void* stream);
 
+/* K3 forward on the tensor cores (same contract and outputs as tfrs_inbatch_softmax_fwd; d <= 128):
+ * hi/lo fp16 split of q and c (|err| <= 2^-21 |q||c| on a score), tcgen05 GEMM with fp32 TMEM accumulation and
+ * an online log-sum-exp epilogue -- the [B,C] logits are never written.  Returns TFRS_ERR_UNSUPPORTED
+ * (workspace_bytes == 0) outside its shape range; the caller then uses tfrs_inbatch_softmax_fwd. */
+size_t tfrs_inbatch_softmax_tc_workspace_bytes(int64_t B, int64_t C, int d);
+int tfrs_inbatch_softmax_tc_fwd(const float* q, const float* c, int64_t B, int64_t C, int d,
+                                float inv_temperature, const float* sample_weight, float* loss, float* lse,
+                                void* ws, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K4  sparse Adagrad on the rows touched by a batch (optimizer.apply_gradients with IndexedSlices,
  * models/base.py:77-78; Adagrad chosen by the user, README.md:84).  Duplicate ids are summed in

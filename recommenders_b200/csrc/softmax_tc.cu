@@ -1,0 +1,288 @@
+// softmax_tc.cu -- K3 forward on the tensor cores: in-batch sampled-softmax loss of tfrs.tasks.Retrieval
+//   tasks/retrieval.py:178-180 (scores = q . c^T), :185 (labels = eye), :187-188 (/temperature), :210 + :86-87
+//   loss = sum_i w_i * (logsumexp_j (q_i . c_j / T)  -  q_i . c_i / T)
+// as ONE tcgen05 GEMM whose epilogue keeps an online (max, sum-exp) per query row and picks the diagonal --
+// the [B,C] logits and the eye() labels never exist.  fp32 parity: hi/lo fp16 split of both operands (tc_split.cuh),
+// 3 MMAs per K step, fp32 accumulation in TMEM (~2^-21 relative on a score).
+//
+// CTA shape = the top-K scan's: 256 query rows (two 128-row A blocks, hi+lo, resident), candidate tiles of
+// 128 rows streamed through a bulk-TMA ring, 2x2 TMEM accumulator buffers, 16 epilogue warps (one row x 64
+// columns per thread).  Grid = query blocks x candidate parts; every (row, part, column-half) leaves a partial
+// (max, sum-exp) pair that `smtc_combine_kernel` folds into lse_i and the weighted row loss; the scalar loss is
+// reduced in fixed order in fp64 (deterministic).  The backward pass (softmax.cu) consumes the same `lse`.
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "tc_split.cuh"
+
+namespace tfrs {
+namespace tc {
+
+constexpr int SX_THREADS = 640;
+// candidate-tile ring depth: 4 x 32 KB at d <= 64, 1 x 64 KB at d <= 128 (A = 128 KB there)
+__host__ __device__ constexpr int sx_stages(int kb) { return kb == 1 ? 4 : 1; }
+constexpr float SX_LOG2E = 1.4426950408889634f;
+
+struct SoftmaxTcParams {
+  const unsigned char* qimg;  // [2*nqb tiles][kb][hi|lo][16 KB]
+  const unsigned char* cimg;  // [n_ctiles][kb][hi|lo][16 KB]
+  const CxStats* qst; const CxStats* cst;
+  long long B, C;
+  int nqb, parts, kb;
+  long long n_ctiles;
+  float inv_t;
+  float2* partial;            // [Bp, parts, 2] (max, sum-exp) in log2 units
+  float* pos;                 // [Bp] positive logit q_i.c_i/T (natural units)
+};
+
+template <int KB>
+__global__ void __launch_bounds__(SX_THREADS, 1)
+softmax_tc_kernel(const SoftmaxTcParams p) {
+  extern __shared__ __align__(1024) unsigned char sx_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sx_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int SX_STAGES = sx_stages(KB);
+  constexpr int A_BYTES = 2 * KB * 32768;      // two A blocks, hi+lo per K slab
+  constexpr int B_BYTES = KB * 32768;          // one candidate tile, hi+lo per K slab
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + SX_STAGES * B_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + SX_STAGES;
+  uint64_t* a_full = bars + 2 * SX_STAGES;
+  uint64_t* t_full = a_full + 1;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = blockIdx.x % p.nqb, part = blockIdx.x / p.nqb;
+  const long long t_begin = (long long)part * p.n_ctiles / p.parts;
+  const long long t_end = (long long)(part + 1) * p.n_ctiles / p.parts;
+  const int n_iter = (int)(t_end - t_begin);
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < SX_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(a_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 16); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(a_full, A_BYTES);
+      bulk_g2s(sA, p.qimg + (long long)qb * A_BYTES, A_BYTES, a_full);
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < n_iter; ++it) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], B_BYTES);
+        bulk_g2s(sB + stage * B_BYTES, p.cimg + (t_begin + it) * (long long)B_BYTES, B_BYTES, &full[stage]);
+        if (++stage == SX_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(a_full, 0);
+      tc_fence_after();
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < n_iter; ++it) {
+        const int buf = it & 1;
+        const uint32_t tphase = (it >> 1) & 1;
+        mbar_wait(&t_empty[buf], tphase ^ 1);
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+#pragma unroll
+        for (int ab = 0; ab < 2; ++ab) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)((ab * 2 + buf) * 128);
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint32_t a0 = smem_u32(sA + (ab * KB + kb) * 32768), b0 = smem_u32(sB + stage * B_BYTES + kb * 32768);
+            const uint64_t a_hi = make_smem_desc(a0), a_lo = make_smem_desc(a0 + 16384);
+            const uint64_t b_hi = make_smem_desc(b0), b_lo = make_smem_desc(b0 + 16384);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t o = (uint64_t)(k4 * 2);
+              umma_f16(d_tmem, a_hi + o, b_hi + o, IDESC_F16_M128_N128, (uint32_t)((kb | k4) != 0));
+              umma_f16(d_tmem, a_lo + o, b_hi + o, IDESC_F16_M128_N128, 1u);
+              umma_f16(d_tmem, a_hi + o, b_lo + o, IDESC_F16_M128_N128, 1u);
+            }
+          }
+        }
+        umma_commit(&empty[stage]);
+        umma_commit(&t_full[buf]);
+        if (++stage == SX_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int half = ew >> 3, ab = (ew >> 2) & 1, quad = ew & 3;
+    const long long row = (long long)qb * 256 + ab * 128 + quad * 32 + lane;
+    // logits in log2 units: s2 = acc * 2^-(eq+ec) * invT * log2(e)
+    const float scale2 = ldexpf(p.inv_t * SX_LOG2E, -(p.qst->exp + p.cst->exp));
+    float m2 = -INFINITY, l = 0.f, pos2 = 0.f;
+    for (int it = 0; it < n_iter; ++it) {
+      const int buf = it & 1;
+      const uint32_t tphase = (it >> 1) & 1;
+      const long long col0 = (t_begin + it) * 128 + half * 64;
+      mbar_wait(&t_full[buf], tphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ab * 2 + buf) * 128 + half * 64);
+      uint32_t r[64];
+      tmem_ld64(taddr, r);
+      tmem_ld_wait64(r);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[buf]);
+      const int n_valid = (int)min(64ll, p.C - col0);  // columns beyond C are zero-padded rows of the image
+      if (n_valid > 0) {
+        float v[64];
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          v[j] = (j < n_valid) ? __uint_as_float(r[j]) * scale2 : -INFINITY;
+          tmax = fmaxf(tmax, v[j]);
+        }
+        if (row >= col0 && row < col0 + 64) {   // the positive of query i is candidate i (retrieval.py:185)
+          const int jd = (int)(row - col0);
+#pragma unroll
+          for (int j = 0; j < 64; ++j) if (j == jd) pos2 = v[j];
+        }
+        const float m_new = fmaxf(m2, tmax);
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) acc += exp2f(v[j] - m_new);
+        l = l * exp2f(m2 - m_new) + acc;
+        m2 = m_new;
+      }
+    }
+    if (row < p.B) {
+      p.partial[(row * p.parts + part) * 2 + half] = make_float2(m2, l);
+      // exactly one (part, half) thread of the row saw the diagonal column
+      const long long dt = row / 128;
+      if (dt >= t_begin && dt < t_end && ((row % 128) / 64) == half) p.pos[row] = pos2 * (1.0f / SX_LOG2E);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// lse_i = ln2 * (M + log2(sum_p l_p 2^(m_p - M)));  rowloss_i = w_i (lse_i - pos_i)
+__global__ void __launch_bounds__(256)
+smtc_combine_kernel(const float2* __restrict__ partial, int n_partials, const float* __restrict__ pos,
+                    const float* __restrict__ w, long long B, float* __restrict__ lse, float* __restrict__ rowloss) {
+  const long long row = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (row >= B) return;
+  const float2* pp = partial + row * n_partials;
+  float M = -INFINITY;
+  for (int i = 0; i < n_partials; ++i) M = fmaxf(M, pp[i].x);
+  float L = 0.f;
+  for (int i = 0; i < n_partials; ++i) L += pp[i].y * exp2f(pp[i].x - M);
+  const float l = (M + log2f(L)) * 0.6931471805599453f;
+  lse[row] = l;
+  rowloss[row] = (w ? w[row] : 1.0f) * (l - pos[row]);
+}
+
+__global__ void __launch_bounds__(1024) smtc_reduce_loss(const float* __restrict__ rowloss, long long B, float* __restrict__ loss) {
+  __shared__ double red[1024];
+  double a = 0.0;
+  for (long long i = threadIdx.x; i < B; i += 1024) a += (double)rowloss[i];
+  red[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) { if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s]; __syncthreads(); }
+  if (threadIdx.x == 0) loss[0] = (float)red[0];
+}
+
+struct SxPlan { int kb, nqb, parts; long long Bp, n_ctiles; size_t smem, o_qst, o_cst, o_qimg, o_cimg, o_partial, o_pos, o_rowloss, total; };
+
+static bool sx_plan(long long B, long long C, int d, SxPlan& pl) {
+  if (B <= 0 || C < B || d <= 0 || d > 128) return false;
+  pl.kb = (int)ceil_div(d, 64);
+  pl.nqb = (int)ceil_div(B, 256);
+  pl.Bp = (long long)pl.nqb * 256;
+  pl.n_ctiles = ceil_div(C, 128);
+  // candidate parts: fill whole waves of the SMs, keep >= 8 tiles per CTA so the resident A block amortises
+  int parts = 1; double best = 0.0;
+  const int sms = sm_count();
+  for (int c = 1; c <= 16 && (c == 1 || pl.n_ctiles / c >= 8); ++c) {
+    const long long ctas = (long long)pl.nqb * c;
+    const double eff = (double)ctas / (double)(ceil_div(ctas, sms) * sms);
+    if (eff > best + 0.02) { best = eff; parts = c; }
+  }
+  pl.parts = parts;
+  pl.smem = (size_t)(2 + sx_stages(pl.kb)) * pl.kb * 32768 + 1024 + 256;
+  if (pl.smem > 227 * 1024) return false;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 1024); return r; };
+  pl.o_qst = take(sizeof(CxStats)); pl.o_cst = take(sizeof(CxStats));
+  pl.o_qimg = take(cx_img_bytes(pl.Bp, d));
+  pl.o_cimg = take(cx_img_bytes(pl.n_ctiles * 128, d));
+  pl.o_partial = take((size_t)pl.Bp * parts * 2 * sizeof(float2));
+  pl.o_pos = take((size_t)pl.Bp * 4);
+  pl.o_rowloss = take((size_t)pl.Bp * 4);
+  pl.total = o;
+  return true;
+}
+
+}  // namespace tc
+}  // namespace tfrs
+using namespace tfrs;
+using namespace tfrs::tc;
+
+extern "C" size_t tfrs_inbatch_softmax_tc_workspace_bytes(int64_t B, int64_t C, int d) {
+  SxPlan pl;
+  return sx_plan(B, C, d, pl) ? pl.total : 0;
+}
+
+extern "C" int tfrs_inbatch_softmax_tc_fwd(const float* q, const float* c, int64_t B, int64_t C, int d, float inv_temperature,
+                                           const float* sample_weight, float* loss, float* lse, void* ws, size_t ws_bytes,
+                                           void* stream) {
+  TFRS_CHECK_ARG(q && c && loss && lse, "inbatch_softmax_tc_fwd: NULL pointer");
+  SxPlan pl;
+  if (!sx_plan(B, C, d, pl)) { set_error("inbatch_softmax_tc_fwd: shape outside the tensor-core path (need B <= C, d <= 128)"); return TFRS_ERR_UNSUPPORTED; }
+  if (!ws || ws_bytes < pl.total) { set_error("inbatch_softmax_tc_fwd: workspace too small"); return TFRS_ERR_WORKSPACE_TOO_SMALL; }
+  TFRS_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "inbatch_softmax_tc_fwd: workspace must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* w = (unsigned char*)ws;
+  CxStats* qst = (CxStats*)(w + pl.o_qst); CxStats* cst = (CxStats*)(w + pl.o_cst);
+  unsigned char* qimg = w + pl.o_qimg; unsigned char* cimg = w + pl.o_cimg;
+  float2* partial = (float2*)(w + pl.o_partial);
+  float* pos = (float*)(w + pl.o_pos); float* rowloss = (float*)(w + pl.o_rowloss);
+  TFRS_CUDA(cudaMemsetAsync(w, 0, 2048, st));  // both stats blocks
+  cx_amax_kernel<<<(unsigned)ceil_div(B * 32, 256), 256, 0, st>>>(q, B, d, d, qst);
+  TFRS_LAUNCH_CHECK();
+  cx_amax_kernel<<<(unsigned)ceil_div(C * 32, 256), 256, 0, st>>>(c, C, d, d, cst);
+  TFRS_LAUNCH_CHECK();
+  cx_exp_kernel<<<1, 1, 0, st>>>(qst);
+  TFRS_LAUNCH_CHECK();
+  cx_exp_kernel<<<1, 1, 0, st>>>(cst);
+  TFRS_LAUNCH_CHECK();
+  {
+    long long chunks = pl.Bp / 128 * 128 * (long long)pl.kb * 8;
+    cx_split_image_kernel<false><<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(q, B, d, d, pl.kb, pl.Bp / 128, qst, qimg);
+    TFRS_LAUNCH_CHECK();
+    chunks = pl.n_ctiles * 128 * (long long)pl.kb * 8;
+    cx_split_image_kernel<false><<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(c, C, d, d, pl.kb, pl.n_ctiles, cst, cimg);
+    TFRS_LAUNCH_CHECK();
+  }
+  SoftmaxTcParams p{};
+  p.qimg = qimg; p.cimg = cimg; p.qst = qst; p.cst = cst; p.B = B; p.C = C; p.nqb = pl.nqb; p.parts = pl.parts; p.kb = pl.kb;
+  p.n_ctiles = pl.n_ctiles; p.inv_t = inv_temperature; p.partial = partial; p.pos = pos;
+  static bool attr = false;
+  if (!attr) {
+    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 + sx_stages(1)) * 32768 + 1280)));
+    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 + sx_stages(2)) * 2 * 32768 + 1280)));
+    attr = true;
+  }
+  if (pl.kb == 1) softmax_tc_kernel<1><<<(unsigned)(pl.nqb * pl.parts), SX_THREADS, pl.smem, st>>>(p);
+  else softmax_tc_kernel<2><<<(unsigned)(pl.nqb * pl.parts), SX_THREADS, pl.smem, st>>>(p);
+  TFRS_LAUNCH_CHECK();
+  smtc_combine_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, st>>>(partial, pl.parts * 2, pos, sample_weight, B, lse, rowloss);
+  TFRS_LAUNCH_CHECK();
+  smtc_reduce_loss<<<1, 1024, 0, st>>>(rowloss, B, loss);
+  TFRS_LAUNCH_CHECK();
+  return TFRS_OK;
+}

@@ -259,6 +259,23 @@ def rowwise_dot(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # K3 in-batch softmax loss
 # ------------------------------------------------------------------------------------------------
+SOFTMAX_TC_MIN_B = 512  # below this the exact CUDA-core forward is launch-latency bound anyway
+
+
+def inbatch_softmax_tc(q: torch.Tensor, c: torch.Tensor, sample_weight: Optional[torch.Tensor] = None,
+                       inv_temperature: float = 1.0):
+  """Tensor-core forward only (any B): returns (loss scalar, lse [B]).  Raises NotImplementedError when d > 128."""
+  q = f32c(q, "query_embeddings"); c = f32c(c, "candidate_embeddings")
+  B, d = q.shape; C = c.shape[0]
+  w = None if sample_weight is None else f32c(sample_weight, "sample_weight").view(-1)
+  loss = torch.empty((1,), dtype=torch.float32, device=q.device)
+  lse = torch.empty((B,), dtype=torch.float32, device=q.device)
+  ws = workspace(max(lib().tfrs_inbatch_softmax_tc_workspace_bytes(B, C, d), 256), q.device, "softmax_tc")
+  check(lib().tfrs_inbatch_softmax_tc_fwd(ptr(q), ptr(c), B, C, d, c_f(inv_temperature), ptr(w), ptr(loss), ptr(lse),
+                                          ptr(ws), ws.numel(), stream()), "inbatch_softmax_tc_fwd")
+  return loss.view(()), lse
+
+
 class _InBatchSoftmax(torch.autograd.Function):
 
   @staticmethod
@@ -268,10 +285,16 @@ class _InBatchSoftmax(torch.autograd.Function):
     w = None if sample_weight is None else f32c(sample_weight, "sample_weight").view(-1)
     loss = torch.empty((1,), dtype=torch.float32, device=q.device)
     lse = torch.empty((B,), dtype=torch.float32, device=q.device)
-    wsb = lib().tfrs_inbatch_softmax_workspace_bytes(B, C, d)
-    ws = workspace(wsb, q.device, "softmax")
-    check(lib().tfrs_inbatch_softmax_fwd(ptr(q), ptr(c), B, C, d, c_f(inv_temperature), ptr(w), ptr(loss), ptr(lse),
-                                         ptr(ws), ws.numel(), stream()), "inbatch_softmax_fwd")
+    tcb = lib().tfrs_inbatch_softmax_tc_workspace_bytes(B, C, d) if B >= SOFTMAX_TC_MIN_B else 0
+    if tcb:  # tensor-core forward (hi/lo fp16 split, fp32 accumulate, online log-sum-exp epilogue)
+      ws = workspace(tcb, q.device, "softmax_tc")
+      check(lib().tfrs_inbatch_softmax_tc_fwd(ptr(q), ptr(c), B, C, d, c_f(inv_temperature), ptr(w), ptr(loss), ptr(lse),
+                                              ptr(ws), ws.numel(), stream()), "inbatch_softmax_tc_fwd")
+    else:
+      wsb = lib().tfrs_inbatch_softmax_workspace_bytes(B, C, d)
+      ws = workspace(wsb, q.device, "softmax")
+      check(lib().tfrs_inbatch_softmax_fwd(ptr(q), ptr(c), B, C, d, c_f(inv_temperature), ptr(w), ptr(loss), ptr(lse),
+                                           ptr(ws), ws.numel(), stream()), "inbatch_softmax_fwd")
     ctx.save_for_backward(q, c, lse, w if w is not None else torch.empty(0, device=q.device))
     ctx.has_w = w is not None
     ctx.inv_t = inv_temperature
