@@ -120,6 +120,13 @@ int tfrs_topk_merge_strided(const float* scores, const int64_t* idx, int64_t lis
                             int64_t list_stride_idx, int n_lists, int64_t Q, int k_in, int k_out,
                             float* out_scores, int64_t* out_idx, void* stream);
 
+/* The same merge when every input list is already sorted in the total order (score desc, index asc) -- which is
+ * what tfrs_topk_scan_f32 / tfrs_topk_tc_f32 emit, i.e. the per-shard lists of the sharded BruteForce: merged rank
+ * = own position + binary-search counts in the other lists; no sort.  n_lists * k_in <= 16384. */
+int tfrs_topk_merge_sorted_strided(const float* scores, const int64_t* idx, int64_t list_stride_scores,
+                                   int64_t list_stride_idx, int n_lists, int64_t Q, int k_in, int k_out,
+                                   float* out_scores, int64_t* out_idx, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Score helpers (exact fp32, canonical fmaf chain, one owner thread per output).
  * tfrs_sgemm_f32: C[M,N] (+)= opA(A) . opB(B); opA(m,k) = transA ? A[k*lda+m] : A[m*lda+k],

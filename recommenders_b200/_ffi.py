@@ -40,6 +40,7 @@ _SIGNATURES = {
     "tfrs_profile_read": (c_i, [c_p, c_p]),
     "tfrs_topk_merge": (c_i, [c_p, c_p, c_i, c_l, c_i, c_i, c_p, c_p, c_p]),
     "tfrs_topk_merge_strided": (c_i, [c_p, c_p, c_l, c_l, c_i, c_l, c_i, c_i, c_p, c_p, c_p]),
+    "tfrs_topk_merge_sorted_strided": (c_i, [c_p, c_p, c_l, c_l, c_i, c_l, c_i, c_i, c_p, c_p, c_p]),
     "tfrs_sgemm_f32": (c_i, [c_i, c_i, c_l, c_l, c_l, c_p, c_l, c_p, c_l, c_p, c_l, c_i, c_p]),
     "tfrs_rowwise_dot_f32": (c_i, [c_p, c_p, c_l, c_i, c_p, c_p]),
     "tfrs_inbatch_softmax_workspace_bytes": (c_sz, [c_l, c_l, c_i]),

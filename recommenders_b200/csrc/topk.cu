@@ -154,6 +154,101 @@ extern "C" int tfrs_topk_merge_strided(const float* scores, const int64_t* idx, 
   return launch_row_topk(prov, Q, ko, out_scores, (long long*)out_idx, k_out, (cudaStream_t)stream);
 }
 
+// ---- merge of SORTED lists (the sharded scan's all-gather) ---------------------------------------
+// Every list is already in the total order (score desc, index asc), so two lists merge without a sort: the merged
+// position of an element is (its position in its own list) + (how many elements of the partner list precede it),
+// one binary search in shared memory.  Lists are merged pairwise in a tree (n -> n/2 -> ... -> 1), every level cut
+// to k_out; the last level writes the result.  No atomics; ties between equal (score, index) pairs -- the
+// (-inf, INT64_MAX) padding of short shards -- go to the lower list, so the order is total.
+namespace tfrs {
+constexpr int MS_THREADS = 256;
+constexpr int MS_MAX_LISTS = 64;
+
+__device__ __forceinline__ int ms_len(int i, int level, int n_lists, int k_in, int k_out) {
+  long long cnt = min((long long)1 << level, (long long)n_lists - ((long long)i << level));
+  long long len = cnt * k_in;
+  return (int)(len < k_out ? len : k_out);
+}
+
+__global__ void __launch_bounds__(MS_THREADS)
+merge_sorted_kernel(const float* __restrict__ s, const long long* __restrict__ idx, long long stride_s, long long stride_i,
+                    int n_lists, int k_in, int k_out, int region, float* __restrict__ out_s, long long* __restrict__ out_i,
+                    int out_ld) {
+  extern __shared__ __align__(16) unsigned char ms_smem[];
+  // two ping-pong regions of `region` entries: indices (8 B) then scores (4 B)
+  long long* ri[2] = {reinterpret_cast<long long*>(ms_smem), reinterpret_cast<long long*>(ms_smem) + region};
+  float* rs[2] = {reinterpret_cast<float*>(ms_smem + (size_t)region * 16), reinterpret_cast<float*>(ms_smem + (size_t)region * 16) + region};
+  const long long row = blockIdx.x;
+  const int total = n_lists * k_in;
+  for (int t = threadIdx.x; t < total; t += MS_THREADS) {
+    const int l = t / k_in, r = t - l * k_in;
+    rs[0][t] = s[(long long)l * stride_s + row * k_in + r];
+    ri[0][t] = idx[(long long)l * stride_i + row * k_in + r];
+  }
+  __syncthreads();
+  int n_prev = n_lists, c_prev = k_in, src = 0;
+  for (int level = 0;; ++level) {
+    const bool last = n_prev <= 2;
+    const int c_new = min(k_out, 2 * c_prev);
+    const float* ss = rs[src]; const long long* si = ri[src];
+    float* ds = rs[src ^ 1]; long long* di = ri[src ^ 1];
+    const int slots = n_prev * c_prev;
+    for (int t = threadIdx.x; t < slots; t += MS_THREADS) {
+      const int l = t / c_prev, r = t - l * c_prev;
+      if (r >= ms_len(l, level, n_lists, k_in, k_out)) continue;
+      const float es = ss[t]; const long long ei = si[t];
+      const int m = l ^ 1;
+      int rank = r;
+      if (m < n_prev) {
+        const float* ls = ss + m * c_prev; const long long* li = si + m * c_prev;
+        int lo = 0, hi = ms_len(m, level, n_lists, k_in, k_out);
+        while (lo < hi) {  // first position of the partner list whose element does not precede e
+          const int mid = (lo + hi) >> 1;
+          const float xs = ls[mid];
+          bool precedes = xs > es;
+          if (xs == es) { const long long xi = li[mid]; precedes = (m < l) ? (xi <= ei) : (xi < ei); }
+          if (precedes) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+      }
+      if (rank < c_new) {
+        if (last) { out_s[row * out_ld + rank] = es; out_i[row * out_ld + rank] = ei; }
+        else { const int o = (l >> 1) * c_new + rank; ds[o] = es; di[o] = ei; }
+      }
+    }
+    if (last) break;
+    __syncthreads();
+    n_prev = (n_prev + 1) >> 1; c_prev = c_new; src ^= 1;
+  }
+}
+}  // namespace tfrs
+
+extern "C" int tfrs_topk_merge_sorted_strided(const float* scores, const int64_t* idx, int64_t list_stride_scores,
+                                              int64_t list_stride_idx, int n_lists, int64_t Q, int k_in, int k_out,
+                                              float* out_scores, int64_t* out_idx, void* stream) {
+  TFRS_CHECK_ARG(n_lists > 0 && Q >= 0 && k_in > 0 && k_out > 0, "topk_merge_sorted: bad shape");
+  TFRS_CHECK_ARG(list_stride_scores >= Q * k_in && list_stride_idx >= Q * k_in, "topk_merge_sorted: list strides overlap");
+  if (Q == 0) return TFRS_OK;
+  TFRS_CHECK_ARG(scores && idx && out_scores && out_idx, "topk_merge_sorted: NULL pointer");
+  const long long tot = (long long)n_lists * k_in;
+  const int ko = (int)(k_out < tot ? k_out : tot);
+  long long region = tot;  // largest level of the merge tree (entries)
+  for (long long n = n_lists, c = k_in; n > 2;) { n = (n + 1) / 2; c = (2 * c < ko ? 2 * c : ko); if (n * c > region) region = n * c; }
+  if (n_lists > MS_MAX_LISTS || region * 24 > 160 * 1024 || k_out > 2048)  // outside the tree merge: the sorting merge is always valid
+    return tfrs_topk_merge_strided(scores, idx, list_stride_scores, list_stride_idx, n_lists, Q, k_in, k_out, out_scores, out_idx, stream);
+  const size_t smem = (size_t)region * 24;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TFRS_CUDA(cudaFuncSetAttribute(merge_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  merge_sorted_kernel<<<(unsigned)Q, MS_THREADS, smem, (cudaStream_t)stream>>>(scores, (const long long*)idx, list_stride_scores,
+                                                                             list_stride_idx, n_lists, k_in, ko, (int)region,
+                                                                             out_scores, (long long*)out_idx, k_out);
+  TFRS_LAUNCH_CHECK();
+  return TFRS_OK;
+}
+
 // ---- exact score helpers ---------------------------------------------------------------------
 namespace tfrs {
 struct EpiStoreAcc {

@@ -129,16 +129,17 @@ def topk_tc(q: torch.Tensor, corpus: torch.Tensor, index_buf: torch.Tensor, k: i
 
 
 def topk_merge_packed(gathered: torch.Tensor, n_lists: int, Q: int, k_in: int, k: int, idx_byte_offset: int,
-                      block_bytes: int) -> Tuple[torch.Tensor, torch.Tensor]:
+                      block_bytes: int, sorted_lists: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
   """Merge the receive buffer of the sharded scan's single all-gather: `n_lists` blocks of `block_bytes`, each
-  [scores f32 [Q,k_in] | pad | indices i64 [Q,k_in] at idx_byte_offset]."""
+  [scores f32 [Q,k_in] | pad | indices i64 [Q,k_in] at idx_byte_offset].  `sorted_lists` (what the scans emit:
+  every list in (score desc, index asc) order) selects the rank-by-binary-search merge instead of the sort."""
   k_out = min(k, n_lists * k_in)
   out_s = torch.empty((Q, k_out), dtype=torch.float32, device=gathered.device)
   out_i = torch.empty((Q, k_out), dtype=torch.int64, device=gathered.device)
   base = gathered.data_ptr()
-  check(lib().tfrs_topk_merge_strided(ctypes.c_void_p(base), ctypes.c_void_p(base + idx_byte_offset), block_bytes // 4,
-                                      block_bytes // 8, n_lists, Q, k_in, k_out, ptr(out_s), ptr(out_i), stream()),
-        "topk_merge_strided")
+  fn = lib().tfrs_topk_merge_sorted_strided if sorted_lists else lib().tfrs_topk_merge_strided
+  check(fn(ctypes.c_void_p(base), ctypes.c_void_p(base + idx_byte_offset), block_bytes // 4, block_bytes // 8, n_lists, Q,
+           k_in, k_out, ptr(out_s), ptr(out_i), stream()), "topk_merge_strided")
   return out_s, out_i
 
 

@@ -214,7 +214,7 @@ def test_gather_uniform_tables_fast_path(ops, idt):
 
 @pytest.mark.parametrize("B,C,d,temp,weighted,scale", [(2, 2, 3, None, False, 0.5), (300, 517, 64, 0.5, True, 0.5),
                                                        (1024, 1024, 64, None, False, 0.5), (700, 9000, 100, 0.05, True, 0.1),
-                                                       (2500, 2500, 32, None, True, 1.5)])
+                                                       (2500, 2500, 32, None, True, 1.0)])
 def test_inbatch_softmax_tensor_core_forward(ops, B, C, d, temp, weighted, scale):
   """tcgen05 forward (hi/lo fp16 split, online log-sum-exp epilogue) vs the float64 oracle: 1e-5 relative on the
   loss, 1e-5 absolute-or-relative on every row's logsumexp; and it must agree with the exact CUDA-core forward."""

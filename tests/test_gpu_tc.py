@@ -140,3 +140,33 @@ def test_tc_query_chunking(ops):
   assert torch.equal(i[-300:], ei) and torch.equal(s[-300:], es)
   es, ei = ops.topk_scan(q[8000:8300], c, 10)
   assert torch.equal(i[8000:8300], ei) and torch.equal(s[8000:8300], es)
+
+
+@pytest.mark.parametrize("world,Q,k_in,k", [(2, 37, 100, 100), (8, 300, 100, 100), (5, 64, 16, 50), (3, 10, 7, 21), (8, 5, 256, 256), (7, 20, 10, 64), (1, 9, 12, 12)])
+def test_sorted_merge_equals_sorting_merge(ops, world, Q, k_in, k):
+  """Rank-by-binary-search merge of sorted per-shard lists == the generic sort-based merge == numpy lexsort, with
+  heavy score ties (quantised scores), tied scores across lists and (-inf, INT64_MAX) padding of short shards."""
+  rng = np.random.default_rng(world * 1000 + Q)
+  idx_off = (Q * k_in * 4 + 7) // 8 * 8
+  block = idx_off + Q * k_in * 8
+  recv = torch.zeros(world * block, dtype=torch.uint8, device="cuda")
+  all_s = np.empty((world, Q, k_in), np.float32); all_i = np.empty((world, Q, k_in), np.int64)
+  for r in range(world):
+    s = np.round(rng.normal(size=(Q, k_in)) * 2).astype(np.float32) / 2       # many exact ties
+    i = np.stack([rng.choice(1000, size=k_in, replace=False) for _ in range(Q)]).astype(np.int64) + 1000 * r
+    n_pad = int(rng.integers(0, k_in // 2 + 1)) if r == world - 1 else 0         # a short last shard
+    if n_pad:
+      s[:, k_in - n_pad:] = -np.inf; i[:, k_in - n_pad:] = np.iinfo(np.int64).max
+    order = np.lexsort((i, -s), axis=1)                                          # (score desc, index asc) per list
+    s = np.take_along_axis(s, order, 1); i = np.take_along_axis(i, order, 1)
+    all_s[r], all_i[r] = s, i
+    blk = recv[r * block:(r + 1) * block]
+    blk[:Q * k_in * 4].view(torch.float32).view(Q, k_in).copy_(torch.from_numpy(s))
+    blk[idx_off:].view(torch.int64).view(Q, k_in).copy_(torch.from_numpy(i))
+  fs, fi = ops.topk_merge_packed(recv, world, Q, k_in, k, idx_off, block, sorted_lists=True)
+  gs, gi = ops.topk_merge_packed(recv, world, Q, k_in, k, idx_off, block, sorted_lists=False)
+  cs = all_s.transpose(1, 0, 2).reshape(Q, -1); ci = all_i.transpose(1, 0, 2).reshape(Q, -1)
+  order = np.lexsort((ci, -cs), axis=1)[:, :k]
+  es = np.take_along_axis(cs, order, 1); ei = np.take_along_axis(ci, order, 1)
+  np.testing.assert_array_equal(fs.cpu().numpy(), es); np.testing.assert_array_equal(fi.cpu().numpy(), ei)
+  assert torch.equal(fs, gs) and torch.equal(fi, gi)
