@@ -165,6 +165,17 @@ int tfrs_inbatch_softmax_tc_fwd(const float* q, const float* c, int64_t B, int64
                                 float inv_temperature, const float* sample_weight, float* loss, float* lse,
                                 void* ws, size_t ws_bytes, void* stream);
 
+/* K3b on the tensor cores (same contract and outputs as tfrs_inbatch_softmax_bwd; d <= 64): two launches of one
+ * flash-attention-backward-shaped kernel -- S = X.Y^T (tcgen05, split fp16 operands), G built from TMEM by the
+ * epilogue warps and written back over S (tcgen05.st), dX += G.Y with G read from TMEM and the Y tile as an MN-major
+ * operand; X = q gives dq, X = c gives dc.  Deterministic (no atomics).  workspace_bytes == 0 / TFRS_ERR_UNSUPPORTED
+ * outside its range. */
+size_t tfrs_inbatch_softmax_tc_bwd_workspace_bytes(int64_t B, int64_t C, int d);
+int tfrs_inbatch_softmax_tc_bwd(const float* q, const float* c, int64_t B, int64_t C, int d,
+                                float inv_temperature, const float* sample_weight, const float* lse,
+                                const float* grad_loss, float* dq, float* dc, void* ws, size_t ws_bytes,
+                                void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K4  sparse Adagrad on the rows touched by a batch (optimizer.apply_gradients with IndexedSlices,
  * models/base.py:77-78; Adagrad chosen by the user, README.md:84).  Duplicate ids are summed in

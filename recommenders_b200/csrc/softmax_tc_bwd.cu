@@ -1,0 +1,354 @@
+// softmax_tc_bwd.cu -- K3b on the tensor cores: backward of the in-batch softmax loss of tfrs.tasks.Retrieval
+//   (tape.gradient at models/base.py:77 through tasks/retrieval.py:178-210)
+//   G_ij = (softmax(s)_ij - [i == j]) * w_i * grad_loss / T ;   dq = G . c  [B,d] ;   dc = G^T . q  [C,d]
+// as two launches of ONE kernel (flash-attention-backward shape, deterministic -- no atomics):
+//   stationary operand X (128 rows = TMEM lanes, resident in smem), streaming operand Y (128-row tiles, bulk-TMA ring)
+//     S   = X . Y^T          tcgen05 SS-mode, hi/lo fp16 split operands (3 MMAs per K16), fp32 in TMEM
+//     A   = (exp(S/T - lse_q) - diag) * w_q     computed by the epilogue warps from TMEM, split into fp16 hi/lo and
+//                                               written back IN PLACE over S with tcgen05.st (128 fp32 cols -> 64+64)
+//     dX += A . Y            tcgen05 TS-mode: A from TMEM, Y straight from the same smem tile as an MN-major operand
+//   launch 1: X = q, Y = c  -> dq ;  launch 2: X = c, Y = q (lse/w become per-column vectors staged with the tile) -> dc.
+// The [B,C] logits / probabilities never touch HBM; the scores are the same split products as the forward pass
+// (softmax_tc.cu), so exp(s - lse) is consistent with the saved lse.  d <= 64.
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "tc_split.cuh"
+
+namespace tfrs {
+namespace tc {
+
+constexpr int SB_THREADS = 640;
+constexpr int SB_STAGES = 4;
+constexpr int SB_Y_BYTES = 32768;              // one 128-row tile: hi 16 KB | lo 16 KB
+constexpr int SB_STAGE_BYTES = SB_Y_BYTES + 1024;  // + lse[128] | w[128] of the tile (transposed launch)
+constexpr float SB_LOG2E = 1.4426950408889634f;
+
+struct SoftmaxBwdParams {
+  const unsigned char* ximg; const unsigned char* yimg;
+  const CxStats* xst; const CxStats* yst; const CxStats* wst;
+  const float* lse_pad; const float* w_pad;   // indexed by QUERY, padded to a multiple of 128 (w already * 2^wst.exp)
+  const float* grad_loss;
+  long long n_x_rows, n_y_valid, n_ytiles, part_stride;
+  int n_xb, parts, d;
+  float inv_t;
+  float* out;
+};
+
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(SB_THREADS, 1)
+softmax_tc_bwd_kernel(const SoftmaxBwdParams p) {
+  extern __shared__ __align__(1024) unsigned char sb_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sb_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sX = smem;                       // 32 KB
+  unsigned char* sY = smem + 32768;               // SB_STAGES x SB_STAGE_BYTES
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sY + SB_STAGES * SB_STAGE_BYTES);
+  uint64_t* y_full = bars;
+  uint64_t* y_empty = bars + SB_STAGES;
+  uint64_t* x_full = bars + 2 * SB_STAGES;
+  uint64_t* s_full = x_full + 1;     // [2]
+  uint64_t* g_ready = s_full + 2;    // [2]
+  uint64_t* dx_full = g_ready + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dx_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int xb = blockIdx.x % p.n_xb, part = blockIdx.x / p.n_xb;
+  const long long t_begin = (long long)part * p.n_ytiles / p.parts;
+  const long long t_end = (long long)(part + 1) * p.n_ytiles / p.parts;
+  const int n_iter = (int)(t_end - t_begin);
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < SB_STAGES; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
+    mbar_init(x_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&g_ready[b], 8); }
+    mbar_init(dx_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_dx = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(x_full, 32768);
+      bulk_g2s(sX, p.ximg + (long long)xb * 32768, 32768, x_full);
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < n_iter; ++it) {
+        mbar_wait(&y_empty[stage], phase ^ 1);
+        unsigned char* dst = sY + stage * SB_STAGE_BYTES;
+        const long long tile = t_begin + it;
+        mbar_expect_tx(&y_full[stage], TRANSPOSED ? SB_STAGE_BYTES : SB_Y_BYTES);
+        bulk_g2s(dst, p.yimg + tile * SB_Y_BYTES, SB_Y_BYTES, &y_full[stage]);
+        if (TRANSPOSED) {
+          bulk_g2s(dst + SB_Y_BYTES, p.lse_pad + tile * 128, 512, &y_full[stage]);
+          bulk_g2s(dst + SB_Y_BYTES + 512, p.w_pad + tile * 128, 512, &y_full[stage]);
+        }
+        if (++stage == SB_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(x_full, 0);
+      tc_fence_after();
+      const uint32_t x0 = smem_u32(sX);
+      const uint64_t x_hi = make_smem_desc(x0), x_lo = make_smem_desc(x0 + 16384);
+      // dX(u) += A(u) . Y(u):  A from TMEM buffer u&1 (hi | lo per 64-column half), Y tile as MN-major B (K = its rows)
+      auto issue_dx = [&](int u) {
+        const int buf = u & 1, stage = u % SB_STAGES;
+        mbar_wait(&g_ready[buf], (uint32_t)((u >> 1) & 1));
+        tc_fence_after();
+        const uint32_t y0 = smem_u32(sY + stage * SB_STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t a_hi = tmem_base + (uint32_t)(buf * 128 + 64 * (j >> 2) + 8 * (j & 3));
+          const uint32_t a_lo = a_hi + 32;
+          const uint64_t b_hi = make_smem_desc(y0 + j * 2048), b_lo = make_smem_desc(y0 + 16384 + j * 2048);
+          umma_f16_ts(tmem_dx, a_hi, b_hi, IDESC_F16_M128_N64_BMN, (uint32_t)((u | j) != 0));
+          umma_f16_ts(tmem_dx, a_lo, b_hi, IDESC_F16_M128_N64_BMN, 1u);
+          umma_f16_ts(tmem_dx, a_hi, b_lo, IDESC_F16_M128_N64_BMN, 1u);
+        }
+        umma_commit(&y_empty[stage]);
+      };
+      for (int it = 0; it < n_iter; ++it) {
+        const int buf = it & 1, stage = it % SB_STAGES;
+        mbar_wait(&y_full[stage], (uint32_t)((it / SB_STAGES) & 1));
+        tc_fence_after();
+        const uint32_t y0 = smem_u32(sY + stage * SB_STAGE_BYTES);
+        const uint64_t y_hi = make_smem_desc(y0), y_lo = make_smem_desc(y0 + 16384);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint64_t o = (uint64_t)(k4 * 2);
+          // same three products, in the same order, as the forward pass (q_hi c_hi, q_lo c_hi, q_hi c_lo)
+          umma_f16(d_tmem, x_hi + o, y_hi + o, IDESC_F16_M128_N128, (uint32_t)(k4 != 0));
+          if (TRANSPOSED) {
+            umma_f16(d_tmem, x_hi + o, y_lo + o, IDESC_F16_M128_N128, 1u);
+            umma_f16(d_tmem, x_lo + o, y_hi + o, IDESC_F16_M128_N128, 1u);
+          } else {
+            umma_f16(d_tmem, x_lo + o, y_hi + o, IDESC_F16_M128_N128, 1u);
+            umma_f16(d_tmem, x_hi + o, y_lo + o, IDESC_F16_M128_N128, 1u);
+          }
+        }
+        umma_commit(&s_full[buf]);
+        if (it >= 1) issue_dx(it - 1);
+      }
+      if (n_iter > 0) issue_dx(n_iter - 1);
+      umma_commit(dx_full);
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int grp = ew >> 3, half = (ew >> 2) & 1, quad = ew & 3;
+    const int r_local = quad * 32 + lane;
+    const long long row = (long long)xb * 128 + r_local;
+    const float scale = ldexpf(p.inv_t, -(p.xst->exp + p.yst->exp));  // accumulator -> logit (natural units)
+    float lse_r = 0.f, w_r = 0.f;
+    if (!TRANSPOSED) { lse_r = p.lse_pad[row]; w_r = p.w_pad[row]; }  // padded arrays: in range for every row of the block
+    for (int it = grp; it < n_iter; it += 2) {
+      const int stage = it % SB_STAGES;
+      const long long col0 = (t_begin + it) * 128 + half * 64;
+      mbar_wait(&s_full[grp], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * 128 + half * 64);
+      uint32_t r[64];
+      tmem_ld64(taddr, r);
+      tmem_ld_wait64(r);
+      if (TRANSPOSED) mbar_wait(&y_full[stage], (uint32_t)((it / SB_STAGES) & 1));  // the tile's lse | w vectors (bulk-copied)
+      const float4* aux4 = reinterpret_cast<const float4*>(sY + stage * SB_STAGE_BYTES + SB_Y_BYTES) + half * 16;
+      const int n_valid = (int)max(0ll, min(64ll, p.n_y_valid - col0));
+      const int jd = (row >= col0 && row < col0 + 64) ? (int)(row - col0) : -1;  // the positive: query i <-> candidate i
+      uint32_t o[64];
+#pragma unroll
+      for (int j4 = 0; j4 < 16; ++j4) {
+        float lq[4] = {lse_r, lse_r, lse_r, lse_r}, wq[4] = {w_r, w_r, w_r, w_r};
+        if (TRANSPOSED) {
+          const float4 l4 = aux4[j4], w4 = aux4[32 + j4];
+          lq[0] = l4.x; lq[1] = l4.y; lq[2] = l4.z; lq[3] = l4.w;
+          wq[0] = w4.x; wq[1] = w4.y; wq[2] = w4.z; wq[3] = w4.w;
+        }
+        float a[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 4 * j4 + e;
+          float pr = ex2_approx(fmaf(__uint_as_float(r[j]), scale, -lq[e]) * SB_LOG2E);
+          if (j == jd) pr -= 1.0f;
+          a[e] = (j < n_valid) ? pr * wq[e] : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const __half2 h = __floats2half2_rn(a[2 * e], a[2 * e + 1]);
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn(a[2 * e] - hf.x, a[2 * e + 1] - hf.y);
+          o[2 * j4 + e] = *reinterpret_cast<const uint32_t*>(&h);
+          o[32 + 2 * j4 + e] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+      }
+      tmem_st64(taddr, o);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&g_ready[grp]);
+    }
+    // ---- dX block: 128 rows x 64 columns of fp32 in TMEM; thread = (row, 16 columns)
+    mbar_wait(dx_full, 0);
+    tc_fence_after();
+    const int c0 = grp * 32 + half * 16;
+    if (n_iter > 0) {
+      uint32_t acc[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + 256u + (uint32_t)c0, acc);
+      tmem_ld_wait16(acc);
+      if (row < p.n_x_rows) {
+        const float gl = p.grad_loss ? p.grad_loss[0] : 1.0f;
+        const float fs = ldexpf(gl * p.inv_t, -(p.wst->exp + p.yst->exp));
+        float* dst = p.out + (long long)part * p.part_stride + row * p.d;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < p.d) dst[c0 + i] = __uint_as_float(acc[i]) * fs;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// max |w| (1 when w == NULL) -> the exact power-of-two scale that puts it in [2^13, 2^14)
+__global__ void __launch_bounds__(1024) sb_wstats_kernel(const float* __restrict__ w, long long B, CxStats* __restrict__ st) {
+  __shared__ float red[32];
+  float a = w ? 0.f : 1.0f;
+  if (w) for (long long i = threadIdx.x; i < B; i += 1024) a = fmaxf(a, fabsf(w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 32; ++i) a = fmaxf(a, red[i]);
+    int x = 0;
+    const bool ok = a > 0.f && a < INFINITY;
+    if (ok) (void)frexpf(a, &x);
+    st->amax_bits = __float_as_uint(a);
+    st->exp = ok ? (CX_TARGET_EXP - x) : 0;
+  }
+}
+__global__ void __launch_bounds__(256)
+sb_prep_kernel(const float* __restrict__ lse, const float* __restrict__ w, long long B, long long Bpad,
+               const CxStats* __restrict__ wst, float* __restrict__ lse_pad, float* __restrict__ w_pad) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= Bpad) return;
+  lse_pad[i] = i < B ? lse[i] : 0.f;
+  w_pad[i] = i < B ? ldexpf(w ? w[i] : 1.0f, wst->exp) : 0.f;
+}
+// out[e] = sum_z partial[z][e], z ascending (deterministic)
+__global__ void __launch_bounds__(256)
+sb_reduce_parts_kernel(const float* __restrict__ partial, long long elems, int parts, float* __restrict__ out) {
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (e >= elems) return;
+  float a = partial[e];
+  for (int z = 1; z < parts; ++z) a += partial[(long long)z * elems + e];
+  out[e] = a;
+}
+
+static int sb_parts(long long n_xb, long long n_ytiles) {
+  int parts = 1; double best = 0.0;
+  const int sms = sm_count();
+  for (int c = 1; c <= 16 && (c == 1 || n_ytiles / c >= 8); ++c) {
+    const long long ctas = n_xb * c;
+    const double eff = (double)ctas / (double)(ceil_div(ctas, sms) * sms);
+    if (eff > best + 0.02) { best = eff; parts = c; }
+  }
+  return parts;
+}
+
+struct SbPlan {
+  long long q_tiles, c_tiles; int parts_q, parts_c;
+  size_t o_qst, o_cst, o_wst, o_qimg, o_cimg, o_lse, o_w, o_partial, total;
+};
+static bool sb_plan(long long B, long long C, int d, SbPlan& pl) {
+  if (B <= 0 || C < B || d <= 0 || d > 64) return false;
+  pl.q_tiles = ceil_div(B, 128); pl.c_tiles = ceil_div(C, 128);
+  pl.parts_q = sb_parts(pl.q_tiles, pl.c_tiles);   // dq: X = q blocks, Y = c tiles
+  pl.parts_c = sb_parts(pl.c_tiles, pl.q_tiles);   // dc: X = c blocks, Y = q tiles
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 1024); return r; };
+  pl.o_qst = take(sizeof(CxStats)); pl.o_cst = take(sizeof(CxStats)); pl.o_wst = take(sizeof(CxStats));
+  pl.o_qimg = take((size_t)pl.q_tiles * 32768);
+  pl.o_cimg = take((size_t)pl.c_tiles * 32768);
+  pl.o_lse = take((size_t)pl.q_tiles * 128 * 4);
+  pl.o_w = take((size_t)pl.q_tiles * 128 * 4);
+  size_t pq = pl.parts_q > 1 ? (size_t)pl.parts_q * B * d * 4 : 0, pc = pl.parts_c > 1 ? (size_t)pl.parts_c * C * d * 4 : 0;
+  pl.o_partial = take(pq > pc ? pq : pc);
+  pl.total = o;
+  return true;
+}
+
+}  // namespace tc
+}  // namespace tfrs
+using namespace tfrs;
+using namespace tfrs::tc;
+
+extern "C" size_t tfrs_inbatch_softmax_tc_bwd_workspace_bytes(int64_t B, int64_t C, int d) {
+  SbPlan pl;
+  return sb_plan(B, C, d, pl) ? pl.total : 0;
+}
+
+extern "C" int tfrs_inbatch_softmax_tc_bwd(const float* q, const float* c, int64_t B, int64_t C, int d, float inv_temperature,
+                                           const float* sample_weight, const float* lse, const float* grad_loss, float* dq,
+                                           float* dc, void* ws, size_t ws_bytes, void* stream) {
+  TFRS_CHECK_ARG(q && c && lse && dq && dc, "inbatch_softmax_tc_bwd: NULL pointer");
+  SbPlan pl;
+  if (!sb_plan(B, C, d, pl)) { set_error("inbatch_softmax_tc_bwd: shape outside the tensor-core path (need B <= C, d <= 64)"); return TFRS_ERR_UNSUPPORTED; }
+  if (!ws || ws_bytes < pl.total) { set_error("inbatch_softmax_tc_bwd: workspace too small"); return TFRS_ERR_WORKSPACE_TOO_SMALL; }
+  TFRS_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "inbatch_softmax_tc_bwd: workspace must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* w8 = (unsigned char*)ws;
+  CxStats* qst = (CxStats*)(w8 + pl.o_qst); CxStats* cst = (CxStats*)(w8 + pl.o_cst); CxStats* wst = (CxStats*)(w8 + pl.o_wst);
+  unsigned char* qimg = w8 + pl.o_qimg; unsigned char* cimg = w8 + pl.o_cimg;
+  float* lse_pad = (float*)(w8 + pl.o_lse); float* w_pad = (float*)(w8 + pl.o_w); float* partial = (float*)(w8 + pl.o_partial);
+  TFRS_CUDA(cudaMemsetAsync(w8, 0, 3072, st));
+  cx_amax_kernel<<<(unsigned)ceil_div(B * 32, 256), 256, 0, st>>>(q, B, d, d, qst);
+  TFRS_LAUNCH_CHECK();
+  cx_amax_kernel<<<(unsigned)ceil_div(C * 32, 256), 256, 0, st>>>(c, C, d, d, cst);
+  TFRS_LAUNCH_CHECK();
+  cx_exp_kernel<<<1, 1, 0, st>>>(qst);
+  TFRS_LAUNCH_CHECK();
+  cx_exp_kernel<<<1, 1, 0, st>>>(cst);
+  TFRS_LAUNCH_CHECK();
+  cx_split_image_kernel<false><<<(unsigned)ceil_div(pl.q_tiles * 128 * 8, 256), 256, 0, st>>>(q, B, d, d, 1, pl.q_tiles, qst, qimg);
+  TFRS_LAUNCH_CHECK();
+  cx_split_image_kernel<false><<<(unsigned)ceil_div(pl.c_tiles * 128 * 8, 256), 256, 0, st>>>(c, C, d, d, 1, pl.c_tiles, cst, cimg);
+  TFRS_LAUNCH_CHECK();
+  sb_wstats_kernel<<<1, 1024, 0, st>>>(sample_weight, B, wst);
+  TFRS_LAUNCH_CHECK();
+  sb_prep_kernel<<<(unsigned)ceil_div(pl.q_tiles * 128, 256), 256, 0, st>>>(lse, sample_weight, B, pl.q_tiles * 128, wst, lse_pad, w_pad);
+  TFRS_LAUNCH_CHECK();
+  const size_t smem = 32768 + (size_t)SB_STAGES * SB_STAGE_BYTES + 1024 + 256;
+  static bool attr = false;
+  if (!attr) {
+    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  SoftmaxBwdParams p{};
+  p.xst = qst; p.yst = cst; p.wst = wst; p.lse_pad = lse_pad; p.w_pad = w_pad; p.grad_loss = grad_loss; p.d = d; p.inv_t = inv_temperature;
+  // ---- dq: X = q, Y = c
+  p.ximg = qimg; p.yimg = cimg; p.n_x_rows = B; p.n_y_valid = C; p.n_ytiles = pl.c_tiles; p.n_xb = (int)pl.q_tiles; p.parts = pl.parts_q;
+  p.part_stride = B * (long long)d; p.out = pl.parts_q > 1 ? partial : dq;
+  softmax_tc_bwd_kernel<false><<<(unsigned)(pl.q_tiles * pl.parts_q), SB_THREADS, smem, st>>>(p);
+  TFRS_LAUNCH_CHECK();
+  if (pl.parts_q > 1) {
+    sb_reduce_parts_kernel<<<(unsigned)ceil_div(B * d, 256), 256, 0, st>>>(partial, B * (long long)d, pl.parts_q, dq);
+    TFRS_LAUNCH_CHECK();
+  }
+  // ---- dc: X = c, Y = q (only the B query rows exist; candidates beyond B are pure negatives)
+  p.ximg = cimg; p.yimg = qimg; p.xst = cst; p.yst = qst; p.n_x_rows = C; p.n_y_valid = B; p.n_ytiles = pl.q_tiles; p.n_xb = (int)pl.c_tiles;
+  p.parts = pl.parts_c; p.part_stride = C * (long long)d; p.out = pl.parts_c > 1 ? partial : dc;
+  softmax_tc_bwd_kernel<true><<<(unsigned)(pl.c_tiles * pl.parts_c), SB_THREADS, smem, st>>>(p);
+  TFRS_LAUNCH_CHECK();
+  if (pl.parts_c > 1) {
+    sb_reduce_parts_kernel<<<(unsigned)ceil_div(C * d, 256), 256, 0, st>>>(partial, C * (long long)d, pl.parts_c, dc);
+    TFRS_LAUNCH_CHECK();
+  }
+  return TFRS_OK;
+}

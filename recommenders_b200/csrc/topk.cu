@@ -164,12 +164,6 @@ namespace tfrs {
 constexpr int MS_THREADS = 256;
 constexpr int MS_MAX_LISTS = 64;
 
-__device__ __forceinline__ int ms_len(int i, int level, int n_lists, int k_in, int k_out) {
-  long long cnt = min((long long)1 << level, (long long)n_lists - ((long long)i << level));
-  long long len = cnt * k_in;
-  return (int)(len < k_out ? len : k_out);
-}
-
 __global__ void __launch_bounds__(MS_THREADS)
 merge_sorted_kernel(const float* __restrict__ s, const long long* __restrict__ idx, long long stride_s, long long stride_i,
                     int n_lists, int k_in, int k_out, int region, float* __restrict__ out_s, long long* __restrict__ out_i,
@@ -178,6 +172,8 @@ merge_sorted_kernel(const float* __restrict__ s, const long long* __restrict__ i
   // two ping-pong regions of `region` entries: indices (8 B) then scores (4 B)
   long long* ri[2] = {reinterpret_cast<long long*>(ms_smem), reinterpret_cast<long long*>(ms_smem) + region};
   float* rs[2] = {reinterpret_cast<float*>(ms_smem + (size_t)region * 16), reinterpret_cast<float*>(ms_smem + (size_t)region * 16) + region};
+  __shared__ int lens[2][MS_MAX_LISTS];
+  __shared__ float tau_sh;
   const long long row = blockIdx.x;
   const int total = n_lists * k_in;
   for (int t = threadIdx.x; t < total; t += MS_THREADS) {
@@ -186,22 +182,44 @@ merge_sorted_kernel(const float* __restrict__ s, const long long* __restrict__ i
     ri[0][t] = idx[(long long)l * stride_i + row * k_in + r];
   }
   __syncthreads();
+  // Pruning: with rr = ceil(k_out / n_lists), the first rr entries of every list are >= tau = min_l list_l[rr-1], so
+  // at least k_out entries score >= tau and nothing scoring below tau can be in the result.
+  const int rr = min(k_in, (k_out + n_lists - 1) / n_lists);
+  if (threadIdx.x < 32) {
+    float m = INFINITY;
+    for (int l = threadIdx.x; l < n_lists; l += 32) m = fminf(m, rs[0][l * k_in + rr - 1]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) tau_sh = m;
+  }
+  __syncthreads();
+  if (threadIdx.x < n_lists) {  // entries of this list that score >= tau (the list is descending)
+    const float tau = tau_sh;
+    const float* ls = rs[0] + threadIdx.x * k_in;
+    int lo = rr, hi = k_in;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ls[mid] >= tau) lo = mid + 1; else hi = mid; }
+    lens[0][threadIdx.x] = lo;
+  }
+  __syncthreads();
   int n_prev = n_lists, c_prev = k_in, src = 0;
-  for (int level = 0;; ++level) {
+  for (;;) {
     const bool last = n_prev <= 2;
     const int c_new = min(k_out, 2 * c_prev);
     const float* ss = rs[src]; const long long* si = ri[src];
     float* ds = rs[src ^ 1]; long long* di = ri[src ^ 1];
-    const int slots = n_prev * c_prev;
+    const int* ln = lens[src];
+    int cap = 0;
+    for (int l = 0; l < n_prev; ++l) cap = max(cap, ln[l]);
+    const int slots = n_prev * cap;
     for (int t = threadIdx.x; t < slots; t += MS_THREADS) {
-      const int l = t / c_prev, r = t - l * c_prev;
-      if (r >= ms_len(l, level, n_lists, k_in, k_out)) continue;
-      const float es = ss[t]; const long long ei = si[t];
+      const int l = t / cap, r = t - l * cap;
+      if (r >= ln[l]) continue;
+      const float es = ss[l * c_prev + r]; const long long ei = si[l * c_prev + r];
       const int m = l ^ 1;
       int rank = r;
       if (m < n_prev) {
         const float* ls = ss + m * c_prev; const long long* li = si + m * c_prev;
-        int lo = 0, hi = ms_len(m, level, n_lists, k_in, k_out);
+        int lo = 0, hi = ln[m];
         while (lo < hi) {  // first position of the partner list whose element does not precede e
           const int mid = (lo + hi) >> 1;
           const float xs = ls[mid];
@@ -217,8 +235,13 @@ merge_sorted_kernel(const float* __restrict__ s, const long long* __restrict__ i
       }
     }
     if (last) break;
+    const int n_new = (n_prev + 1) >> 1;
+    if (threadIdx.x < n_new) {
+      const int a = ln[2 * threadIdx.x], b2 = (2 * threadIdx.x + 1 < n_prev) ? ln[2 * threadIdx.x + 1] : 0;
+      lens[src ^ 1][threadIdx.x] = min(c_new, a + b2);
+    }
     __syncthreads();
-    n_prev = (n_prev + 1) >> 1; c_prev = c_new; src ^= 1;
+    n_prev = n_new; c_prev = c_new; src ^= 1;
   }
 }
 }  // namespace tfrs

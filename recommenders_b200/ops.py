@@ -299,6 +299,7 @@ class _InBatchSoftmax(torch.autograd.Function):
     ctx.save_for_backward(q, c, lse, w if w is not None else torch.empty(0, device=q.device))
     ctx.has_w = w is not None
     ctx.inv_t = inv_temperature
+    ctx.used_tc = bool(tcb)
     return loss.view(())
 
   @staticmethod
@@ -307,12 +308,32 @@ class _InBatchSoftmax(torch.autograd.Function):
     B, d = q.shape; C = c.shape[0]
     g = f32c(g, "grad").view(1)
     dq = torch.empty_like(q); dc = torch.empty_like(c)
+    tcb = lib().tfrs_inbatch_softmax_tc_bwd_workspace_bytes(B, C, d) if ctx.used_tc else 0
+    if tcb:  # tensor-core backward: same split products as the forward pass that produced `lse`
+      ws = workspace(tcb, q.device, "softmax_tc_bwd")
+      check(lib().tfrs_inbatch_softmax_tc_bwd(ptr(q), ptr(c), B, C, d, c_f(ctx.inv_t), ptr(w) if ctx.has_w else None,
+                                              ptr(lse), ptr(g), ptr(dq), ptr(dc), ptr(ws), ws.numel(), stream()),
+            "inbatch_softmax_tc_bwd")
+      return dq, dc, None, None
     wsb = lib().tfrs_inbatch_softmax_workspace_bytes(B, C, d)
     ws = workspace(wsb, q.device, "softmax")
     check(lib().tfrs_inbatch_softmax_bwd(ptr(q), ptr(c), B, C, d, c_f(ctx.inv_t), ptr(w) if ctx.has_w else None,
                                          ptr(lse), ptr(g), ptr(dq), ptr(dc), ptr(ws), ws.numel(), stream()),
           "inbatch_softmax_bwd")
     return dq, dc, None, None
+
+
+def inbatch_softmax_tc_bwd(q, c, lse, sample_weight=None, inv_temperature: float = 1.0, grad_loss=None):
+  """Tensor-core backward only (any B, d <= 64): returns (dq, dc) for the given saved `lse`."""
+  q = f32c(q, "query_embeddings"); c = f32c(c, "candidate_embeddings"); lse = f32c(lse, "lse")
+  B, d = q.shape; C = c.shape[0]
+  w = None if sample_weight is None else f32c(sample_weight, "sample_weight").view(-1)
+  g = None if grad_loss is None else f32c(grad_loss, "grad").view(1)
+  dq = torch.empty_like(q); dc = torch.empty_like(c)
+  ws = workspace(max(lib().tfrs_inbatch_softmax_tc_bwd_workspace_bytes(B, C, d), 256), q.device, "softmax_tc_bwd")
+  check(lib().tfrs_inbatch_softmax_tc_bwd(ptr(q), ptr(c), B, C, d, c_f(inv_temperature), ptr(w), ptr(lse), ptr(g), ptr(dq),
+                                          ptr(dc), ptr(ws), ws.numel(), stream()), "inbatch_softmax_tc_bwd")
+  return dq, dc
 
 
 def inbatch_softmax_loss(q: torch.Tensor, c: torch.Tensor, sample_weight: Optional[torch.Tensor] = None,

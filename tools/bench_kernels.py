@@ -106,7 +106,14 @@ def softmax_fwd_bwd():
 
 t = timeit(softmax_fwd_bwd, iters=5 if not quick else 3, warm=2)
 out["cfg3_inbatch_softmax_fwd_bwd"] = {"seconds": t, "TFLOPs": 8.0 * Bt * Bt * d / t / 1e12, "flops": 8.0 * Bt * Bt * d,
-                                       "path": "exact fp32 CUDA-core SGEMM, L2-resident row blocks"}
+                                       "path": "tcgen05 split-fp16 forward (online log-sum-exp) + tcgen05 backward (G in TMEM)"}
+with torch.no_grad():
+  t = timeit(lambda: ops.inbatch_softmax_tc(qe, ce), iters=10, warm=3)
+  out["cfg3_inbatch_softmax_fwd_only"] = {"seconds": t, "TFLOPs": 2.0 * Bt * Bt * d / t / 1e12}
+  _, lse_t = ops.inbatch_softmax_tc(qe, ce)
+  t = timeit(lambda: ops.inbatch_softmax_tc_bwd(qe, ce, lse_t), iters=10, warm=3)
+  out["cfg3_inbatch_softmax_bwd_only"] = {"seconds": t, "TFLOPs": 4.0 * Bt * Bt * d / t / 1e12,
+                                          "note": "algorithmic flops (dq + dc); the kernels also recompute S twice"}
 gq = qe.grad.detach().clone()
 
 
