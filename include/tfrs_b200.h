@@ -101,6 +101,14 @@ int tfrs_topk_tc_layout(int64_t Q, int64_t N, int d, int k, int64_t* out8);
  * descriptor, raw TMEM dump.  Not on any product path. */
 int tfrs_debug_umma_probe(const void* a_img, const void* b_img, uint32_t idesc, int n_cols, uint32_t* out, void* stream);
 
+/* Memory-system probe (tools/hbm_probe.py): 128-byte rows, the gather's thread layout; mode 0 copy, 1 random-row
+ * read only, 2 write only, 3 random read + sequential write, 4 random read + the gather's strided write.  Not on
+ * any product path. */
+int tfrs_debug_hbm_probe(int mode, const void* src, int64_t src_rows, void* dst, int64_t n, int64_t n_rows_out,
+                         int64_t ld_floats, float* sink, void* stream);
+/* A/B switch between the two gather kernels (0 lane-per-item, 1 warp-chunk = default); identical results. */
+int tfrs_debug_set_gather_variant(int variant);
+
 /* Optional per-stage device timing of tfrs_topk_tc_f32 (CUDA events on the launch stream; used by
  * bench.py for the roofline figure).  tfrs_profile_read synchronises the device and returns the summed
  * times in ms of stage 0 = query image, 1 = sampled pass + threshold, 2 = full filter pass (the
@@ -214,6 +222,14 @@ size_t tfrs_cross_tc_workspace_bytes(int64_t B, int D);
 int tfrs_cross_tc_fwd_f32(const float* x0, const float* x, const void* wbuf, const float* bias, int64_t B, int D,
                           int64_t ld, float diag_scale, float* out, float* prod, void* ws, size_t ws_bytes,
                           void* stream);
+
+/* K5b with both GEMMs on the tensor cores (same contract and outputs as tfrs_cross_bwd_f32): dx = gp.W^T + diag*gp + g
+ * and dW = x^T.gp as split-fp16 tcgen05 GEMMs (dW accumulates the batch in chunks of 1024 rows, partials summed in
+ * fixed order); gp = g*x0, dx0 = g*prod and dbias = colsum(gp) as in the exact path.  Deterministic. */
+size_t tfrs_cross_tc_bwd_workspace_bytes(int64_t B, int D);
+int tfrs_cross_tc_bwd_f32(const float* x0, const float* x, const float* W, const float* prod, const float* dout,
+                          int64_t B, int D, int64_t ld, float diag_scale, float* dx0, float* dx, float* dW,
+                          float* dbias, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -5,6 +5,7 @@
 //   bwd: gp = g*x0 ; dx0 = g*prod ; dx = gp . W^T + diag*gp + g ; dW = x^T . gp (deterministic split-K) ;
 //        dbias = colsum(gp) (two-level fixed-order reduction).
 #include "sgemm.cuh"
+#include "cross_tc.cuh"
 
 namespace tfrs {
 
@@ -119,6 +120,45 @@ extern "C" int tfrs_cross_bwd_f32(const float* x0, const float* x, const float* 
     int used = Z > 1 ? (int)ceil_div(B, kps) : 1;
     cross_reduce_splits<<<(unsigned)ceil_div((long long)D * D, 256), 256, 0, st>>>(part, (long long)D * D, used, dW);
     TFRS_LAUNCH_CHECK();
+  }
+  if (dbias) {
+    long long rps = ceil_div(B, CROSS_COL_SPLITS);
+    int used = (int)ceil_div(B, rps);
+    dim3 grid((unsigned)ceil_div(D, 256), (unsigned)used);
+    cross_colsum_partial<<<grid, 256, 0, st>>>(gp, B, D, rps, colpart);
+    TFRS_LAUNCH_CHECK();
+    cross_reduce_splits<<<(unsigned)ceil_div(D, 256), 256, 0, st>>>(colpart, D, used, dbias);
+    TFRS_LAUNCH_CHECK();
+  }
+  return TFRS_OK;
+}
+
+// ---- K5b with the two GEMMs on the tensor cores (cross_tc_bwd.cu); same contract and outputs as tfrs_cross_bwd_f32
+extern "C" size_t tfrs_cross_tc_bwd_workspace_bytes(int64_t B, int D) {
+  if (B <= 0 || D <= 0) return 0;
+  return align_up((size_t)B * D * 4, 1024) + align_up((size_t)CROSS_COL_SPLITS * D * 4, 1024) + tc::cross_tc_bwd_gemm_workspace(B, D);
+}
+
+extern "C" int tfrs_cross_tc_bwd_f32(const float* x0, const float* x, const float* W, const float* prod,
+                                     const float* dout, int64_t B, int D, int64_t ld, float diag_scale, float* dx0,
+                                     float* dx, float* dW, float* dbias, void* ws, size_t ws_bytes, void* stream) {
+  TFRS_CHECK_ARG(x0 && x && W && dout, "cross_tc_bwd: NULL pointer");
+  TFRS_CHECK_ARG(B > 0 && D > 0 && ld >= D && B < (1ll << 31), "cross_tc_bwd: bad shape");
+  TFRS_CHECK_ARG(!dx0 || prod, "cross_tc_bwd: dx0 needs the saved `prod`");
+  if (!ws || ws_bytes < tfrs_cross_tc_bwd_workspace_bytes(B, D)) { set_error("cross_tc_bwd: workspace too small"); return TFRS_ERR_WORKSPACE_TOO_SMALL; }
+  TFRS_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "cross_tc_bwd: workspace must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* w = (unsigned char*)ws;
+  float* gp = (float*)w; w += align_up((size_t)B * D * 4, 1024);
+  float* colpart = (float*)w; w += align_up((size_t)CROSS_COL_SPLITS * D * 4, 1024);
+  const size_t gemm_ws = ws_bytes - (size_t)(w - (unsigned char*)ws);
+  const long long total = (long long)B * D;
+  const unsigned blocks = (unsigned)(ceil_div(total, 256) < 148 * 16 ? ceil_div(total, 256) : 148 * 16);
+  cross_bwd_elem<<<blocks, 256, 0, st>>>(x0, prod, dout, B, D, ld, gp, dx0);
+  TFRS_LAUNCH_CHECK();
+  if (dx || dW) {
+    int rc = tc::cross_tc_bwd_gemms(x, W, gp, dout, B, D, ld, diag_scale, dx, dW, w, gemm_ws, st);
+    if (rc) return rc;
   }
   if (dbias) {
     long long rps = ceil_div(B, CROSS_COL_SPLITS);

@@ -66,6 +66,49 @@ gather_kernel(GatherParams p, long long n, float* __restrict__ out, long long ou
   }
 }
 
+// Variant "warp-chunk": a warp owns 32 consecutive batch rows of one table.  Lane l loads ids[i0+l] ONCE (one coalesced
+// 128-byte read per 32 rows instead of a redundant id read per 16-byte lane), row ids travel by shuffle, and the
+// warp then issues up to 8 independent 16-byte row reads per thread before the first store.
+template <typename IdT>
+__global__ void __launch_bounds__(GT_THREADS)
+gather_warpchunk_kernel(GatherParams p, long long n, float* __restrict__ out, long long out_ld) {
+  const int t = blockIdx.y;
+  const float4* __restrict__ table = reinterpret_cast<const float4*>(p.table[t]);
+  const IdT* __restrict__ ids = reinterpret_cast<const IdT*>(p.ids[t]);
+  const long long rows = p.rows[t];
+  const int L = p.dim[t] >> 2;             // 16-byte lanes per row: power of two, <= 32 (checked by the host)
+  const int lshift = 31 - __clz(L);
+  const int R = 32 >> lshift;              // rows covered by one warp-wide load
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (L - 1), rsel = lane >> lshift;
+  const long long i0 = ((long long)blockIdx.x * (GT_THREADS / 32) + (threadIdx.x >> 5)) * 32;
+  if (i0 >= n) return;
+  long long rid = -1;
+  if (i0 + lane < n) { const long long r = (long long)ids[i0 + lane]; rid = (r >= 0 && r < rows) ? r : -1; }
+  const bool lane_valid = i0 + lane < n;
+  float4* __restrict__ o4 = reinterpret_cast<float4*>(out + p.col_off[t]);
+  const long long ld4 = out_ld >> 2;
+  const int steps = 32 / R;                // warp-wide loads to cover the 32 rows
+  for (int s0 = 0; s0 < steps; s0 += 8) {
+    float4 v[8]; bool ok[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = (s0 + u) * R + rsel;   // row of the chunk this lane serves in step s0+u
+      const long long r = __shfl_sync(0xffffffffu, rid, j & 31);
+      const bool in = __shfl_sync(0xffffffffu, (int)lane_valid, j & 31) != 0;
+      ok[u] = (s0 + u) < steps && in;
+      v[u] = (ok[u] && r >= 0) ? __ldg(table + r * L + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = (s0 + u) * R + rsel;
+      if (ok[u]) o4[(i0 + j) * ld4 + sub] = v[u];
+    }
+  }
+}
+
+static int g_gather_variant = 1;
+
 }  // namespace tfrs
 using namespace tfrs;
 
@@ -98,6 +141,18 @@ extern "C" int tfrs_gather_f32(const float* const* tables, const int64_t* rows, 
     if (blocks < 1) blocks = 1;
     if (blocks > 1 << 20) blocks = 1 << 20;
     dim3 grid((unsigned)blocks, (unsigned)nt);
+    bool chunkable = vec && g_gather_variant == 1;
+    for (int t = 0; t < nt && chunkable; ++t) {
+      const int L = p.dim[t] / 4;
+      chunkable = L >= 1 && L <= 32 && (L & (L - 1)) == 0;
+    }
+    if (chunkable) {
+      dim3 g2((unsigned)ceil_div(n, (long long)GT_THREADS), (unsigned)nt);  // 32 rows per warp, 8 warps per CTA
+      if (ids_dtype == TFRS_I32) gather_warpchunk_kernel<int32_t><<<g2, GT_THREADS, 0, st>>>(p, n, out, out_ld);
+      else gather_warpchunk_kernel<int64_t><<<g2, GT_THREADS, 0, st>>>(p, n, out, out_ld);
+      TFRS_LAUNCH_CHECK();
+      continue;
+    }
     if (ids_dtype == TFRS_I32) {
       if (vec) gather_kernel<int32_t, true><<<grid, GT_THREADS, 0, st>>>(p, n, out, out_ld);
       else gather_kernel<int32_t, false><<<grid, GT_THREADS, 0, st>>>(p, n, out, out_ld);
@@ -109,3 +164,6 @@ extern "C" int tfrs_gather_f32(const float* const* tables, const int64_t* rows, 
   }
   return TFRS_OK;
 }
+
+// A/B switch for tools/bench_kernels.py: 0 = lane-per-item kernel, 1 = warp-chunk kernel (default).  Same results.
+extern "C" int tfrs_debug_set_gather_variant(int v) { g_gather_variant = v; return TFRS_OK; }

@@ -69,3 +69,56 @@ extern "C" int tfrs_debug_umma_probe(const void* a_img, const void* b_img, uint3
   TFRS_LAUNCH_CHECK();
   return TFRS_OK;
 }
+
+// ---- HBM access-pattern probe (tools/hbm_probe.py): what the memory system gives for the gather's access pattern --
+// rows of 128 B (32 floats); 8 threads x 16 B per row; 4 independent rows in flight per thread.
+//   mode 0: copy            dst[i] = src[i]                   (sequential read + sequential write)
+//   mode 1: random read     sink += src[hash(i)]              (random 128-byte rows, nothing written)
+//   mode 2: write only      dst[i] = const                    (sequential 128-byte rows)
+//   mode 3: random read + sequential write   dst[i] = src[hash(i)]
+//   mode 4: random read + strided write      dst[(i % n_rows_out) * ld + (i / n_rows_out) * 32] = src[hash(i)]   (the gather layout)
+namespace tfrs {
+__global__ void __launch_bounds__(256)
+hbm_probe_kernel(int mode, const float4* __restrict__ src, long long src_rows, float4* __restrict__ dst, long long n,
+                 long long n_rows_out, long long ld4, float* __restrict__ sink) {
+  const long long total = n * 8;  // 16-byte lanes
+  const long long stride = (long long)gridDim.x * 256;
+  float acc = 0.f;
+  for (long long w = (long long)blockIdx.x * 256 + threadIdx.x; w < total; w += stride * 4) {
+    float4 v[4]; long long o[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long e = w + u * stride;
+      o[u] = -1;
+      if (e < total) {
+        const long long i = e >> 3; const int l = (int)(e & 7);
+        long long r = i;
+        if (mode == 1 || mode >= 3) {  // cheap 32-bit mix, scaled into [0, src_rows) (src_rows < 2^32)
+          unsigned int h = (unsigned int)i * 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+          r = (long long)__umulhi(h, (unsigned int)src_rows);
+        }
+        if (mode != 2) v[u] = __ldg(src + r * 8 + l); else v[u] = make_float4(1.f, 2.f, 3.f, 4.f);
+        o[u] = (mode == 4) ? ((i % n_rows_out) * ld4 + (i / n_rows_out) * 8 + l) : (i * 8 + l);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (o[u] >= 0) {
+        if (mode == 1) acc += v[u].x + v[u].y + v[u].z + v[u].w;
+        else dst[o[u]] = v[u];
+      }
+    }
+  }
+  if (mode == 1 && acc == 123.456f) sink[0] = acc;
+}
+}  // namespace tfrs
+
+extern "C" int tfrs_debug_hbm_probe(int mode, const void* src, int64_t src_rows, void* dst, int64_t n, int64_t n_rows_out,
+                                    int64_t ld_floats, float* sink, void* stream) {
+  TFRS_CHECK_ARG(mode >= 0 && mode <= 4 && src && dst && sink && n > 0 && src_rows > 0, "hbm_probe: bad argument");
+  long long blocks = tfrs::ceil_div(n * 8, 256 * 4);
+  tfrs::hbm_probe_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mode, (const float4*)src, src_rows, (float4*)dst, n,
+                                                                               n_rows_out > 0 ? n_rows_out : 1, ld_floats / 4, sink);
+  TFRS_LAUNCH_CHECK();
+  return TFRS_OK;
+}

@@ -49,9 +49,9 @@ softmax_tc_kernel(const SoftmaxTcParams p) {
   uint64_t* full = bars;
   uint64_t* empty = bars + SX_STAGES;
   uint64_t* a_full = bars + 2 * SX_STAGES;
-  uint64_t* t_full = a_full + 1;
-  uint64_t* t_empty = t_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint64_t* t_full = a_full + 1;     // [ab][buf]: the two 128-row halves signal separately, so one half's epilogue warps
+  uint64_t* t_empty = t_full + 4;    //            pull from TMEM while the other half's are busy on the MUFU pipe
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x % p.nqb, part = blockIdx.x / p.nqb;
@@ -62,7 +62,7 @@ softmax_tc_kernel(const SoftmaxTcParams p) {
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < SX_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(a_full, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 16); }
+    for (int b = 0; b < 4; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -91,11 +91,11 @@ softmax_tc_kernel(const SoftmaxTcParams p) {
       for (int it = 0; it < n_iter; ++it) {
         const int buf = it & 1;
         const uint32_t tphase = (it >> 1) & 1;
-        mbar_wait(&t_empty[buf], tphase ^ 1);
         mbar_wait(&full[stage], phase);
-        tc_fence_after();
 #pragma unroll
         for (int ab = 0; ab < 2; ++ab) {
+          mbar_wait(&t_empty[ab * 2 + buf], tphase ^ 1);
+          tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)((ab * 2 + buf) * 128);
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) {
@@ -110,9 +110,9 @@ softmax_tc_kernel(const SoftmaxTcParams p) {
               umma_f16(d_tmem, a_hi + o, b_lo + o, IDESC_F16_M128_N128, 1u);
             }
           }
+          umma_commit(&t_full[ab * 2 + buf]);
         }
         umma_commit(&empty[stage]);
-        umma_commit(&t_full[buf]);
         if (++stage == SX_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -127,7 +127,7 @@ softmax_tc_kernel(const SoftmaxTcParams p) {
       const int buf = it & 1;
       const uint32_t tphase = (it >> 1) & 1;
       const long long col0 = (t_begin + it) * 128 + half * 64;
-      mbar_wait(&t_full[buf], tphase);
+      mbar_wait(&t_full[ab * 2 + buf], tphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ab * 2 + buf) * 128 + half * 64);
       uint32_t r[64];
@@ -135,28 +135,47 @@ softmax_tc_kernel(const SoftmaxTcParams p) {
       tmem_ld_wait64(r);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[buf]);
+      if (lane == 0) mbar_arrive(&t_empty[ab * 2 + buf]);
       const int n_valid = (int)min(64ll, p.C - col0);  // columns beyond C are zero-padded rows of the image
-      if (n_valid > 0) {
-        float v[64];
+      if (n_valid <= 0) continue;
+      const long long blk0 = (long long)qb * 256 + ab * 128;
+      const bool edge = n_valid < 64 || (blk0 < col0 + 64 && col0 < blk0 + 128);  // ragged tail, or the tile with the positives
+      float m_new, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      if (!edge) {
+        // scale2 > 0: the row maximum can be taken on the raw accumulators (FMNMX3 tree), one FFMA + one MUFU per score
+        float t[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float a0 = max3(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]), __uint_as_float(r[8 * g + 2]));
+          const float a1 = max3(__uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+          t[g] = max3(a0, a1, fmaxf(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7])));
+        }
+        const float tmax = max3(max3(t[0], t[1], t[2]), max3(t[3], t[4], t[5]), fmaxf(t[6], t[7]));
+        m_new = fmaxf(m2, tmax * scale2);
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          acc0 += ex2_approx(fmaf(__uint_as_float(r[j]), scale2, -m_new));
+          acc1 += ex2_approx(fmaf(__uint_as_float(r[j + 1]), scale2, -m_new));
+          acc2 += ex2_approx(fmaf(__uint_as_float(r[j + 2]), scale2, -m_new));
+          acc3 += ex2_approx(fmaf(__uint_as_float(r[j + 3]), scale2, -m_new));
+        }
+      } else {
         float tmax = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          v[j] = (j < n_valid) ? __uint_as_float(r[j]) * scale2 : -INFINITY;
-          tmax = fmaxf(tmax, v[j]);
-        }
+        for (int j = 0; j < 64; ++j)
+          if (j < n_valid) tmax = fmaxf(tmax, __uint_as_float(r[j]));
+        m_new = fmaxf(m2, tmax * scale2);
         if (row >= col0 && row < col0 + 64) {   // the positive of query i is candidate i (retrieval.py:185)
           const int jd = (int)(row - col0);
 #pragma unroll
-          for (int j = 0; j < 64; ++j) if (j == jd) pos2 = v[j];
+          for (int j = 0; j < 64; ++j) if (j == jd) pos2 = __uint_as_float(r[j]) * scale2;
         }
-        const float m_new = fmaxf(m2, tmax);
-        float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) acc += exp2f(v[j] - m_new);
-        l = l * exp2f(m2 - m_new) + acc;
-        m2 = m_new;
+        for (int j = 0; j < 64; ++j)
+          if (j < n_valid) acc0 += ex2_approx(fmaf(__uint_as_float(r[j]), scale2, -m_new));
       }
+      l = l * ex2_approx(m2 - m_new) + ((acc0 + acc1) + (acc2 + acc3));
+      m2 = m_new;
     }
     if (row < p.B) {
       p.partial[(row * p.parts + part) * 2 + half] = make_float2(m2, l);
@@ -204,13 +223,12 @@ static bool sx_plan(long long B, long long C, int d, SxPlan& pl) {
   pl.nqb = (int)ceil_div(B, 256);
   pl.Bp = (long long)pl.nqb * 256;
   pl.n_ctiles = ceil_div(C, 128);
-  // candidate parts: fill whole waves of the SMs, keep >= 8 tiles per CTA so the resident A block amortises
-  int parts = 1; double best = 0.0;
+  // candidate parts: minimise waves x (tiles per CTA + ~6 tile times of fixed cost: A load, pipeline fill, partials)
+  int parts = 1; double best = 1e30;
   const int sms = sm_count();
-  for (int c = 1; c <= 16 && (c == 1 || pl.n_ctiles / c >= 8); ++c) {
-    const long long ctas = (long long)pl.nqb * c;
-    const double eff = (double)ctas / (double)(ceil_div(ctas, sms) * sms);
-    if (eff > best + 0.02) { best = eff; parts = c; }
+  for (int c = 1; c <= 16 && c <= pl.n_ctiles; ++c) {
+    const double cost = (double)ceil_div((long long)pl.nqb * c, sms) * ((double)ceil_div(pl.n_ctiles, c) + 6.0);
+    if (cost < best * 0.97) { best = cost; parts = c; }
   }
   pl.parts = parts;
   pl.smem = (size_t)(2 + sx_stages(pl.kb)) * pl.kb * 32768 + 1024 + 256;
@@ -242,6 +260,7 @@ extern "C" int tfrs_inbatch_softmax_tc_fwd(const float* q, const float* c, int64
                                            void* stream) {
   TFRS_CHECK_ARG(q && c && loss && lse, "inbatch_softmax_tc_fwd: NULL pointer");
   SxPlan pl;
+  if (!(inv_temperature > 0.f)) { set_error("inbatch_softmax_tc_fwd: needs a positive temperature"); return TFRS_ERR_UNSUPPORTED; }
   if (!sx_plan(B, C, d, pl)) { set_error("inbatch_softmax_tc_fwd: shape outside the tensor-core path (need B <= C, d <= 128)"); return TFRS_ERR_UNSUPPORTED; }
   if (!ws || ws_bytes < pl.total) { set_error("inbatch_softmax_tc_fwd: workspace too small"); return TFRS_ERR_WORKSPACE_TOO_SMALL; }
   TFRS_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "inbatch_softmax_tc_fwd: workspace must be 16-byte aligned");
@@ -252,9 +271,9 @@ extern "C" int tfrs_inbatch_softmax_tc_fwd(const float* q, const float* c, int64
   float2* partial = (float2*)(w + pl.o_partial);
   float* pos = (float*)(w + pl.o_pos); float* rowloss = (float*)(w + pl.o_rowloss);
   TFRS_CUDA(cudaMemsetAsync(w, 0, 2048, st));  // both stats blocks
-  cx_amax_kernel<<<(unsigned)ceil_div(B * 32, 256), 256, 0, st>>>(q, B, d, d, qst);
+  cx_amax_kernel<<<cx_amax_grid(B), 256, 0, st>>>(q, B, d, d, qst);
   TFRS_LAUNCH_CHECK();
-  cx_amax_kernel<<<(unsigned)ceil_div(C * 32, 256), 256, 0, st>>>(c, C, d, d, cst);
+  cx_amax_kernel<<<cx_amax_grid(C), 256, 0, st>>>(c, C, d, d, cst);
   TFRS_LAUNCH_CHECK();
   cx_exp_kernel<<<1, 1, 0, st>>>(qst);
   TFRS_LAUNCH_CHECK();

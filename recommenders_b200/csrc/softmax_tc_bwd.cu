@@ -18,8 +18,14 @@
 namespace tfrs {
 namespace tc {
 
-constexpr int SB_THREADS = 640;
+constexpr int SB_THREADS = 640;                // warp 0 producer, 1 MMA, 2 TMEM alloc, 4-19 epilogue (TMEM lane quad = warp & 3)
+constexpr int SB_W_PROD = 0, SB_W_MMA = 1, SB_W_ALLOC = 2;
 constexpr int SB_STAGES = 4;
+// the tensor core's fp32 adder truncates: a chain of thousands of accumulations into the same TMEM tile drifts (5e-5 of
+// the gradient scale at C = 16384), so the dX tile is drained into fp32 registers (round-to-nearest adds) every
+// SB_DRAIN streamed tiles = 192 accumulation steps, the length of the forward Cross chain
+constexpr int SB_DRAIN = 8;
+constexpr int SB_BUFS = 3;                     // S/G accumulator buffers in TMEM (3 x 128 columns) + dX (64 columns)
 constexpr int SB_Y_BYTES = 32768;              // one 128-row tile: hi 16 KB | lo 16 KB
 constexpr int SB_STAGE_BYTES = SB_Y_BYTES + 1024;  // + lse[128] | w[128] of the tile (transposed launch)
 constexpr float SB_LOG2E = 1.4426950408889634f;
@@ -35,6 +41,46 @@ struct SoftmaxBwdParams {
   float* out;
 };
 
+// One thread's 64 accumulator columns -> A, split into fp16 hi (written in place over r[0..31]: output slot 2*j4+e
+// is only written after inputs 4*j4.. are consumed) and lo[32].
+//   non-transposed: A = (exp(s/T - lse_i) - diag) * 2^14 -- lse_r already carries the -14 ln2, the weight of row i is
+//                   applied once to the dX block;   transposed: A = (exp(s/T - lse_j) - diag) * w^_j (per-column vectors).
+// EDGE = the tile holds the diagonal or columns beyond the valid range (rare): masks compiled in only there.
+template <bool TRANSPOSED, bool EDGE>
+__device__ __forceinline__ void sb_transform(uint32_t (&r)[64], uint32_t (&lo)[32], float scale, float lse_r,
+                                             const float4* __restrict__ aux4, int n_valid, int jd) {
+#pragma unroll
+  for (int j4 = 0; j4 < 16; ++j4) {
+    float lq[4] = {lse_r, lse_r, lse_r, lse_r}, wq[4] = {16384.f, 16384.f, 16384.f, 16384.f};
+    if (TRANSPOSED) {
+      const float4 l4 = aux4[j4], w4 = aux4[32 + j4];
+      lq[0] = l4.x; lq[1] = l4.y; lq[2] = l4.z; lq[3] = l4.w;
+      wq[0] = w4.x; wq[1] = w4.y; wq[2] = w4.z; wq[3] = w4.w;
+    }
+    float a[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = 4 * j4 + e;
+      float pr = ex2_approx(fmaf(__uint_as_float(r[j]), scale, -lq[e]) * SB_LOG2E);
+      if (TRANSPOSED) {
+        if (EDGE && j == jd) pr -= 1.0f;
+        pr *= wq[e];
+      } else {
+        if (EDGE && j == jd) pr -= 16384.f;
+      }
+      a[e] = (!EDGE || j < n_valid) ? pr : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const __half2 h = __floats2half2_rn(a[2 * e], a[2 * e + 1]);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(a[2 * e] - hf.x, a[2 * e + 1] - hf.y);
+      r[2 * j4 + e] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[2 * j4 + e] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+  }
+}
+
 template <bool TRANSPOSED>
 __global__ void __launch_bounds__(SB_THREADS, 1)
 softmax_tc_bwd_kernel(const SoftmaxBwdParams p) {
@@ -46,10 +92,11 @@ softmax_tc_bwd_kernel(const SoftmaxBwdParams p) {
   uint64_t* y_full = bars;
   uint64_t* y_empty = bars + SB_STAGES;
   uint64_t* x_full = bars + 2 * SB_STAGES;
-  uint64_t* s_full = x_full + 1;     // [2]
-  uint64_t* g_ready = s_full + 2;    // [2]
-  uint64_t* dx_full = g_ready + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dx_full + 1);
+  uint64_t* s_full = x_full + 1;     // [SB_BUFS]
+  uint64_t* g_ready = s_full + SB_BUFS;
+  uint64_t* dx_full = g_ready + SB_BUFS;
+  uint64_t* dx_drained = dx_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dx_drained + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int xb = blockIdx.x % p.n_xb, part = blockIdx.x / p.n_xb;
@@ -57,21 +104,22 @@ softmax_tc_bwd_kernel(const SoftmaxBwdParams p) {
   const long long t_end = (long long)(part + 1) * p.n_ytiles / p.parts;
   const int n_iter = (int)(t_end - t_begin);
 
-  if (warp == 1 && lane == 0) {
+  if (warp == SB_W_MMA && lane == 0) {
     for (int s = 0; s < SB_STAGES; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
     mbar_init(x_full, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&g_ready[b], 8); }
+    for (int b = 0; b < SB_BUFS; ++b) { mbar_init(&s_full[b], 1); mbar_init(&g_ready[b], 8); }
     mbar_init(dx_full, 1);
+    mbar_init(dx_drained, 16);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == SB_W_ALLOC) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_dx = tmem_base + 256;
+  const uint32_t tmem_dx = tmem_base + SB_BUFS * 128;
 
-  if (warp == 0) {
+  if (warp == SB_W_PROD) {
     if (lane == 0) {
       mbar_expect_tx(x_full, 32768);
       bulk_g2s(sX, p.ximg + (long long)xb * 32768, 32768, x_full);
@@ -89,7 +137,7 @@ softmax_tc_bwd_kernel(const SoftmaxBwdParams p) {
         if (++stage == SB_STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == SB_W_MMA) {
     if (lane == 0) {
       mbar_wait(x_full, 0);
       tc_fence_after();
@@ -97,8 +145,10 @@ softmax_tc_bwd_kernel(const SoftmaxBwdParams p) {
       const uint64_t x_hi = make_smem_desc(x0), x_lo = make_smem_desc(x0 + 16384);
       // dX(u) += A(u) . Y(u):  A from TMEM buffer u&1 (hi | lo per 64-column half), Y tile as MN-major B (K = its rows)
       auto issue_dx = [&](int u) {
-        const int buf = u & 1, stage = u % SB_STAGES;
-        mbar_wait(&g_ready[buf], (uint32_t)((u >> 1) & 1));
+        const int buf = u % SB_BUFS, stage = u % SB_STAGES;
+        const int chunk = u / SB_DRAIN, first = (u % SB_DRAIN) == 0;
+        if (first && chunk > 0) mbar_wait(dx_drained, (uint32_t)((chunk - 1) & 1));  // epilogue took the previous chunk's sum
+        mbar_wait(&g_ready[buf], (uint32_t)((u / SB_BUFS) & 1));
         tc_fence_after();
         const uint32_t y0 = smem_u32(sY + stage * SB_STAGE_BYTES);
 #pragma unroll
@@ -106,14 +156,15 @@ softmax_tc_bwd_kernel(const SoftmaxBwdParams p) {
           const uint32_t a_hi = tmem_base + (uint32_t)(buf * 128 + 64 * (j >> 2) + 8 * (j & 3));
           const uint32_t a_lo = a_hi + 32;
           const uint64_t b_hi = make_smem_desc(y0 + j * 2048), b_lo = make_smem_desc(y0 + 16384 + j * 2048);
-          umma_f16_ts(tmem_dx, a_hi, b_hi, IDESC_F16_M128_N64_BMN, (uint32_t)((u | j) != 0));
+          umma_f16_ts(tmem_dx, a_hi, b_hi, IDESC_F16_M128_N64_BMN, (uint32_t)(!first || j != 0));
           umma_f16_ts(tmem_dx, a_lo, b_hi, IDESC_F16_M128_N64_BMN, 1u);
           umma_f16_ts(tmem_dx, a_hi, b_lo, IDESC_F16_M128_N64_BMN, 1u);
         }
         umma_commit(&y_empty[stage]);
+        if ((u % SB_DRAIN) == SB_DRAIN - 1 || u == n_iter - 1) umma_commit(dx_full);  // chunk complete
       };
       for (int it = 0; it < n_iter; ++it) {
-        const int buf = it & 1, stage = it % SB_STAGES;
+        const int buf = it % SB_BUFS, stage = it % SB_STAGES;
         mbar_wait(&y_full[stage], (uint32_t)((it / SB_STAGES) & 1));
         tc_fence_after();
         const uint32_t y0 = smem_u32(sY + stage * SB_STAGE_BYTES);
@@ -133,10 +184,10 @@ softmax_tc_bwd_kernel(const SoftmaxBwdParams p) {
           }
         }
         umma_commit(&s_full[buf]);
-        if (it >= 1) issue_dx(it - 1);
+        if (it >= 2) issue_dx(it - 2);   // two tiles behind: the epilogue of tile it-2 has had two S-MMA times to finish
       }
-      if (n_iter > 0) issue_dx(n_iter - 1);
-      umma_commit(dx_full);
+      if (n_iter >= 2) issue_dx(n_iter - 2);
+      issue_dx(n_iter - 1);
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;
@@ -144,74 +195,80 @@ softmax_tc_bwd_kernel(const SoftmaxBwdParams p) {
     const int r_local = quad * 32 + lane;
     const long long row = (long long)xb * 128 + r_local;
     const float scale = ldexpf(p.inv_t, -(p.xst->exp + p.yst->exp));  // accumulator -> logit (natural units)
-    float lse_r = 0.f, w_r = 0.f;
-    if (!TRANSPOSED) { lse_r = p.lse_pad[row]; w_r = p.w_pad[row]; }  // padded arrays: in range for every row of the block
+    float lse_r = 0.f, w_r = 1.f;
+    if (!TRANSPOSED) {  // padded arrays: in range for every row of the block
+      lse_r = p.lse_pad[row] - 14.0f * 0.6931471805599453f;  // folds the 2^14 fp16 range scale into the exponent
+      w_r = p.w_pad[row];                                     // w_i * 2^wst.exp, applied to the dX row at the end
+    }
+    // dX block: 128 rows x 64 columns of fp32 in TMEM; thread = (row, 16 columns).  Chunk k (tiles [8k, 8k+8)) is added
+    // into dacc once its last dX MMA has retired; a warp does that before it waits for a tile >= 3 past the chunk end
+    // (everything that chunk needs was issued before the MMA thread can block on dx_drained: no circular wait).
+    const int c0 = grp * 32 + half * 16;
+    const uint32_t dx_addr = tmem_dx + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
+    float dacc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dacc[i] = 0.f;
+    const int n_chunks = (n_iter + SB_DRAIN - 1) / SB_DRAIN;
+    int next_chunk = 0;
+    auto drain_until = [&](int t_next) {  // drain every chunk whose last tile is <= t_next - 3
+      while (next_chunk < n_chunks && min(next_chunk * SB_DRAIN + SB_DRAIN - 1, n_iter - 1) + 3 <= t_next) {
+        mbar_wait(dx_full, (uint32_t)(next_chunk & 1));
+        tc_fence_after();
+        uint32_t acc[16];
+        tmem_ld16(dx_addr, acc);
+        tmem_ld_wait16(acc);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dacc[i] += __uint_as_float(acc[i]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dx_drained);
+        ++next_chunk;
+      }
+    };
     for (int it = grp; it < n_iter; it += 2) {
-      const int stage = it % SB_STAGES;
+      drain_until(it);
+      const int stage = it % SB_STAGES, buf = it % SB_BUFS;
       const long long col0 = (t_begin + it) * 128 + half * 64;
-      mbar_wait(&s_full[grp], (uint32_t)((it >> 1) & 1));
+      mbar_wait(&s_full[buf], (uint32_t)((it / SB_BUFS) & 1));
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * 128 + half * 64);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 128 + half * 64);
       uint32_t r[64];
       tmem_ld64(taddr, r);
       tmem_ld_wait64(r);
       if (TRANSPOSED) mbar_wait(&y_full[stage], (uint32_t)((it / SB_STAGES) & 1));  // the tile's lse | w vectors (bulk-copied)
       const float4* aux4 = reinterpret_cast<const float4*>(sY + stage * SB_STAGE_BYTES + SB_Y_BYTES) + half * 16;
       const int n_valid = (int)max(0ll, min(64ll, p.n_y_valid - col0));
-      const int jd = (row >= col0 && row < col0 + 64) ? (int)(row - col0) : -1;  // the positive: query i <-> candidate i
-      uint32_t o[64];
-#pragma unroll
-      for (int j4 = 0; j4 < 16; ++j4) {
-        float lq[4] = {lse_r, lse_r, lse_r, lse_r}, wq[4] = {w_r, w_r, w_r, w_r};
-        if (TRANSPOSED) {
-          const float4 l4 = aux4[j4], w4 = aux4[32 + j4];
-          lq[0] = l4.x; lq[1] = l4.y; lq[2] = l4.z; lq[3] = l4.w;
-          wq[0] = w4.x; wq[1] = w4.y; wq[2] = w4.z; wq[3] = w4.w;
-        }
-        float a[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = 4 * j4 + e;
-          float pr = ex2_approx(fmaf(__uint_as_float(r[j]), scale, -lq[e]) * SB_LOG2E);
-          if (j == jd) pr -= 1.0f;
-          a[e] = (j < n_valid) ? pr * wq[e] : 0.f;
-        }
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const __half2 h = __floats2half2_rn(a[2 * e], a[2 * e + 1]);
-          const float2 hf = __half22float2(h);
-          const __half2 l = __floats2half2_rn(a[2 * e] - hf.x, a[2 * e + 1] - hf.y);
-          o[2 * j4 + e] = *reinterpret_cast<const uint32_t*>(&h);
-          o[32 + 2 * j4 + e] = *reinterpret_cast<const uint32_t*>(&l);
-        }
+      // the positive (query i <-> candidate i) can only sit in the tile whose columns cover this block's rows
+      const bool edge = n_valid < 64 || ((long long)xb * 128 < col0 + 64 && col0 < (long long)xb * 128 + 128);
+      uint32_t lo[32];
+      if (edge) {
+        const int jd = (row >= col0 && row < col0 + 64) ? (int)(row - col0) : -1;
+        sb_transform<TRANSPOSED, true>(r, lo, scale, lse_r, aux4, n_valid, jd);
+      } else {
+        sb_transform<TRANSPOSED, false>(r, lo, scale, lse_r, aux4, 64, -1);
       }
-      tmem_st64(taddr, o);
+      tmem_st32(taddr, r);        // hi: columns [0, 32) of this 64-column half
+      tmem_st32(taddr + 32, lo);  // lo: columns [32, 64)
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&g_ready[grp]);
+      if (lane == 0) mbar_arrive(&g_ready[buf]);
     }
-    // ---- dX block: 128 rows x 64 columns of fp32 in TMEM; thread = (row, 16 columns)
-    mbar_wait(dx_full, 0);
-    tc_fence_after();
-    const int c0 = grp * 32 + half * 16;
-    if (n_iter > 0) {
-      uint32_t acc[16];
-      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + 256u + (uint32_t)c0, acc);
-      tmem_ld_wait16(acc);
-      if (row < p.n_x_rows) {
-        const float gl = p.grad_loss ? p.grad_loss[0] : 1.0f;
-        const float fs = ldexpf(gl * p.inv_t, -(p.wst->exp + p.yst->exp));
-        float* dst = p.out + (long long)part * p.part_stride + row * p.d;
+    drain_until(n_iter + 3 + SB_DRAIN);  // the remaining chunks
+    if (row < p.n_x_rows) {
+      const float gl = p.grad_loss ? p.grad_loss[0] : 1.0f;
+      // transposed: A carried w^ = w 2^wexp per column; otherwise A carried 2^14 and the row weight is applied here
+      const float fs = TRANSPOSED ? ldexpf(gl * p.inv_t, -(p.wst->exp + p.yst->exp))
+                                  : ldexpf(gl * p.inv_t * w_r, -(p.wst->exp + 14 + p.yst->exp));
+      float* dst = p.out + (long long)part * p.part_stride + row * p.d;
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (c0 + i < p.d) dst[c0 + i] = __uint_as_float(acc[i]) * fs;
-      }
+      for (int i = 0; i < 16; ++i)
+        if (c0 + i < p.d) dst[c0 + i] = dacc[i] * fs;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (warp == SB_W_ALLOC) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 // max |w| (1 when w == NULL) -> the exact power-of-two scale that puts it in [2^13, 2^14)
@@ -250,13 +307,14 @@ sb_reduce_parts_kernel(const float* __restrict__ partial, long long elems, int p
   out[e] = a;
 }
 
+// streaming-range splits per stationary block: minimise waves x (tiles per CTA + fixed cost of ~6 tile times:
+// X load, pipeline fill/drain, dX epilogue, partial reduction)
 static int sb_parts(long long n_xb, long long n_ytiles) {
-  int parts = 1; double best = 0.0;
+  int parts = 1; double best = 1e30;
   const int sms = sm_count();
-  for (int c = 1; c <= 16 && (c == 1 || n_ytiles / c >= 8); ++c) {
-    const long long ctas = n_xb * c;
-    const double eff = (double)ctas / (double)(ceil_div(ctas, sms) * sms);
-    if (eff > best + 0.02) { best = eff; parts = c; }
+  for (int c = 1; c <= 16 && c <= n_ytiles; ++c) {
+    const double cost = (double)ceil_div(n_xb * c, sms) * ((double)ceil_div(n_ytiles, c) + 6.0);
+    if (cost < best * 0.97) { best = cost; parts = c; }
   }
   return parts;
 }
@@ -307,9 +365,9 @@ extern "C" int tfrs_inbatch_softmax_tc_bwd(const float* q, const float* c, int64
   unsigned char* qimg = w8 + pl.o_qimg; unsigned char* cimg = w8 + pl.o_cimg;
   float* lse_pad = (float*)(w8 + pl.o_lse); float* w_pad = (float*)(w8 + pl.o_w); float* partial = (float*)(w8 + pl.o_partial);
   TFRS_CUDA(cudaMemsetAsync(w8, 0, 3072, st));
-  cx_amax_kernel<<<(unsigned)ceil_div(B * 32, 256), 256, 0, st>>>(q, B, d, d, qst);
+  cx_amax_kernel<<<cx_amax_grid(B), 256, 0, st>>>(q, B, d, d, qst);
   TFRS_LAUNCH_CHECK();
-  cx_amax_kernel<<<(unsigned)ceil_div(C * 32, 256), 256, 0, st>>>(c, C, d, d, cst);
+  cx_amax_kernel<<<cx_amax_grid(C), 256, 0, st>>>(c, C, d, d, cst);
   TFRS_LAUNCH_CHECK();
   cx_exp_kernel<<<1, 1, 0, st>>>(qst);
   TFRS_LAUNCH_CHECK();

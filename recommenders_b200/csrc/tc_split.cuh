@@ -27,7 +27,19 @@ cx_amax_kernel(const float* __restrict__ src, long long rows, int D, long long l
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
-  if (lane == 0 && a > 0.f) atomicMax(&st->amax_bits, __float_as_uint(a));
+  __shared__ float red[8];
+  if (lane == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {  // one atomic per CTA (non-negative floats order like their bit patterns)
+#pragma unroll
+    for (int i = 1; i < 8; ++i) a = fmaxf(a, red[i]);
+    if (a > 0.f) atomicMax(&st->amax_bits, __float_as_uint(a));
+  }
+}
+// grid for cx_amax_kernel: one warp per row, capped at a few CTAs per SM (the kernel strides over the rows)
+static inline unsigned cx_amax_grid(long long rows) {
+  const long long want = ceil_div(rows * 32, 256), cap = (long long)sm_count() * 4;
+  return (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 static __global__ void cx_exp_kernel(CxStats* st) {
   const float amax = __uint_as_float(st->amax_bits);

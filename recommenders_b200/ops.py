@@ -323,6 +323,19 @@ class _InBatchSoftmax(torch.autograd.Function):
     return dq, dc, None, None
 
 
+def inbatch_softmax_bwd_exact(q, c, lse, sample_weight=None, inv_temperature: float = 1.0, grad_loss=None):
+  """Exact fp32 CUDA-core backward for a given saved `lse` (the anchor the tensor-core backward is tested against)."""
+  q = f32c(q, "query_embeddings"); c = f32c(c, "candidate_embeddings"); lse = f32c(lse, "lse")
+  B, d = q.shape; C = c.shape[0]
+  w = None if sample_weight is None else f32c(sample_weight, "sample_weight").view(-1)
+  g = None if grad_loss is None else f32c(grad_loss, "grad").view(1)
+  dq = torch.empty_like(q); dc = torch.empty_like(c)
+  ws = workspace(lib().tfrs_inbatch_softmax_workspace_bytes(B, C, d), q.device, "softmax")
+  check(lib().tfrs_inbatch_softmax_bwd(ptr(q), ptr(c), B, C, d, c_f(inv_temperature), ptr(w), ptr(lse), ptr(g), ptr(dq), ptr(dc),
+                                       ptr(ws), ws.numel(), stream()), "inbatch_softmax_bwd")
+  return dq, dc
+
+
 def inbatch_softmax_tc_bwd(q, c, lse, sample_weight=None, inv_temperature: float = 1.0, grad_loss=None):
   """Tensor-core backward only (any B, d <= 64): returns (dq, dc) for the given saved `lse`."""
   q = f32c(q, "query_embeddings"); c = f32c(c, "candidate_embeddings"); lse = f32c(lse, "lse")
@@ -396,7 +409,8 @@ class _Cross(torch.autograd.Function):
     out = torch.empty_like(x0)
     need_grad = any(ctx.needs_input_grad[:4])
     prod = torch.empty_like(x0) if need_grad else None
-    if B >= CROSS_TC_MIN_B and D >= CROSS_TC_MIN_D and W.shape == (D, D):
+    ctx.used_tc = B >= CROSS_TC_MIN_B and D >= CROSS_TC_MIN_D and W.shape == (D, D)
+    if ctx.used_tc:
       wimg = cross_weight_image(W)
       wsb = lib().tfrs_cross_tc_workspace_bytes(B, D)
       ws = workspace(wsb, x0.device, "cross_tc")
@@ -421,6 +435,11 @@ class _Cross(torch.autograd.Function):
     dx = torch.empty_like(x) if n1 else None
     dW = torch.empty_like(W) if n2 else None
     db = torch.empty((D,), dtype=torch.float32, device=x0.device) if (n3 and ctx.has_bias) else None
+    if ctx.used_tc:  # the two GEMMs (dx, dW) on the tensor cores
+      ws = workspace(lib().tfrs_cross_tc_bwd_workspace_bytes(B, D), x0.device, "cross_tc_bwd")
+      check(lib().tfrs_cross_tc_bwd_f32(ptr(x0), ptr(x), ptr(W), ptr(prod), ptr(g), B, D, D, c_f(ctx.diag), ptr(dx0), ptr(dx),
+                                        ptr(dW), ptr(db), ptr(ws), ws.numel(), stream()), "cross_tc_bwd")
+      return dx0, dx, dW, db, None
     wsb = lib().tfrs_cross_bwd_workspace_bytes(B, D)
     ws = workspace(wsb, x0.device, "cross")
     check(lib().tfrs_cross_bwd_f32(ptr(x0), ptr(x), ptr(W), ptr(prod), ptr(g), B, D, D, c_f(ctx.diag), ptr(dx0), ptr(dx),

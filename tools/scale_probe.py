@@ -76,31 +76,22 @@ out_s = send[:Q * k * 4].view(torch.float32).view(Q, k)
 out_i = send[idx_off:].view(torch.int64).view(Q, k)
 recv = torch.empty(W * block, dtype=torch.uint8, device=dev)
 
-out["local_scan"] = timeit(lambda: layer._local_topk(queries, k, lo, out=(out_s, out_i)))
+def note(key, val):
+  out[key] = val
+  if rank == 0:
+    print(key, val, flush=True)
+
+
+note("local_scan", timeit(lambda: layer._local_topk(queries, k, lo, out=(out_s, out_i))))
 if world > 1:
-  out["all_gather"] = timeit(lambda: dist.all_gather_into_tensor(recv, send))
+  note("all_gather", timeit(lambda: dist.all_gather_into_tensor(recv, send)))
 else:
   for r in range(W):
     recv[r * block:(r + 1) * block].copy_(send)
-out["merge"] = timeit(lambda: ops.topk_merge_packed(recv, W, Q, k, k, idx_off, block))
+note("merge", timeit(lambda: ops.topk_merge_packed(recv, W, Q, k, k, idx_off, block)))
 out["block_mb"] = block / 1e6
 if world > 1:
   out["full_step"] = timeit(lambda: layer(queries))
-  # the same step replayed from a CUDA graph (no host enqueue cost)
-  try:
-    s = torch.cuda.Stream()
-    s.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(s):
-      for _ in range(3):
-        layer(queries)
-    torch.cuda.current_stream().wait_stream(s)
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-      res = layer(queries)
-    out["full_step_graph"] = timeit(graph.replay)
-  except Exception as e:  # report, do not hide
-    out["full_step_graph"] = "failed: %r" % (e,)
 else:
   out["full_step"] = timeit(lambda: layer(queries))
 if rank == 0:

@@ -20,3 +20,11 @@ for _ in range(iters):
   loss.backward()
 torch.cuda.synchronize()
 print("loss", float(loss.detach()), "dq", float(q.grad.abs().max()), "dc", float(c.grad.abs().max()))
+
+# tensor-core backward vs the exact CUDA-core backward at this size (same lse): error relative to the gradient scale
+with torch.no_grad():
+  _, lse = ops.inbatch_softmax_tc(q, c)
+  tq, tc_ = ops.inbatch_softmax_tc_bwd(q, c, lse)
+  eq, ec = ops.inbatch_softmax_bwd_exact(q, c, lse)
+  for name, a, b in (("dq", tq, eq), ("dc", tc_, ec)):
+    print(name, "max|tc - exact| / max|exact| =", float((a - b).abs().max() / b.abs().max()))
