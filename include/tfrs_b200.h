@@ -231,6 +231,19 @@ int tfrs_cross_tc_bwd_f32(const float* x0, const float* x, const float* W, const
                           int64_t B, int D, int64_t ld, float diag_scale, float* dx0, float* dx, float* dW,
                           float* dbias, void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * DLRM DotInteraction (layers/feature_interaction/dot_interaction.py:53-104): feats [B,F,d] ->
+ * pairwise dots e_i.e_j of every sample; output = lower triangle in (i,j) row-major order without
+ * (self_interaction=0) or with the diagonal, [B, out_dim], or the full [B,F*F] matrix with the excluded part
+ * zeroed (skip_gather=1).  Every dot is the canonical sequential fmaf chain.  F <= 64.
+ * Backward: dfeats[b,i,:] = sum_j G'(i,j) feats[b,j,:] with G' the symmetrised upstream gradient.
+ * ------------------------------------------------------------------------------------------- */
+int tfrs_dot_interaction_out_dim(int F, int self_interaction, int skip_gather);
+int tfrs_dot_interaction_fwd_f32(const float* feats, int64_t B, int F, int d, int self_interaction, int skip_gather,
+                                 float* out, void* stream);
+int tfrs_dot_interaction_bwd_f32(const float* feats, const float* gout, int64_t B, int F, int d, int self_interaction,
+                                 int skip_gather, float* dfeats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -299,6 +299,52 @@ def cross(x0, x, W, bias=None, diag_scale: float = 0.0, U=None, V=None, preactiv
   return (x0_ * prod + x_).astype(np.float32)
 
 
+def multi_layer_dcn(x0, Us, Vs, biases=None):
+  """x_{l+1} = x0 * ((x_l @ U_l) @ V_l + b_l) + x_l  (layers/feature_interaction/multi_layer_dcn.py:136-153); float64."""
+  x0_ = np.asarray(x0, np.float64); xl = x0_
+  for l in range(len(Us)):
+    prod = (xl @ np.asarray(Us[l], np.float64)) @ np.asarray(Vs[l], np.float64)
+    if biases is not None:
+      prod = prod + np.asarray(biases[l], np.float64)
+    xl = x0_ * prod + xl
+  return xl.astype(np.float32)
+
+
+def dot_interaction(inputs, self_interaction: bool = False, skip_gather: bool = False):
+  """DLRM dot interaction (layers/feature_interaction/dot_interaction.py:53-104): concat -> [B, F, d] (:75-77),
+  xactions = feats @ feats^T (:83), lower triangle with / without the diagonal via boolean_mask in row-major order
+  (:85-102), or the full matrix with the upper part zeroed when skip_gather (:95-100).  Every dot product is the
+  canonical sequential float32 fmaf chain (dots())."""
+  dims = {np.asarray(t).shape[1] for t in inputs}
+  if len(dims) != 1:
+    raise ValueError("Input tensors` dimensions must be equal")
+  feats = np.stack([np.asarray(t, np.float32) for t in inputs], 1)  # [B, F, d]
+  B, F, d = feats.shape
+  x = np.zeros((B, F, F), np.float32)
+  for b in range(B):
+    x[b] = scores(feats[b], feats[b])
+  i, j = np.meshgrid(np.arange(F), np.arange(F), indexing="ij")
+  lower = (j <= i) if self_interaction else (j < i)
+  if skip_gather:
+    return np.where(lower[None], x, np.float32(0)).reshape(B, F * F)
+  return x[:, lower]  # boolean mask walks (i, j) row-major
+
+
+def dot_interaction_grads(inputs, gout, self_interaction: bool = False, skip_gather: bool = False):
+  """d out / d feats [B, F, d] in float64."""
+  feats = np.stack([np.asarray(t, np.float64) for t in inputs], 1)
+  B, F, d = feats.shape
+  i, j = np.meshgrid(np.arange(F), np.arange(F), indexing="ij")
+  lower = (j <= i) if self_interaction else (j < i)
+  G = np.zeros((B, F, F))
+  g = np.asarray(gout, np.float64)
+  if skip_gather:
+    G = np.where(lower[None], g.reshape(B, F, F), 0.0)
+  else:
+    G[:, lower] = g
+  return np.einsum("bij,bjd->bid", G + G.transpose(0, 2, 1), feats)
+
+
 def cross_grads(x0, x, W, bias, dout, diag_scale: float = 0.0):
   """Backward of the full-rank Cross without preactivation (float64)."""
   x0_ = np.asarray(x0, np.float64); x_ = np.asarray(x, np.float64); W_ = np.asarray(W, np.float64)

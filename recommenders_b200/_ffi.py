@@ -36,6 +36,9 @@ _SIGNATURES = {
     "tfrs_topk_tc_f32": (c_i, [c_p, c_l, c_p, c_p, c_l, c_i, c_i, c_l, c_p, c_p, c_p, c_sz, c_p]),
     "tfrs_topk_tc_layout": (c_i, [c_l, c_l, c_i, c_i, c_p]),
     "tfrs_debug_umma_probe": (c_i, [c_p, c_p, ctypes.c_uint32, c_i, c_p, c_p]),
+    "tfrs_dot_interaction_out_dim": (c_i, [c_i, c_i, c_i]),
+    "tfrs_dot_interaction_fwd_f32": (c_i, [c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "tfrs_dot_interaction_bwd_f32": (c_i, [c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_p]),
     "tfrs_debug_set_gather_variant": (c_i, [c_i]),
     "tfrs_debug_hbm_probe": (c_i, [c_i, c_p, c_l, c_p, c_l, c_l, c_l, c_p, c_p]),
     "tfrs_profile_enable": (c_i, [c_i]),

@@ -31,16 +31,34 @@ struct EpiCrossDx {
   }
 };
 
+// gp = g * x0 (dense [B,D]); dx0 = g * prod; optionally max |gp| (bits of a non-negative float, one atomic per CTA) for
+// the tensor-core path's power-of-two rescale.
 __global__ void __launch_bounds__(256)
 cross_bwd_elem(const float* __restrict__ x0, const float* __restrict__ prod, const float* __restrict__ g,
-               long long B, int D, long long ld, float* __restrict__ gp, float* __restrict__ dx0) {
+               long long B, int D, long long ld, float* __restrict__ gp, float* __restrict__ dx0,
+               unsigned int* __restrict__ gp_amax_bits) {
   const long long total = B * D;
+  float amax = 0.f;
   for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
     long long m = e / D; int n = (int)(e - m * D);
     long long o = m * ld + n;
     float gv = g[o];
-    gp[e] = gv * x0[o];
+    const float v = gv * x0[o];
+    gp[e] = v;
+    amax = fmaxf(amax, fabsf(v));
     if (dx0) dx0[o] = gv * prod[o];
+  }
+  if (gp_amax_bits) {
+    __shared__ float red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int i = 1; i < 8; ++i) amax = fmaxf(amax, red[i]);
+      if (amax > 0.f) atomicMax(gp_amax_bits, __float_as_uint(amax));
+    }
   }
 }
 
@@ -52,7 +70,15 @@ cross_colsum_partial(const float* __restrict__ gp, long long B, int D, long long
   long long r0 = (long long)blockIdx.y * rows_per_split;
   long long r1 = r0 + rows_per_split < B ? r0 + rows_per_split : B;
   float a = 0.f;
-  for (long long r = r0; r < r1; ++r) a += gp[r * D + n];
+  long long r = r0;
+  for (; r + 8 <= r1; r += 8) {  // 8 independent loads in flight, summed in row order (same result as the plain loop)
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = gp[(r + u) * D + n];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a += v[u];
+  }
+  for (; r < r1; ++r) a += gp[r * D + n];
   partial[(long long)blockIdx.y * D + n] = a;
 }
 
@@ -105,7 +131,7 @@ extern "C" int tfrs_cross_bwd_f32(const float* x0, const float* x, const float* 
 
   long long total = (long long)B * D;
   unsigned blocks = (unsigned)(ceil_div(total, 256) < 148 * 16 ? ceil_div(total, 256) : 148 * 16);
-  cross_bwd_elem<<<blocks, 256, 0, st>>>(x0, prod, dout, B, D, ld, gp, dx0);
+  cross_bwd_elem<<<blocks, 256, 0, st>>>(x0, prod, dout, B, D, ld, gp, dx0, nullptr);
   TFRS_LAUNCH_CHECK();
   int rc;
   if (dx) {
@@ -154,7 +180,9 @@ extern "C" int tfrs_cross_tc_bwd_f32(const float* x0, const float* x, const floa
   const size_t gemm_ws = ws_bytes - (size_t)(w - (unsigned char*)ws);
   const long long total = (long long)B * D;
   const unsigned blocks = (unsigned)(ceil_div(total, 256) < 148 * 16 ? ceil_div(total, 256) : 148 * 16);
-  cross_bwd_elem<<<blocks, 256, 0, st>>>(x0, prod, dout, B, D, ld, gp, dx0);
+  // max |gp| is produced by the element-wise pass itself (first word of the GEMM workspace = its CxStats slot)
+  TFRS_CUDA(cudaMemsetAsync(w, 0, 4096, st));
+  cross_bwd_elem<<<blocks, 256, 0, st>>>(x0, prod, dout, B, D, ld, gp, dx0, (dx || dW) ? (unsigned int*)w : nullptr);
   TFRS_LAUNCH_CHECK();
   if (dx || dW) {
     int rc = tc::cross_tc_bwd_gemms(x, W, gp, dout, B, D, ld, diag_scale, dx, dW, w, gemm_ws, st);

@@ -201,12 +201,13 @@ cx_split_image_t_kernel(const float* __restrict__ src, long long K, int M, long 
                         const CxStats* __restrict__ st, unsigned char* __restrict__ img) {
   __shared__ float tile[64][129];
   const int ks = blockIdx.x, mt = blockIdx.y;
-  const int sexp = st->exp;
+  const float sc = ldexpf(1.0f, st->exp);  // exact power of two (|exp| is far inside the float range)
+#pragma unroll 8
   for (int e = threadIdx.x; e < 64 * 128; e += 256) {
     const int kk = e >> 7, mm = e & 127;
     const long long k = (long long)ks * 64 + kk; const int m = mt * 128 + mm;
-    const float f = (k < K && m < M) ? src[k * ld + m] : 0.f;
-    tile[kk][mm] = ldexpf(f, sexp);
+    const float f = (k < K && m < M) ? __ldg(src + k * ld + m) : 0.f;
+    tile[kk][mm] = f * sc;
   }
   __syncthreads();
   unsigned char* base = img + ((long long)mt * kb_total + ks) * 32768;
@@ -279,6 +280,7 @@ static int sg_launch(int mode, const SgParams& p, cudaStream_t st) {
 }
 
 // dx (if non-NULL) and dW (if non-NULL) from gp [B,D] (dense, ld = D), x / dout / dx with row stride ld.
+// Contract with the caller: the first 4 KB of `ws` (the CxStats slots) were zeroed and slot 0's amax_bits = max |gp|.
 int cross_tc_bwd_gemms(const float* x, const float* W, const float* gp, const float* dout, long long B, int D, long long ld,
                        float diag, float* dx, float* dW, void* ws, size_t ws_bytes, cudaStream_t st) {
   CbPlan pl; cb_plan(B, D, pl);
@@ -286,9 +288,7 @@ int cross_tc_bwd_gemms(const float* x, const float* W, const float* gp, const fl
   TFRS_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "cross_tc_bwd: workspace must be 16-byte aligned");
   unsigned char* w8 = (unsigned char*)ws;
   CxStats* gst = (CxStats*)(w8 + pl.o_st); CxStats* wst = (CxStats*)(w8 + pl.o_st + 1024); CxStats* xst = (CxStats*)(w8 + pl.o_st + 2048);
-  TFRS_CUDA(cudaMemsetAsync(w8 + pl.o_st, 0, 4096, st));
-  cx_amax_kernel<<<cx_amax_grid(B), 256, 0, st>>>(gp, B, D, D, gst);
-  TFRS_LAUNCH_CHECK();
+  // gst->amax_bits was filled by the caller's element-wise pass (cross.cu: cross_bwd_elem), the other slots are zero
   cx_exp_kernel<<<1, 1, 0, st>>>(gst);
   TFRS_LAUNCH_CHECK();
   if (dx) {

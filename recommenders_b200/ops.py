@@ -453,5 +453,38 @@ def cross(x0: torch.Tensor, x: torch.Tensor, W: torch.Tensor, bias: Optional[tor
   return _Cross.apply(x0, x, W, bias, float(diag_scale))
 
 
+# ------------------------------------------------------------------------------------------------
+# DotInteraction (DLRM pairwise feature dots)
+# ------------------------------------------------------------------------------------------------
+class _DotInteraction(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, feats, self_interaction, skip_gather):
+    feats = f32c(feats, "features")
+    B, F, d = feats.shape
+    od = lib().tfrs_dot_interaction_out_dim(F, int(self_interaction), int(skip_gather))
+    out = torch.empty((B, od), dtype=torch.float32, device=feats.device)
+    check(lib().tfrs_dot_interaction_fwd_f32(ptr(feats), B, F, d, int(self_interaction), int(skip_gather), ptr(out), stream()),
+          "dot_interaction_fwd")
+    ctx.save_for_backward(feats)
+    ctx.cfg = (int(self_interaction), int(skip_gather))
+    return out
+
+  @staticmethod
+  def backward(ctx, g):
+    (feats,) = ctx.saved_tensors
+    g = f32c(g, "grad")
+    B, F, d = feats.shape
+    df = torch.empty_like(feats)
+    check(lib().tfrs_dot_interaction_bwd_f32(ptr(feats), ptr(g), B, F, d, ctx.cfg[0], ctx.cfg[1], ptr(df), stream()),
+          "dot_interaction_bwd")
+    return df, None, None
+
+
+def dot_interaction(feats: torch.Tensor, self_interaction: bool = False, skip_gather: bool = False) -> torch.Tensor:
+  """feats [B, F, d] -> pairwise dots, lower triangle (dot_interaction.py:72-104)."""
+  return _DotInteraction.apply(feats, bool(self_interaction), bool(skip_gather))
+
+
 def launch_count() -> int:
   return int(lib().tfrs_launch_count())

@@ -319,3 +319,61 @@ def test_streaming_carried_state_across_scans(tfrs):
   layer2._coalesce_rows = 1
   s2, i2 = layer2(cu(q))
   np.testing.assert_array_equal(i2.cpu().numpy(), ids[ei]); np.testing.assert_array_equal(s2.cpu().numpy(), es)
+
+
+def test_dot_interaction_layer_known_answers_and_parity():
+  """dot_interaction_test.py:27-72 through the layer, then bit-exact parity (canonical fmaf chain) and gradients vs the
+  oracle on random data, all four (self_interaction, skip_gather) modes, cfg5-like shape."""
+  import recommenders_b200 as tfrs
+  DotInteraction = tfrs.layers.feature_interaction.DotInteraction
+  f1 = np.asarray([[0.1, -4.3, 0.2, 1.1, 0.3]], np.float32)
+  f2 = np.asarray([[2.0, 3.2, -1.0, 0.0, 1.0]], np.float32)
+  f3 = np.asarray([[0.0, 1.0, -3.0, -2.2, -0.2]], np.float32)
+  for si in (True, False):
+    for sg in (True, False):
+      exp = orc.dot_interaction([f1, f2, f3], si, sg)
+      got = DotInteraction(self_interaction=si, skip_gather=sg)([cu(f1), cu(f2), cu(f3)])
+      np.testing.assert_array_equal(got.cpu().numpy(), exp)
+  with pytest.raises(ValueError, match="dimensions must be equal"):
+    DotInteraction()([cu(np.zeros((1, 3), np.float32)), cu(np.zeros((1, 3), np.float32)), cu(np.zeros((1, 2), np.float32))])
+  rng = np.random.RandomState(3)
+  for (B, F, d) in ((37, 27, 32), (5, 1, 8), (130, 8, 17)):
+    feats = [rng.normal(size=(B, d)).astype(np.float32) for _ in range(F)]
+    for si in (True, False):
+      for sg in (True, False):
+        exp = orc.dot_interaction(feats, si, sg)
+        ts = [cu(f).requires_grad_(True) for f in feats]
+        got = DotInteraction(self_interaction=si, skip_gather=sg)(ts)
+        np.testing.assert_array_equal(got.detach().cpu().numpy(), exp)
+        if exp.shape[1] == 0:
+          continue
+        g = rng.normal(size=exp.shape).astype(np.float32)
+        got.backward(cu(g))
+        edf = orc.dot_interaction_grads(feats, g, si, sg)
+        for f in range(F):
+          err = np.abs(ts[f].grad.cpu().numpy().astype(np.float64) - edf[:, f, :]).max()
+          assert err <= 1e-5 * max(1.0, np.abs(edf).max())
+
+
+def test_multi_layer_dcn_known_answers_and_parity():
+  """multi_layer_dcn_test.py:28-59, then parity with the float64 oracle on random weights (1e-5)."""
+  import recommenders_b200 as tfrs
+  MultiLayerDCN = tfrs.layers.feature_interaction.MultiLayerDCN
+  x0 = cu(np.asarray([[0.1, 0.2, 0.3]], np.float32))
+  out = MultiLayerDCN(projection_dim=3, num_layers=1, use_bias=False, kernel_initializer="ones")(x0)
+  np.testing.assert_allclose(out.detach().cpu().numpy(), [[0.28, 0.56, 0.84]], rtol=1e-6)
+  out = MultiLayerDCN(projection_dim=1, num_layers=1, use_bias=False, kernel_initializer="ones")(x0)
+  np.testing.assert_allclose(out.detach().cpu().numpy(), [[0.16, 0.32, 0.48]], rtol=1e-6)
+  out = MultiLayerDCN(projection_dim=1, kernel_initializer="ones", bias_initializer="ones")(x0)
+  np.testing.assert_allclose(out.detach().cpu().numpy(), [[0.9256, 1.8512, 2.7768]], rtol=1e-5)
+  layer = MultiLayerDCN(projection_dim=1)
+  assert MultiLayerDCN.from_config(layer.get_config()).get_config() == layer.get_config()
+  rng = np.random.RandomState(9)
+  x = rng.uniform(size=(300, 40)).astype(np.float32)
+  layer = MultiLayerDCN(projection_dim=10, num_layers=3)
+  y = layer(cu(x))
+  exp = orc.multi_layer_dcn(x, [u.detach().cpu().numpy() for u in layer.u_kernels], [v.detach().cpu().numpy() for v in layer.v_kernels],
+                            [b.detach().cpu().numpy() for b in layer.biases])
+  np.testing.assert_allclose(y.detach().cpu().numpy(), exp, rtol=1e-5, atol=1e-5 * np.abs(exp).max())
+  y.sum().backward()
+  assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in layer.parameters())

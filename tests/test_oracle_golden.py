@@ -233,3 +233,27 @@ def test_tie_rule_lowest_index_first():
   q = np.ones((1, 4), np.float32); c = np.ones((9, 4), np.float32)
   _, i = orc.topk_scan(q, c, 4)
   np.testing.assert_array_equal(i, [[0, 1, 2, 3]])
+
+
+def test_multi_layer_dcn_known_answers():
+  """multi_layer_dcn_test.py:28-59 (kernel_initializer="ones")."""
+  x0 = np.asarray([[0.1, 0.2, 0.3]], np.float32)
+  np.testing.assert_allclose(orc.multi_layer_dcn(x0, [np.ones((3, 3))], [np.ones((3, 3))]), [[0.28, 0.56, 0.84]], rtol=1e-6)
+  np.testing.assert_allclose(orc.multi_layer_dcn(x0, [np.ones((3, 1))], [np.ones((1, 3))]), [[0.16, 0.32, 0.48]], rtol=1e-6)
+  ones_u, ones_v, ones_b = [np.ones((3, 1))] * 3, [np.ones((1, 3))] * 3, [np.ones(3)] * 3
+  np.testing.assert_allclose(orc.multi_layer_dcn(x0, ones_u, ones_v, ones_b), [[0.9256, 1.8512, 2.7768]], rtol=1e-5)
+
+
+def test_dot_interaction_known_answers():
+  """dot_interaction_test.py:27-65."""
+  f1 = np.asarray([[0.1, -4.3, 0.2, 1.1, 0.3]], np.float32)
+  f2 = np.asarray([[2.0, 3.2, -1.0, 0.0, 1.0]], np.float32)
+  f3 = np.asarray([[0.0, 1.0, -3.0, -2.2, -0.2]], np.float32)
+  d = lambda a, b: np.dot(a[0], b[0])
+  f11, f12, f13, f22, f23, f33 = d(f1, f1), d(f1, f2), d(f1, f3), d(f2, f2), d(f2, f3), d(f3, f3)
+  np.testing.assert_allclose(orc.dot_interaction([f1, f2, f3], True, False), [[f11, f12, f22, f13, f23, f33]], rtol=1e-6)
+  np.testing.assert_allclose(orc.dot_interaction([f1, f2, f3], True, True), [[f11, 0, 0, f12, f22, 0, f13, f23, f33]], rtol=1e-6)
+  np.testing.assert_allclose(orc.dot_interaction([f1, f2, f3], False, False), [[f12, f13, f23]], rtol=1e-6)
+  np.testing.assert_allclose(orc.dot_interaction([f1, f2, f3], False, True), [[0, 0, 0, f12, 0, 0, f13, f23, 0]], rtol=1e-6)
+  with pytest.raises(ValueError, match="dimensions must be equal"):
+    orc.dot_interaction([np.zeros((1, 3), np.float32), np.zeros((1, 3), np.float32), np.zeros((1, 2), np.float32)])
