@@ -166,12 +166,14 @@ int tfrs_inbatch_softmax_bwd(const float* q, const float* c, int64_t B, int64_t 
 
 /* K3 forward on the tensor cores (same contract and outputs as tfrs_inbatch_softmax_fwd; d <= 128):
  * hi/lo fp16 split of q and c (|err| <= 2^-21 |q||c| on a score), tcgen05 GEMM with fp32 TMEM accumulation and
- * an online log-sum-exp epilogue -- the [B,C] logits are never written.  Returns TFRS_ERR_UNSUPPORTED
+ * an online log-sum-exp epilogue -- the [B,C] logits are never written.  `candidate_bias` (nullable, [C]) is added
+ * to every logit of its column after the temperature: with bias_j = -log(clip(p_j, 1e-6, 1)) it is the
+ * sampling-probability correction of tasks/retrieval.py:190-192 / layers/loss.py:150-158.  Returns TFRS_ERR_UNSUPPORTED
  * (workspace_bytes == 0) outside its shape range; the caller then uses tfrs_inbatch_softmax_fwd. */
 size_t tfrs_inbatch_softmax_tc_workspace_bytes(int64_t B, int64_t C, int d);
 int tfrs_inbatch_softmax_tc_fwd(const float* q, const float* c, int64_t B, int64_t C, int d,
-                                float inv_temperature, const float* sample_weight, float* loss, float* lse,
-                                void* ws, size_t ws_bytes, void* stream);
+                                float inv_temperature, const float* sample_weight, const float* candidate_bias,
+                                float* loss, float* lse, void* ws, size_t ws_bytes, void* stream);
 
 /* K3b on the tensor cores (same contract and outputs as tfrs_inbatch_softmax_bwd; d <= 64): two launches of one
  * flash-attention-backward-shaped kernel -- S = X.Y^T (tcgen05, split fp16 operands), G built from TMEM by the
@@ -180,9 +182,9 @@ int tfrs_inbatch_softmax_tc_fwd(const float* q, const float* c, int64_t B, int64
  * outside its range. */
 size_t tfrs_inbatch_softmax_tc_bwd_workspace_bytes(int64_t B, int64_t C, int d);
 int tfrs_inbatch_softmax_tc_bwd(const float* q, const float* c, int64_t B, int64_t C, int d,
-                                float inv_temperature, const float* sample_weight, const float* lse,
-                                const float* grad_loss, float* dq, float* dc, void* ws, size_t ws_bytes,
-                                void* stream);
+                                float inv_temperature, const float* sample_weight, const float* candidate_bias,
+                                const float* lse, const float* grad_loss, float* dq, float* dc, void* ws,
+                                size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K4  sparse Adagrad on the rows touched by a batch (optimizer.apply_gradients with IndexedSlices,

@@ -32,10 +32,11 @@ struct SoftmaxTcParams {
   long long n_ctiles;
   float inv_t;
   float2* partial;            // [Bp, parts, 2] (max, sum-exp) in log2 units
-  float* pos;                 // [Bp] positive logit q_i.c_i/T (natural units)
+  float* pos;                 // [Bp] positive logit q_i.c_i/T (+ bias_i) (natural units)
+  const float* cbias2;        // BIAS: per-candidate logit bias in log2 units, padded to n_ctiles*128 (zeros beyond C)
 };
 
-template <int KB>
+template <int KB, bool BIAS>
 __global__ void __launch_bounds__(SX_THREADS, 1)
 softmax_tc_kernel(const SoftmaxTcParams p) {
   extern __shared__ __align__(1024) unsigned char sx_raw[];
@@ -138,6 +139,20 @@ softmax_tc_kernel(const SoftmaxTcParams p) {
       if (lane == 0) mbar_arrive(&t_empty[ab * 2 + buf]);
       const int n_valid = (int)min(64ll, p.C - col0);  // columns beyond C are zero-padded rows of the image
       if (n_valid <= 0) continue;
+      // BIAS (sampling-probability correction, retrieval.py:190-192): logits s/T + b_j.  The scores are turned into
+      // log2-unit logits in place (one FFMA with the per-candidate bias, read through L2), the rest runs with scale 1.
+      if (BIAS) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.cbias2 + col0);
+#pragma unroll
+        for (int j4 = 0; j4 < 16; ++j4) {
+          const float4 bb = __ldg(b4 + j4);
+          r[4 * j4 + 0] = __float_as_uint(fmaf(__uint_as_float(r[4 * j4 + 0]), scale2, bb.x));
+          r[4 * j4 + 1] = __float_as_uint(fmaf(__uint_as_float(r[4 * j4 + 1]), scale2, bb.y));
+          r[4 * j4 + 2] = __float_as_uint(fmaf(__uint_as_float(r[4 * j4 + 2]), scale2, bb.z));
+          r[4 * j4 + 3] = __float_as_uint(fmaf(__uint_as_float(r[4 * j4 + 3]), scale2, bb.w));
+        }
+      }
+      const float sc = BIAS ? 1.0f : scale2;
       const long long blk0 = (long long)qb * 256 + ab * 128;
       const bool edge = n_valid < 64 || (blk0 < col0 + 64 && col0 < blk0 + 128);  // ragged tail, or the tile with the positives
       float m_new, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
@@ -151,28 +166,28 @@ softmax_tc_kernel(const SoftmaxTcParams p) {
           t[g] = max3(a0, a1, fmaxf(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7])));
         }
         const float tmax = max3(max3(t[0], t[1], t[2]), max3(t[3], t[4], t[5]), fmaxf(t[6], t[7]));
-        m_new = fmaxf(m2, tmax * scale2);
+        m_new = fmaxf(m2, tmax * sc);
 #pragma unroll
         for (int j = 0; j < 64; j += 4) {
-          acc0 += ex2_approx(fmaf(__uint_as_float(r[j]), scale2, -m_new));
-          acc1 += ex2_approx(fmaf(__uint_as_float(r[j + 1]), scale2, -m_new));
-          acc2 += ex2_approx(fmaf(__uint_as_float(r[j + 2]), scale2, -m_new));
-          acc3 += ex2_approx(fmaf(__uint_as_float(r[j + 3]), scale2, -m_new));
+          acc0 += ex2_approx(fmaf(__uint_as_float(r[j]), sc, -m_new));
+          acc1 += ex2_approx(fmaf(__uint_as_float(r[j + 1]), sc, -m_new));
+          acc2 += ex2_approx(fmaf(__uint_as_float(r[j + 2]), sc, -m_new));
+          acc3 += ex2_approx(fmaf(__uint_as_float(r[j + 3]), sc, -m_new));
         }
       } else {
         float tmax = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 64; ++j)
           if (j < n_valid) tmax = fmaxf(tmax, __uint_as_float(r[j]));
-        m_new = fmaxf(m2, tmax * scale2);
+        m_new = fmaxf(m2, tmax * sc);
         if (row >= col0 && row < col0 + 64) {   // the positive of query i is candidate i (retrieval.py:185)
           const int jd = (int)(row - col0);
 #pragma unroll
-          for (int j = 0; j < 64; ++j) if (j == jd) pos2 = __uint_as_float(r[j]) * scale2;
+          for (int j = 0; j < 64; ++j) if (j == jd) pos2 = __uint_as_float(r[j]) * sc;
         }
 #pragma unroll
         for (int j = 0; j < 64; ++j)
-          if (j < n_valid) acc0 += ex2_approx(fmaf(__uint_as_float(r[j]), scale2, -m_new));
+          if (j < n_valid) acc0 += ex2_approx(fmaf(__uint_as_float(r[j]), sc, -m_new));
       }
       l = l * ex2_approx(m2 - m_new) + ((acc0 + acc1) + (acc2 + acc3));
       m2 = m_new;
@@ -215,7 +230,7 @@ __global__ void __launch_bounds__(1024) smtc_reduce_loss(const float* __restrict
   if (threadIdx.x == 0) loss[0] = (float)red[0];
 }
 
-struct SxPlan { int kb, nqb, parts; long long Bp, n_ctiles; size_t smem, o_qst, o_cst, o_qimg, o_cimg, o_partial, o_pos, o_rowloss, total; };
+struct SxPlan { int kb, nqb, parts; long long Bp, n_ctiles; size_t smem, o_qst, o_cst, o_qimg, o_cimg, o_partial, o_pos, o_rowloss, o_bias, total; };
 
 static bool sx_plan(long long B, long long C, int d, SxPlan& pl) {
   if (B <= 0 || C < B || d <= 0 || d > 128) return false;
@@ -241,6 +256,7 @@ static bool sx_plan(long long B, long long C, int d, SxPlan& pl) {
   pl.o_partial = take((size_t)pl.Bp * parts * 2 * sizeof(float2));
   pl.o_pos = take((size_t)pl.Bp * 4);
   pl.o_rowloss = take((size_t)pl.Bp * 4);
+  pl.o_bias = take((size_t)pl.n_ctiles * 128 * 4);
   pl.total = o;
   return true;
 }
@@ -255,9 +271,16 @@ extern "C" size_t tfrs_inbatch_softmax_tc_workspace_bytes(int64_t B, int64_t C, 
   return sx_plan(B, C, d, pl) ? pl.total : 0;
 }
 
+// cbias2[i] = bias[i] * log2(e) for i < C, 0 on the padding
+__global__ void __launch_bounds__(256)
+smtc_bias_kernel(const float* __restrict__ bias, long long C, long long Cpad, float* __restrict__ cbias2) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < Cpad) cbias2[i] = i < C ? bias[i] * SX_LOG2E : 0.f;
+}
+
 extern "C" int tfrs_inbatch_softmax_tc_fwd(const float* q, const float* c, int64_t B, int64_t C, int d, float inv_temperature,
-                                           const float* sample_weight, float* loss, float* lse, void* ws, size_t ws_bytes,
-                                           void* stream) {
+                                           const float* sample_weight, const float* candidate_bias, float* loss, float* lse,
+                                           void* ws, size_t ws_bytes, void* stream) {
   TFRS_CHECK_ARG(q && c && loss && lse, "inbatch_softmax_tc_fwd: NULL pointer");
   SxPlan pl;
   if (!(inv_temperature > 0.f)) { set_error("inbatch_softmax_tc_fwd: needs a positive temperature"); return TFRS_ERR_UNSUPPORTED; }
@@ -292,12 +315,25 @@ extern "C" int tfrs_inbatch_softmax_tc_fwd(const float* q, const float* c, int64
   p.n_ctiles = pl.n_ctiles; p.inv_t = inv_temperature; p.partial = partial; p.pos = pos;
   static bool attr = false;
   if (!attr) {
-    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 + sx_stages(1)) * 32768 + 1280)));
-    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 + sx_stages(2)) * 2 * 32768 + 1280)));
+    const int s1 = (int)((2 + sx_stages(1)) * 32768 + 1280), s2 = (int)((2 + sx_stages(2)) * 2 * 32768 + 1280);
+    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
+    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
     attr = true;
   }
-  if (pl.kb == 1) softmax_tc_kernel<1><<<(unsigned)(pl.nqb * pl.parts), SX_THREADS, pl.smem, st>>>(p);
-  else softmax_tc_kernel<2><<<(unsigned)(pl.nqb * pl.parts), SX_THREADS, pl.smem, st>>>(p);
+  const unsigned grid = (unsigned)(pl.nqb * pl.parts);
+  if (candidate_bias) {
+    float* cb2 = (float*)(w + pl.o_bias);
+    smtc_bias_kernel<<<(unsigned)ceil_div(pl.n_ctiles * 128, 256), 256, 0, st>>>(candidate_bias, C, pl.n_ctiles * 128, cb2);
+    TFRS_LAUNCH_CHECK();
+    p.cbias2 = cb2;
+    if (pl.kb == 1) softmax_tc_kernel<1, true><<<grid, SX_THREADS, pl.smem, st>>>(p);
+    else softmax_tc_kernel<2, true><<<grid, SX_THREADS, pl.smem, st>>>(p);
+  } else {
+    if (pl.kb == 1) softmax_tc_kernel<1, false><<<grid, SX_THREADS, pl.smem, st>>>(p);
+    else softmax_tc_kernel<2, false><<<grid, SX_THREADS, pl.smem, st>>>(p);
+  }
   TFRS_LAUNCH_CHECK();
   smtc_combine_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, st>>>(partial, pl.parts * 2, pos, sample_weight, B, lse, rowloss);
   TFRS_LAUNCH_CHECK();

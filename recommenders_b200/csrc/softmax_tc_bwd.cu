@@ -35,6 +35,7 @@ struct SoftmaxBwdParams {
   const CxStats* xst; const CxStats* yst; const CxStats* wst;
   const float* lse_pad; const float* w_pad;   // indexed by QUERY, padded to a multiple of 128 (w already * 2^wst.exp)
   const float* grad_loss;
+  const float* cbias_pad;                     // BIAS: per-CANDIDATE logit bias (natural units), padded to a multiple of 128
   long long n_x_rows, n_y_valid, n_ytiles, part_stride;
   int n_xb, parts, d;
   float inv_t;
@@ -46,9 +47,12 @@ struct SoftmaxBwdParams {
 //   non-transposed: A = (exp(s/T - lse_i) - diag) * 2^14 -- lse_r already carries the -14 ln2, the weight of row i is
 //                   applied once to the dX block;   transposed: A = (exp(s/T - lse_j) - diag) * w^_j (per-column vectors).
 // EDGE = the tile holds the diagonal or columns beyond the valid range (rare): masks compiled in only there.
-template <bool TRANSPOSED, bool EDGE>
+// BIAS: logits carry a per-candidate bias b_c: the exponent is s/T + b_c - lse_q.  Non-transposed: candidates are the
+// columns (cb4 = this thread's 64 biases, read through L2); transposed: the candidate is the row (bias_r).
+template <bool TRANSPOSED, bool EDGE, bool BIAS>
 __device__ __forceinline__ void sb_transform(uint32_t (&r)[64], uint32_t (&lo)[32], float scale, float lse_r,
-                                             const float4* __restrict__ aux4, int n_valid, int jd) {
+                                             const float4* __restrict__ aux4, int n_valid, int jd,
+                                             const float4* __restrict__ cb4, float bias_r) {
 #pragma unroll
   for (int j4 = 0; j4 < 16; ++j4) {
     float lq[4] = {lse_r, lse_r, lse_r, lse_r}, wq[4] = {16384.f, 16384.f, 16384.f, 16384.f};
@@ -56,6 +60,10 @@ __device__ __forceinline__ void sb_transform(uint32_t (&r)[64], uint32_t (&lo)[3
       const float4 l4 = aux4[j4], w4 = aux4[32 + j4];
       lq[0] = l4.x; lq[1] = l4.y; lq[2] = l4.z; lq[3] = l4.w;
       wq[0] = w4.x; wq[1] = w4.y; wq[2] = w4.z; wq[3] = w4.w;
+      if (BIAS) { lq[0] -= bias_r; lq[1] -= bias_r; lq[2] -= bias_r; lq[3] -= bias_r; }
+    } else if (BIAS) {
+      const float4 bb = __ldg(cb4 + j4);
+      lq[0] -= bb.x; lq[1] -= bb.y; lq[2] -= bb.z; lq[3] -= bb.w;
     }
     float a[4];
 #pragma unroll
@@ -81,7 +89,7 @@ __device__ __forceinline__ void sb_transform(uint32_t (&r)[64], uint32_t (&lo)[3
   }
 }
 
-template <bool TRANSPOSED>
+template <bool TRANSPOSED, bool BIAS>
 __global__ void __launch_bounds__(SB_THREADS, 1)
 softmax_tc_bwd_kernel(const SoftmaxBwdParams p) {
   extern __shared__ __align__(1024) unsigned char sb_raw[];
@@ -196,6 +204,7 @@ softmax_tc_bwd_kernel(const SoftmaxBwdParams p) {
     const long long row = (long long)xb * 128 + r_local;
     const float scale = ldexpf(p.inv_t, -(p.xst->exp + p.yst->exp));  // accumulator -> logit (natural units)
     float lse_r = 0.f, w_r = 1.f;
+    const float bias_r = (BIAS && TRANSPOSED) ? p.cbias_pad[row] : 0.f;  // padded: in range for every row of the block
     if (!TRANSPOSED) {  // padded arrays: in range for every row of the block
       lse_r = p.lse_pad[row] - 14.0f * 0.6931471805599453f;  // folds the 2^14 fp16 range scale into the exponent
       w_r = p.w_pad[row];                                     // w_i * 2^wst.exp, applied to the dX row at the end
@@ -241,11 +250,12 @@ softmax_tc_bwd_kernel(const SoftmaxBwdParams p) {
       // the positive (query i <-> candidate i) can only sit in the tile whose columns cover this block's rows
       const bool edge = n_valid < 64 || ((long long)xb * 128 < col0 + 64 && col0 < (long long)xb * 128 + 128);
       uint32_t lo[32];
+      const float4* cb4 = (BIAS && !TRANSPOSED) ? reinterpret_cast<const float4*>(p.cbias_pad + col0) : nullptr;
       if (edge) {
         const int jd = (row >= col0 && row < col0 + 64) ? (int)(row - col0) : -1;
-        sb_transform<TRANSPOSED, true>(r, lo, scale, lse_r, aux4, n_valid, jd);
+        sb_transform<TRANSPOSED, true, BIAS>(r, lo, scale, lse_r, aux4, n_valid, jd, cb4, bias_r);
       } else {
-        sb_transform<TRANSPOSED, false>(r, lo, scale, lse_r, aux4, 64, -1);
+        sb_transform<TRANSPOSED, false, BIAS>(r, lo, scale, lse_r, aux4, 64, -1, cb4, bias_r);
       }
       tmem_st32(taddr, r);        // hi: columns [0, 32) of this 64-column half
       tmem_st32(taddr + 32, lo);  // lo: columns [32, 64)
@@ -321,7 +331,7 @@ static int sb_parts(long long n_xb, long long n_ytiles) {
 
 struct SbPlan {
   long long q_tiles, c_tiles; int parts_q, parts_c;
-  size_t o_qst, o_cst, o_wst, o_qimg, o_cimg, o_lse, o_w, o_partial, total;
+  size_t o_qst, o_cst, o_wst, o_qimg, o_cimg, o_lse, o_w, o_bias, o_partial, total;
 };
 static bool sb_plan(long long B, long long C, int d, SbPlan& pl) {
   if (B <= 0 || C < B || d <= 0 || d > 64) return false;
@@ -335,6 +345,7 @@ static bool sb_plan(long long B, long long C, int d, SbPlan& pl) {
   pl.o_cimg = take((size_t)pl.c_tiles * 32768);
   pl.o_lse = take((size_t)pl.q_tiles * 128 * 4);
   pl.o_w = take((size_t)pl.q_tiles * 128 * 4);
+  pl.o_bias = take((size_t)pl.c_tiles * 128 * 4);
   size_t pq = pl.parts_q > 1 ? (size_t)pl.parts_q * B * d * 4 : 0, pc = pl.parts_c > 1 ? (size_t)pl.parts_c * C * d * 4 : 0;
   pl.o_partial = take(pq > pc ? pq : pc);
   pl.total = o;
@@ -351,9 +362,15 @@ extern "C" size_t tfrs_inbatch_softmax_tc_bwd_workspace_bytes(int64_t B, int64_t
   return sb_plan(B, C, d, pl) ? pl.total : 0;
 }
 
+// pad[i] = src[i] for i < n, 0 on the padding
+__global__ void __launch_bounds__(256) sb_pad_kernel(const float* __restrict__ src, long long n, long long npad, float* __restrict__ pad) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < npad) pad[i] = i < n ? src[i] : 0.f;
+}
+
 extern "C" int tfrs_inbatch_softmax_tc_bwd(const float* q, const float* c, int64_t B, int64_t C, int d, float inv_temperature,
-                                           const float* sample_weight, const float* lse, const float* grad_loss, float* dq,
-                                           float* dc, void* ws, size_t ws_bytes, void* stream) {
+                                           const float* sample_weight, const float* candidate_bias, const float* lse,
+                                           const float* grad_loss, float* dq, float* dc, void* ws, size_t ws_bytes, void* stream) {
   TFRS_CHECK_ARG(q && c && lse && dq && dc, "inbatch_softmax_tc_bwd: NULL pointer");
   SbPlan pl;
   if (!sb_plan(B, C, d, pl)) { set_error("inbatch_softmax_tc_bwd: shape outside the tensor-core path (need B <= C, d <= 64)"); return TFRS_ERR_UNSUPPORTED; }
@@ -384,8 +401,10 @@ extern "C" int tfrs_inbatch_softmax_tc_bwd(const float* q, const float* c, int64
   const size_t smem = 32768 + (size_t)SB_STAGES * SB_STAGE_BYTES + 1024 + 256;
   static bool attr = false;
   if (!attr) {
-    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   SoftmaxBwdParams p{};
@@ -393,7 +412,15 @@ extern "C" int tfrs_inbatch_softmax_tc_bwd(const float* q, const float* c, int64
   // ---- dq: X = q, Y = c
   p.ximg = qimg; p.yimg = cimg; p.n_x_rows = B; p.n_y_valid = C; p.n_ytiles = pl.c_tiles; p.n_xb = (int)pl.q_tiles; p.parts = pl.parts_q;
   p.part_stride = B * (long long)d; p.out = pl.parts_q > 1 ? partial : dq;
-  softmax_tc_bwd_kernel<false><<<(unsigned)(pl.q_tiles * pl.parts_q), SB_THREADS, smem, st>>>(p);
+  if (candidate_bias) {
+    float* cbp = (float*)(w8 + pl.o_bias);
+    sb_pad_kernel<<<(unsigned)ceil_div(pl.c_tiles * 128, 256), 256, 0, st>>>(candidate_bias, C, pl.c_tiles * 128, cbp);
+    TFRS_LAUNCH_CHECK();
+    p.cbias_pad = cbp;
+    softmax_tc_bwd_kernel<false, true><<<(unsigned)(pl.q_tiles * pl.parts_q), SB_THREADS, smem, st>>>(p);
+  } else {
+    softmax_tc_bwd_kernel<false, false><<<(unsigned)(pl.q_tiles * pl.parts_q), SB_THREADS, smem, st>>>(p);
+  }
   TFRS_LAUNCH_CHECK();
   if (pl.parts_q > 1) {
     sb_reduce_parts_kernel<<<(unsigned)ceil_div(B * d, 256), 256, 0, st>>>(partial, B * (long long)d, pl.parts_q, dq);
@@ -402,7 +429,8 @@ extern "C" int tfrs_inbatch_softmax_tc_bwd(const float* q, const float* c, int64
   // ---- dc: X = c, Y = q (only the B query rows exist; candidates beyond B are pure negatives)
   p.ximg = cimg; p.yimg = qimg; p.xst = cst; p.yst = qst; p.n_x_rows = C; p.n_y_valid = B; p.n_ytiles = pl.q_tiles; p.n_xb = (int)pl.c_tiles;
   p.parts = pl.parts_c; p.part_stride = C * (long long)d; p.out = pl.parts_c > 1 ? partial : dc;
-  softmax_tc_bwd_kernel<true><<<(unsigned)(pl.c_tiles * pl.parts_c), SB_THREADS, smem, st>>>(p);
+  if (candidate_bias) softmax_tc_bwd_kernel<true, true><<<(unsigned)(pl.c_tiles * pl.parts_c), SB_THREADS, smem, st>>>(p);
+  else softmax_tc_bwd_kernel<true, false><<<(unsigned)(pl.c_tiles * pl.parts_c), SB_THREADS, smem, st>>>(p);
   TFRS_LAUNCH_CHECK();
   if (pl.parts_c > 1) {
     sb_reduce_parts_kernel<<<(unsigned)ceil_div(C * d, 256), 256, 0, st>>>(partial, C * (long long)d, pl.parts_c, dc);

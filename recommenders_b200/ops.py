@@ -264,15 +264,17 @@ SOFTMAX_TC_MIN_B = 512  # below this the exact CUDA-core forward is launch-laten
 
 
 def inbatch_softmax_tc(q: torch.Tensor, c: torch.Tensor, sample_weight: Optional[torch.Tensor] = None,
-                       inv_temperature: float = 1.0):
-  """Tensor-core forward only (any B): returns (loss scalar, lse [B]).  Raises NotImplementedError when d > 128."""
+                       inv_temperature: float = 1.0, candidate_bias: Optional[torch.Tensor] = None):
+  """Tensor-core forward only (any B): returns (loss scalar, lse [B]).  Raises NotImplementedError when d > 128.
+  `candidate_bias` [C] is added to every logit of its column (after the temperature)."""
   q = f32c(q, "query_embeddings"); c = f32c(c, "candidate_embeddings")
   B, d = q.shape; C = c.shape[0]
   w = None if sample_weight is None else f32c(sample_weight, "sample_weight").view(-1)
   loss = torch.empty((1,), dtype=torch.float32, device=q.device)
   lse = torch.empty((B,), dtype=torch.float32, device=q.device)
+  cb = None if candidate_bias is None else f32c(candidate_bias, "candidate_bias").view(-1)
   ws = workspace(max(lib().tfrs_inbatch_softmax_tc_workspace_bytes(B, C, d), 256), q.device, "softmax_tc")
-  check(lib().tfrs_inbatch_softmax_tc_fwd(ptr(q), ptr(c), B, C, d, c_f(inv_temperature), ptr(w), ptr(loss), ptr(lse),
+  check(lib().tfrs_inbatch_softmax_tc_fwd(ptr(q), ptr(c), B, C, d, c_f(inv_temperature), ptr(w), ptr(cb), ptr(loss), ptr(lse),
                                           ptr(ws), ws.numel(), stream()), "inbatch_softmax_tc_fwd")
   return loss.view(()), lse
 
@@ -280,31 +282,37 @@ def inbatch_softmax_tc(q: torch.Tensor, c: torch.Tensor, sample_weight: Optional
 class _InBatchSoftmax(torch.autograd.Function):
 
   @staticmethod
-  def forward(ctx, q, c, sample_weight, inv_temperature):
+  def forward(ctx, q, c, sample_weight, inv_temperature, candidate_bias=None):
     q = f32c(q, "query_embeddings"); c = f32c(c, "candidate_embeddings")
     B, d = q.shape; C = c.shape[0]
     w = None if sample_weight is None else f32c(sample_weight, "sample_weight").view(-1)
+    cb = None if candidate_bias is None else f32c(candidate_bias, "candidate_bias").view(-1)
+    if cb is not None and not inbatch_softmax_bias_supported(B, C, d):
+      raise NotImplementedError("inbatch_softmax_loss: candidate_bias needs the tensor-core path "
+                                f"(B >= {SOFTMAX_TC_MIN_B}, d <= 64); got B={B}, d={d}")
     loss = torch.empty((1,), dtype=torch.float32, device=q.device)
     lse = torch.empty((B,), dtype=torch.float32, device=q.device)
     tcb = lib().tfrs_inbatch_softmax_tc_workspace_bytes(B, C, d) if B >= SOFTMAX_TC_MIN_B else 0
     if tcb:  # tensor-core forward (hi/lo fp16 split, fp32 accumulate, online log-sum-exp epilogue)
       ws = workspace(tcb, q.device, "softmax_tc")
-      check(lib().tfrs_inbatch_softmax_tc_fwd(ptr(q), ptr(c), B, C, d, c_f(inv_temperature), ptr(w), ptr(loss), ptr(lse),
+      check(lib().tfrs_inbatch_softmax_tc_fwd(ptr(q), ptr(c), B, C, d, c_f(inv_temperature), ptr(w), ptr(cb), ptr(loss), ptr(lse),
                                               ptr(ws), ws.numel(), stream()), "inbatch_softmax_tc_fwd")
     else:
       wsb = lib().tfrs_inbatch_softmax_workspace_bytes(B, C, d)
       ws = workspace(wsb, q.device, "softmax")
       check(lib().tfrs_inbatch_softmax_fwd(ptr(q), ptr(c), B, C, d, c_f(inv_temperature), ptr(w), ptr(loss), ptr(lse),
                                            ptr(ws), ws.numel(), stream()), "inbatch_softmax_fwd")
-    ctx.save_for_backward(q, c, lse, w if w is not None else torch.empty(0, device=q.device))
+    ctx.save_for_backward(q, c, lse, w if w is not None else torch.empty(0, device=q.device),
+                          cb if cb is not None else torch.empty(0, device=q.device))
     ctx.has_w = w is not None
+    ctx.has_cb = cb is not None
     ctx.inv_t = inv_temperature
     ctx.used_tc = bool(tcb)
     return loss.view(())
 
   @staticmethod
   def backward(ctx, g):
-    q, c, lse, w = ctx.saved_tensors
+    q, c, lse, w, cb = ctx.saved_tensors
     B, d = q.shape; C = c.shape[0]
     g = f32c(g, "grad").view(1)
     dq = torch.empty_like(q); dc = torch.empty_like(c)
@@ -312,15 +320,17 @@ class _InBatchSoftmax(torch.autograd.Function):
     if tcb:  # tensor-core backward: same split products as the forward pass that produced `lse`
       ws = workspace(tcb, q.device, "softmax_tc_bwd")
       check(lib().tfrs_inbatch_softmax_tc_bwd(ptr(q), ptr(c), B, C, d, c_f(ctx.inv_t), ptr(w) if ctx.has_w else None,
-                                              ptr(lse), ptr(g), ptr(dq), ptr(dc), ptr(ws), ws.numel(), stream()),
-            "inbatch_softmax_tc_bwd")
-      return dq, dc, None, None
+                                              ptr(cb) if ctx.has_cb else None, ptr(lse), ptr(g), ptr(dq), ptr(dc), ptr(ws),
+                                              ws.numel(), stream()), "inbatch_softmax_tc_bwd")
+      return dq, dc, None, None, None
+    if ctx.has_cb:
+      raise NotImplementedError("inbatch_softmax_loss backward with candidate_bias needs the tensor-core path")
     wsb = lib().tfrs_inbatch_softmax_workspace_bytes(B, C, d)
     ws = workspace(wsb, q.device, "softmax")
     check(lib().tfrs_inbatch_softmax_bwd(ptr(q), ptr(c), B, C, d, c_f(ctx.inv_t), ptr(w) if ctx.has_w else None,
                                          ptr(lse), ptr(g), ptr(dq), ptr(dc), ptr(ws), ws.numel(), stream()),
           "inbatch_softmax_bwd")
-    return dq, dc, None, None
+    return dq, dc, None, None, None
 
 
 def inbatch_softmax_bwd_exact(q, c, lse, sample_weight=None, inv_temperature: float = 1.0, grad_loss=None):
@@ -336,7 +346,7 @@ def inbatch_softmax_bwd_exact(q, c, lse, sample_weight=None, inv_temperature: fl
   return dq, dc
 
 
-def inbatch_softmax_tc_bwd(q, c, lse, sample_weight=None, inv_temperature: float = 1.0, grad_loss=None):
+def inbatch_softmax_tc_bwd(q, c, lse, sample_weight=None, inv_temperature: float = 1.0, grad_loss=None, candidate_bias=None):
   """Tensor-core backward only (any B, d <= 64): returns (dq, dc) for the given saved `lse`."""
   q = f32c(q, "query_embeddings"); c = f32c(c, "candidate_embeddings"); lse = f32c(lse, "lse")
   B, d = q.shape; C = c.shape[0]
@@ -344,16 +354,24 @@ def inbatch_softmax_tc_bwd(q, c, lse, sample_weight=None, inv_temperature: float
   g = None if grad_loss is None else f32c(grad_loss, "grad").view(1)
   dq = torch.empty_like(q); dc = torch.empty_like(c)
   ws = workspace(max(lib().tfrs_inbatch_softmax_tc_bwd_workspace_bytes(B, C, d), 256), q.device, "softmax_tc_bwd")
-  check(lib().tfrs_inbatch_softmax_tc_bwd(ptr(q), ptr(c), B, C, d, c_f(inv_temperature), ptr(w), ptr(lse), ptr(g), ptr(dq),
-                                          ptr(dc), ptr(ws), ws.numel(), stream()), "inbatch_softmax_tc_bwd")
+  cb = None if candidate_bias is None else f32c(candidate_bias, "candidate_bias").view(-1)
+  check(lib().tfrs_inbatch_softmax_tc_bwd(ptr(q), ptr(c), B, C, d, c_f(inv_temperature), ptr(w), ptr(cb), ptr(lse), ptr(g),
+                                          ptr(dq), ptr(dc), ptr(ws), ws.numel(), stream()), "inbatch_softmax_tc_bwd")
   return dq, dc
 
 
+def inbatch_softmax_bias_supported(B: int, C: int, d: int) -> bool:
+  """True when the loss with a per-candidate logit bias can run fused (tensor-core forward AND backward)."""
+  return (B >= SOFTMAX_TC_MIN_B and lib().tfrs_inbatch_softmax_tc_workspace_bytes(B, C, d) > 0 and
+          lib().tfrs_inbatch_softmax_tc_bwd_workspace_bytes(B, C, d) > 0)
+
+
 def inbatch_softmax_loss(q: torch.Tensor, c: torch.Tensor, sample_weight: Optional[torch.Tensor] = None,
-                         temperature: Optional[float] = None) -> torch.Tensor:
-  """sum_i w_i * (logsumexp_j(q_i.c_j / T) - q_i.c_i / T)  -- tasks/retrieval.py:178-210 default path."""
+                         temperature: Optional[float] = None, candidate_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+  """sum_i w_i * (logsumexp_j(q_i.c_j / T + b_j) - q_i.c_i / T - b_i)  -- tasks/retrieval.py:178-210 default path;
+  b = candidate_bias (e.g. -log(clip(p, 1e-6, 1)): the sampling-probability correction, :190-192), no gradient."""
   inv_t = 1.0 if temperature is None else 1.0 / float(temperature)
-  return _InBatchSoftmax.apply(q, c, sample_weight, inv_t)
+  return _InBatchSoftmax.apply(q, c, sample_weight, inv_t, candidate_bias)
 
 
 # ------------------------------------------------------------------------------------------------

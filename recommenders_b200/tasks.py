@@ -75,9 +75,16 @@ class Retrieval(torch.nn.Module, Task):
            candidate_ids=None, compute_metrics: bool = True, compute_batch_metrics: bool = True,
            score_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     three_d = query_embeddings.dim() == 3
-    need_scores = (three_d or self._loss is not None or candidate_sampling_probability is not None or
-                   self._remove_accidental_hits or score_mask is not None or self._num_hard_negatives is not None or
-                   (compute_batch_metrics and len(self._batch_metrics) > 0))
+    other_transforms = (three_d or self._loss is not None or self._remove_accidental_hits or score_mask is not None or
+                        self._num_hard_negatives is not None)
+    # temperature + sampling-probability correction only (the production "sampled softmax with logQ correction"):
+    # the correction is a per-candidate logit bias, folded into the fused tensor-core loss when the shape allows it
+    fused_bias = (candidate_sampling_probability is not None and not other_transforms and
+                  not (compute_batch_metrics and len(self._batch_metrics) > 0) and
+                  ops.inbatch_softmax_bias_supported(query_embeddings.shape[0], candidate_embeddings.shape[0],
+                                                     query_embeddings.shape[-1]))
+    need_scores = not fused_bias and (other_transforms or candidate_sampling_probability is not None or
+                                      (compute_batch_metrics and len(self._batch_metrics) > 0))
     if self._remove_accidental_hits and candidate_ids is None:
       raise ValueError("When accidental hit removal is enabled, candidate ids must be supplied.")
 
@@ -102,9 +109,13 @@ class Retrieval(torch.nn.Module, Task):
       if self._num_hard_negatives is not None:
         scores, labels = loss_layers.HardNegativeMining(self._num_hard_negatives)(scores, labels)
 
-    plain = not (three_d or self._loss is not None or candidate_sampling_probability is not None or
-                 self._remove_accidental_hits or score_mask is not None or self._num_hard_negatives is not None)
-    if plain:
+    plain = not (other_transforms or candidate_sampling_probability is not None)
+    if fused_bias:
+      # logits - log(clip(p, 1e-6, 1))  (layers/loss.py:150-158) as a bias vector
+      p_c = torch.as_tensor(candidate_sampling_probability, dtype=torch.float32, device=candidate_embeddings.device).reshape(-1)
+      bias = -torch.log(torch.clamp(p_c, 1e-6, 1.0))
+      loss = ops.inbatch_softmax_loss(query_embeddings, candidate_embeddings, sample_weight, self._temperature, bias)
+    elif plain:
       loss = ops.inbatch_softmax_loss(query_embeddings, candidate_embeddings, sample_weight, self._temperature)
     elif self._loss is not None:
       loss = self._loss(labels, scores, sample_weight) if sample_weight is not None else self._loss(labels, scores)

@@ -276,3 +276,33 @@ def test_inbatch_softmax_tensor_core_backward_full_size(ops):
   eq, ec = ops.inbatch_softmax_bwd_exact(q, c, lse, w, 2.0)
   for a, b in ((tq, eq), (tc, ec)):
     assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max())
+
+
+@pytest.mark.parametrize("B,C,d,temp,weighted", [(600, 600, 64, 0.2, True), (1024, 3000, 32, None, False), (2500, 2500, 48, 0.5, True)])
+def test_inbatch_softmax_with_sampling_probability_correction(ops, B, C, d, temp, weighted):
+  """Fused tensor-core loss with the per-candidate bias -log(clip(p, 1e-6, 1)) (retrieval.py:190-192): loss vs the
+  oracle's materialised path, gradients vs float64, and the Retrieval task routes the option to the fused kernels."""
+  import recommenders_b200 as tfrs
+  rng = np.random.RandomState(B + C + d + 7)
+  q = rng.normal(size=(B, d)).astype(np.float32) * 0.4; c = rng.normal(size=(C, d)).astype(np.float32) * 0.4
+  w = rng.uniform(size=(B,)).astype(np.float32) if weighted else None
+  prob = rng.uniform(1e-7, 1.0, size=(C,)).astype(np.float32)   # includes values below the 1e-6 clip
+  exp = orc.retrieval_loss(q, c, sample_weight=w, temperature=temp, candidate_sampling_probability=prob)
+  t = 1.0 if temp is None else temp
+  bias = -np.log(np.clip(prob.astype(np.float64), 1e-6, 1.0))
+  s = q.astype(np.float64) @ c.astype(np.float64).T / t + bias[None, :]
+  p = np.exp(s - s.max(1, keepdims=True)); p /= p.sum(1, keepdims=True)
+  g = (p - np.eye(B, C)) * (np.ones(B) if w is None else w.astype(np.float64))[:, None] / t
+  edq, edc = g @ c.astype(np.float64), g.T @ q.astype(np.float64)
+  assert ops.inbatch_softmax_bias_supported(B, C, d)
+  tq = cu(q).requires_grad_(True); tc = cu(c).requires_grad_(True)
+  task = tfrs.tasks.Retrieval(temperature=temp)
+  loss = task(tq, tc, sample_weight=None if w is None else cu(w), candidate_sampling_probability=cu(prob), compute_metrics=False)
+  loss.backward()
+  assert abs(float(loss) - exp) <= 1e-5 * abs(exp)
+  for got, ref in ((tq.grad, edq), (tc.grad, edc)):
+    err = np.abs(got.cpu().numpy().astype(np.float64) - ref).max()
+    assert err <= 1e-5 * max(1.0, np.abs(ref).max())
+  # the fused op itself, and the materialised path of the task on the same data (forced by a tiny batch-metric-free slice)
+  direct = ops.inbatch_softmax_loss(cu(q), cu(c), None if w is None else cu(w), temp, cu(bias.astype(np.float32)))
+  assert abs(float(direct) - exp) <= 1e-5 * abs(exp)
