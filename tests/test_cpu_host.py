@@ -147,3 +147,30 @@ def test_sharded_protocol_gloo(tmp_path, world):
   outs = [p.communicate(timeout=240)[0] for p in procs]
   for r, (p, o) in enumerate(zip(procs, outs)):
     assert p.returncode == 0 and f"RANK_OK {r}" in o, o
+
+
+def test_host_side_planning_functions():
+  """The *_workspace_bytes / out_dim entry points are pure host code: they run without a GPU and define which shapes
+  take the tensor-core paths (0 = outside the range, the callers then use the exact kernels)."""
+  from recommenders_b200 import _ffi
+  lib = _ffi.lib()
+  # DotInteraction output width (dot_interaction.py:88-100)
+  for F in (1, 2, 3, 27):
+    assert lib.tfrs_dot_interaction_out_dim(F, 0, 0) == F * (F - 1) // 2
+    assert lib.tfrs_dot_interaction_out_dim(F, 1, 0) == F * (F + 1) // 2
+    assert lib.tfrs_dot_interaction_out_dim(F, 0, 1) == F * F and lib.tfrs_dot_interaction_out_dim(F, 1, 1) == F * F
+  # in-batch softmax on tensor cores: forward d <= 128, backward d <= 64, C >= B
+  assert lib.tfrs_inbatch_softmax_tc_workspace_bytes(16384, 16384, 64) > 0
+  assert lib.tfrs_inbatch_softmax_tc_workspace_bytes(16384, 16384, 128) > 0
+  assert lib.tfrs_inbatch_softmax_tc_workspace_bytes(16384, 16384, 129) == 0
+  assert lib.tfrs_inbatch_softmax_tc_workspace_bytes(1024, 512, 64) == 0
+  assert lib.tfrs_inbatch_softmax_tc_bwd_workspace_bytes(16384, 16384, 64) > 0
+  assert lib.tfrs_inbatch_softmax_tc_bwd_workspace_bytes(16384, 16384, 65) == 0
+  # top-K screening path: k <= 256, d <= 128, corpus large enough
+  assert lib.tfrs_topk_tc_workspace_bytes(4096, 1_000_000, 64, 100) > 0
+  assert lib.tfrs_topk_tc_workspace_bytes(4096, 1_000_000, 64, 257) == 0
+  assert lib.tfrs_topk_tc_workspace_bytes(4096, 1_000_000, 129, 100) == 0
+  assert lib.tfrs_topk_tc_workspace_bytes(4096, 1000, 64, 100) == 0
+  # workspaces grow with the problem
+  assert lib.tfrs_cross_tc_bwd_workspace_bytes(65536, 845) > lib.tfrs_cross_tc_bwd_workspace_bytes(4096, 845) > 0
+  assert lib.tfrs_index_bytes(1_000_000, 64) >= 1_000_000 * 64 * 2
