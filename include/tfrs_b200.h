@@ -106,6 +106,11 @@ int tfrs_debug_umma_probe(const void* a_img, const void* b_img, uint32_t idesc, 
  * any product path. */
 int tfrs_debug_hbm_probe(int mode, const void* src, int64_t src_rows, void* dst, int64_t n, int64_t n_rows_out,
                          int64_t ld_floats, float* sink, void* stream);
+/* Tensor-pipe / TMEM timing probe (tools/tc_rate_probe.py): clock64 cycle counts of R rounds of
+ * mode 0 tcgen05.ld x64 (16 warps), 1 the same with .pack::16b, 2 twelve SS MMAs M128 N128 K16, 3 twenty-four TS MMAs
+ * M128 N64 K16 (A from TMEM, MN-major B), 4 both interleaved (the softmax backward's pattern), 5 tcgen05.st;
+ * out_cycles[n_ctas].  Not on any product path. */
+int tfrs_debug_tc_rate_probe(int mode, int rounds, int n_ctas, long long* out_cycles, uint32_t* sink, void* stream);
 /* A/B switch between the two gather kernels (0 lane-per-item, 1 warp-chunk = default); identical results. */
 int tfrs_debug_set_gather_variant(int variant);
 

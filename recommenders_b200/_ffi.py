@@ -39,6 +39,7 @@ _SIGNATURES = {
     "tfrs_dot_interaction_out_dim": (c_i, [c_i, c_i, c_i]),
     "tfrs_dot_interaction_fwd_f32": (c_i, [c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_p]),
     "tfrs_dot_interaction_bwd_f32": (c_i, [c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "tfrs_debug_tc_rate_probe": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p]),
     "tfrs_debug_set_gather_variant": (c_i, [c_i]),
     "tfrs_debug_hbm_probe": (c_i, [c_i, c_p, c_l, c_p, c_l, c_l, c_l, c_p, c_p]),
     "tfrs_profile_enable": (c_i, [c_i]),
