@@ -287,6 +287,10 @@ class _InBatchSoftmax(torch.autograd.Function):
     B, d = q.shape; C = c.shape[0]
     w = None if sample_weight is None else f32c(sample_weight, "sample_weight").view(-1)
     cb = None if candidate_bias is None else f32c(candidate_bias, "candidate_bias").view(-1)
+    if cb is not None and cb.numel() != C:
+      raise ValueError(f"candidate_bias must have one entry per candidate (got {cb.numel()}, expected {C})")
+    if w is not None and w.numel() != B:
+      raise ValueError(f"sample_weight must have one entry per query (got {w.numel()}, expected {B})")
     if cb is not None and not inbatch_softmax_bias_supported(B, C, d):
       raise NotImplementedError("inbatch_softmax_loss: candidate_bias needs the tensor-core path "
                                 f"(B >= {SOFTMAX_TC_MIN_B}, d <= 64); got B={B}, d={d}")
