@@ -174,3 +174,98 @@ def test_host_side_planning_functions():
   # workspaces grow with the problem
   assert lib.tfrs_cross_tc_bwd_workspace_bytes(65536, 845) > lib.tfrs_cross_tc_bwd_workspace_bytes(4096, 845) > 0
   assert lib.tfrs_index_bytes(1_000_000, 64) >= 1_000_000 * 64 * 2
+
+
+def _tree_merge_emulation(scores, idx, k_out):
+  """Line-by-line Python restatement of merge_sorted_kernel (csrc/topk.cu): prune every list at
+  tau = min_l list_l[rr-1], then merge pairwise in a tree, rank = own position + binary search in the partner list,
+  ties between equal (score, index) pairs go to the lower list.  Used to check the ALGORITHM on the CPU; the CUDA
+  kernel itself is checked against the sort-based merge and numpy in tests/test_gpu_tc.py."""
+  n_lists, k_in = scores.shape
+  ko = min(k_out, n_lists * k_in)
+  rr = min(k_in, -(-ko // n_lists))
+  tau = min(scores[l][rr - 1] for l in range(n_lists))
+  lists = []
+  for l in range(n_lists):
+    n = rr
+    while n < k_in and scores[l][n] >= tau:
+      n += 1
+    lists.append([(float(scores[l][r]), int(idx[l][r])) for r in range(n)])
+  if n_lists == 1:
+    return lists[0][:ko]
+
+  def precedes(x, e, x_list_is_lower):
+    return x[0] > e[0] or (x[0] == e[0] and (x[1] <= e[1] if x_list_is_lower else x[1] < e[1]))
+
+  c_prev = k_in
+  while True:
+    last = len(lists) <= 2
+    c_new = min(ko, 2 * c_prev)
+    nxt = [[None] * min(c_new, len(lists[2 * i]) + (len(lists[2 * i + 1]) if 2 * i + 1 < len(lists) else 0))
+           for i in range((len(lists) + 1) // 2)]
+    for l, lst in enumerate(lists):
+      m = l ^ 1
+      for r, e in enumerate(lst):
+        rank = r
+        if m < len(lists):
+          lo, hi = 0, len(lists[m])
+          while lo < hi:
+            mid = (lo + hi) >> 1
+            if precedes(lists[m][mid], e, m < l):
+              lo = mid + 1
+            else:
+              hi = mid
+          rank += lo
+        if rank < c_new:
+          assert nxt[l >> 1][rank] is None, "two elements claimed the same merged position"
+          nxt[l >> 1][rank] = e
+    assert all(x is not None for lst in nxt for x in lst), "a merged position was left empty"
+    lists = nxt
+    if last:
+      return lists[0][:ko]
+    c_prev = c_new
+
+
+def test_sorted_tree_merge_algorithm_matches_a_full_sort():
+  """Property test of the pruned tree merge on the CPU: random list counts / lengths / k, heavy score ties, ties
+  across lists, (-inf, INT64_MAX) padding of short shards."""
+  rng = np.random.default_rng(123)
+  for trial in range(300):
+    n_lists = int(rng.integers(1, 10)); k_in = int(rng.integers(1, 40)); k_out = int(rng.integers(1, 2 * k_in + 3))
+    s = np.round(rng.normal(size=(n_lists, k_in)) * 2) / 2
+    i = np.stack([rng.choice(1000, size=k_in, replace=False) for _ in range(n_lists)]).astype(np.int64)
+    if trial % 3 == 0:  # distinct index ranges per list, as in the sharded scan
+      i += 1000 * np.arange(n_lists)[:, None]
+    n_pad = int(rng.integers(0, k_in)) if trial % 4 == 0 else 0
+    if n_pad:
+      s[-1, k_in - n_pad:] = -np.inf; i[-1, k_in - n_pad:] = np.iinfo(np.int64).max
+    for l in range(n_lists):
+      order = np.lexsort((i[l], -s[l]))
+      s[l], i[l] = s[l][order], i[l][order]
+    got = _tree_merge_emulation(s.astype(np.float32), i, k_out)
+    flat_s, flat_i = s.reshape(-1).astype(np.float32), i.reshape(-1)
+    # expected order: (score desc, index asc), equal pairs in list order -- a stable sort of the concatenation
+    order = sorted(range(flat_s.size), key=lambda t: (-flat_s[t], flat_i[t], t))[:min(k_out, flat_s.size)]
+    exp = [(float(flat_s[t]), int(flat_i[t])) for t in order]
+    assert got == exp, (trial, n_lists, k_in, k_out)
+
+
+def test_dot_interaction_pair_index_inversion():
+  """The forward kernel of csrc/dot_interaction.cu inverts the packed lower-triangle position p -> (i, j) with a
+  float sqrt guess and integer correction loops; check that arithmetic (in float32, as on the device) for every
+  feature count the kernel accepts."""
+  for self_int in (False, True):
+    for F in range(1, 65):
+      expect = [(a, b) for a in range(F) for b in range(a + 1 if self_int else a)]
+      for p, (ei, ej) in enumerate(expect):
+        i = int((np.sqrt(np.float32(8.0) * np.float32(p) + np.float32(1.0)) - np.float32(1.0)) * np.float32(0.5))
+        if self_int:
+          while (i + 1) * (i + 2) // 2 <= p: i += 1
+          while i * (i + 1) // 2 > p: i -= 1
+          j = p - i * (i + 1) // 2
+        else:
+          i += 1
+          while (i + 1) * i // 2 <= p: i += 1
+          while i * (i - 1) // 2 > p: i -= 1
+          j = p - i * (i - 1) // 2
+        assert (i, j) == (ei, ej), (self_int, F, p)
