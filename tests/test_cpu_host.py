@@ -269,3 +269,107 @@ def test_dot_interaction_pair_index_inversion():
           while i * (i - 1) // 2 > p: i -= 1
           j = p - i * (i - 1) // 2
         assert (i, j) == (ei, ej), (self_int, F, p)
+
+
+def _simulate_softmax_bwd_protocol(n_iter, seed, bufs=3, drain=8, stages=4):
+  """Randomised interleaving of the barrier protocol of softmax_tc_bwd_kernel (csrc/softmax_tc_bwd.cu): the producer,
+  the single MMA-issuing thread (S(it) then dX(it-2), dX chunks drained every `drain` tiles) with its asynchronous but
+  in-order tensor pipe, and 16 epilogue warps in two groups.  Barriers are modelled as phase counters; a waiter
+  expecting phase k of a barrier may only ever see k or k+1 completed phases (the parity test of mbarrier.try_wait
+  cannot tell k+2 from k).  Returns when every agent has finished; raises on deadlock or a phase overrun."""
+  import random
+  rnd = random.Random(seed)
+  done = {}        # barrier name -> completed phases
+  arrivals = {}    # barrier name -> arrivals in the current phase
+  need = {}        # barrier name -> arrivals per phase
+
+  def bar(name, count):
+    done[name] = 0; arrivals[name] = 0; need[name] = count
+  for s in range(stages):
+    bar(("y_full", s), 1); bar(("y_empty", s), 1)
+  for b in range(bufs):
+    bar(("s_full", b), 1); bar(("g_ready", b), 8)
+  bar("dx_full", 1); bar("dx_drained", 16)
+
+  def arrive(name):
+    arrivals[name] += 1
+    if arrivals[name] == need[name]:
+      arrivals[name] = 0; done[name] += 1
+
+  def ready(name, k):  # may an agent waiting for the k-th completion of `name` proceed?
+    assert done[name] <= k + 1, ("phase overrun", name, k, done[name])
+    return done[name] >= k + 1
+
+  pipe = []  # in-order queue of commits still to be delivered by the tensor pipe: barrier names
+
+  def producer():
+    for it in range(n_iter):
+      s = it % stages
+      if it >= stages:
+        yield (("y_empty", s), it // stages - 1)
+      arrive(("y_full", s))  # the bulk copy lands (modelled as immediate)
+
+  def mma():
+    def issue_dx(u):
+      chunk, first = u // drain, (u % drain) == 0
+      if first and chunk > 0:
+        yield ("dx_drained", chunk - 1)
+      yield (("g_ready", u % bufs), u // bufs)
+      pipe.append(("y_empty", u % stages))
+      if (u % drain) == drain - 1 or u == n_iter - 1:
+        pipe.append("dx_full")
+    for it in range(n_iter):
+      yield (("y_full", it % stages), it // stages)
+      pipe.append(("s_full", it % bufs))
+      if it >= 2:
+        yield from issue_dx(it - 2)
+    if n_iter >= 2:
+      yield from issue_dx(n_iter - 2)
+    yield from issue_dx(n_iter - 1)
+
+  def epilogue(grp):
+    n_chunks = (n_iter + drain - 1) // drain
+    state = {"next": 0}
+
+    def drain_until(t_next):
+      while state["next"] < n_chunks and min(state["next"] * drain + drain - 1, n_iter - 1) + 3 <= t_next:
+        yield ("dx_full", state["next"])
+        arrive("dx_drained")
+        state["next"] += 1
+    for it in range(grp, n_iter, 2):
+      yield from drain_until(it)
+      yield (("s_full", it % bufs), it // bufs)
+      arrive(("g_ready", it % bufs))
+    yield from drain_until(n_iter + 3 + drain)
+
+  agents = [producer(), mma()] + [epilogue(w >> 3) for w in range(16)]
+  waiting = [None] * len(agents)
+  alive = [True] * len(agents)
+  for a in range(len(agents)):  # prime
+    try:
+      waiting[a] = next(agents[a])
+    except StopIteration:
+      alive[a] = False
+  steps = 0
+  while any(alive) or pipe:
+    steps += 1
+    assert steps < 200000, "no progress bound exceeded"
+    choices = [a for a in range(len(agents)) if alive[a] and ready(*waiting[a])]
+    if pipe:
+      choices.append(-1)
+    assert choices, ("deadlock", n_iter, seed, [w for w, al in zip(waiting, alive) if al])
+    a = rnd.choice(choices)
+    if a == -1:
+      arrive(pipe.pop(0))  # the tensor pipe retires its oldest batch and its commit arrives
+      continue
+    try:
+      waiting[a] = next(agents[a])
+    except StopIteration:
+      alive[a] = False
+  return steps
+
+
+def test_softmax_backward_barrier_protocol_has_no_deadlock_or_phase_overrun():
+  for n_iter in list(range(1, 40)) + [63, 64, 65, 128]:
+    for seed in range(6):
+      _simulate_softmax_bwd_protocol(n_iter, seed)
