@@ -36,7 +36,8 @@ enum {
   TFRS_ERR_INVALID_ARG = -1,
   TFRS_ERR_UNSUPPORTED = -2,
   TFRS_ERR_CUDA = -3,
-  TFRS_ERR_WORKSPACE_TOO_SMALL = -4
+  TFRS_ERR_WORKSPACE_TOO_SMALL = -4,
+  TFRS_ERR_NCCL = -5
 };
 
 enum { TFRS_I32 = 0, TFRS_I64 = 1 };
@@ -91,28 +92,47 @@ int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, const void*
                      int d, int k, int64_t index_offset, float* out_scores, int64_t* out_idx, void* ws,
                      size_t ws_bytes, void* stream);
 
+/* The same tensor-core scan with `query_with_exclusions` fused into the finalize step (layers/factorized_top_k.py
+ * :242-288 + `_exclude` :83-115): the k + n_excl best candidates are selected as above, candidates whose identifier
+ * (identifiers[global index], or the global index itself when identifiers == NULL) appears in exclusions[q, :] get
+ * score - 1e5, the k best ADJUSTED scores win (ties -> better original position) and the ORIGINAL scores / global
+ * indices are written -- bit-for-bit what the reference computes from its over-fetched list.  int64 ids.
+ * Workspace: tfrs_topk_tc_workspace_bytes(Q, N, d, k + n_excl). */
+int tfrs_topk_tc_exclude_f32(const float* q, int64_t Q, const float* corpus, const void* index_buf, int64_t N, int d,
+                             int k, int64_t index_offset, const int64_t* identifiers, const int64_t* exclusions,
+                             int n_excl, float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes, void* stream);
+
+/* The score branch of FactorizedTopK.update_state (metrics/factorized_top_k.py:133-137,181-192) without a top-K
+ * list: out_count[q] = min(k, #{candidates whose exact score is > positive_scores[q]}); the metric for any k' <= k is
+ * then  count < k'  (tf.math.in_top_k: fewer than k' predictions strictly above the target).  Same screening +
+ * exact-rescoring guarantees as tfrs_topk_tc_f32 (only candidates within the error band of the positive are
+ * re-scored).  Workspace: tfrs_topk_tc_workspace_bytes(Q, N, d, k). */
+int tfrs_topk_tc_count_f32(const float* q, int64_t Q, const float* corpus, const void* index_buf, int64_t N, int d,
+                           int k, const float* positive_scores, int32_t* out_count, void* ws, size_t ws_bytes,
+                           void* stream);
+
+/* `_exclude` (layers/factorized_top_k.py:83-115) on an already fetched, sorted [Q, k_fetched] list (Streaming and
+ * the exact CUDA-core path): same rule as tfrs_topk_tc_exclude_f32.  idx are global indices into `identifiers`. */
+int tfrs_topk_exclude_rerank_f32(const float* scores, const int64_t* idx, int64_t Q, int k_fetched,
+                                 const int64_t* identifiers, const int64_t* exclusions, int n_excl, int k_out,
+                                 float* out_scores, int64_t* out_idx, void* stream);
+
+/* out_count[q] = #{t < k : scores[q*ld + t] > positive_scores[q]} -- the in_top_k count on a retrieved list. */
+int tfrs_count_above_f32(const float* scores, int64_t ld, int k, const float* positive_scores, int64_t Q,
+                         int32_t* out_count, void* stream);
+
+/* Device-resident running sums of FactorizedTopK's Mean metrics (metrics/factorized_top_k.py:186-192):
+ *   acc[j] += sum_q w_q * [count_q < ks[j] && isfinite(positive_q)]  (j < n_ks);   acc[n_ks] += sum_q w_q
+ * (w = 1 when sample_weight == NULL).  `ks` is a HOST array (n_ks <= 16), `acc` n_ks + 1 doubles on the device.
+ * Fixed-order fp64 reduction: deterministic; the host reads acc once, in result(). */
+int tfrs_topk_hits_accumulate(const int32_t* count, const float* positive_scores, const float* sample_weight, int64_t Q,
+                              const int32_t* ks, int n_ks, double* acc, void* stream);
+
 /* Test/debug introspection of tfrs_topk_tc_f32's workspace: out8 = {count offset, fallback-flag offset,
  * threshold offset, survivor-list offset, parts, cap_part, padded Q, cut offset} (byte offsets from the
  * 16-byte-aligned workspace base).  Lets the tests assert that the exact fallback was NOT what produced a
  * result. */
 int tfrs_topk_tc_layout(int64_t Q, int64_t N, int d, int k, int64_t* out8);
-
-/* Hardware probe (tools/probe_f16acc.py): one 128x128x64 UMMA tile with a caller-chosen instruction
- * descriptor, raw TMEM dump.  Not on any product path. */
-int tfrs_debug_umma_probe(const void* a_img, const void* b_img, uint32_t idesc, int n_cols, uint32_t* out, void* stream);
-
-/* Memory-system probe (tools/hbm_probe.py): 128-byte rows, the gather's thread layout; mode 0 copy, 1 random-row
- * read only, 2 write only, 3 random read + sequential write, 4 random read + the gather's strided write.  Not on
- * any product path. */
-int tfrs_debug_hbm_probe(int mode, const void* src, int64_t src_rows, void* dst, int64_t n, int64_t n_rows_out,
-                         int64_t ld_floats, float* sink, void* stream);
-/* Tensor-pipe / TMEM timing probe (tools/tc_rate_probe.py): clock64 cycle counts of R rounds of
- * mode 0 tcgen05.ld x64 (16 warps), 1 the same with .pack::16b, 2 twelve SS MMAs M128 N128 K16, 3 twenty-four TS MMAs
- * M128 N64 K16 (A from TMEM, MN-major B), 4 both interleaved (the softmax backward's pattern), 5 tcgen05.st;
- * out_cycles[n_ctas].  Not on any product path. */
-int tfrs_debug_tc_rate_probe(int mode, int rounds, int n_ctas, long long* out_cycles, uint32_t* sink, void* stream);
-/* A/B switch between the two gather kernels (0 lane-per-item, 1 warp-chunk = default); identical results. */
-int tfrs_debug_set_gather_variant(int variant);
 
 /* Optional per-stage device timing of tfrs_topk_tc_f32 (CUDA events on the launch stream; used by
  * bench.py for the roofline figure).  tfrs_profile_read synchronises the device and returns the summed
@@ -139,6 +159,38 @@ int tfrs_topk_merge_strided(const float* scores, const int64_t* idx, int64_t lis
 int tfrs_topk_merge_sorted_strided(const float* scores, const int64_t* idx, int64_t list_stride_scores,
                                    int64_t list_stride_idx, int n_lists, int64_t Q, int k_in, int k_out,
                                    float* out_scores, int64_t* out_idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * C1  the collective of the row-sharded scan (the reference has no sharded scan -- its corpus is one
+ * variable, layers/factorized_top_k.py:571-580 -- and its only collective helper is tasks/retrieval.py:238-321).
+ * One process per GPU; shard g owns a contiguous row block, so global index order == (shard, local index) order and
+ * the lowest-index tie rule survives the merge.  NCCL is bound at run time (dlopen libnccl.so.2: the copy the host
+ * framework already loaded, else the system one; TFRS_NCCL_LIB overrides), so binders need only this header.
+ *
+ *   tfrs_comm_unique_id   rank 0 creates the 128-byte NCCL id; the host framework broadcasts it by any means
+ *   tfrs_comm_create      collective over the group (ncclCommInitRank on the CURRENT device); tfrs_comm_destroy frees it
+ *   tfrs_topk_allgather   every rank's [Q,k] (scores, global indices) -> all_s/all_i [world, Q, k] in rank order
+ *   tfrs_topk_sharded_f32 the whole sharded BruteForce.call in one entry point: local scan (tensor-core path when
+ *                         `index_buf` is given and the shape allows it, exact scan otherwise; shards shorter than k
+ *                         are padded with (-inf, INT64_MAX)) written straight into the send block -> ONE all-gather
+ *                         of the packed blocks -> sorted-list merge on every rank.  Every rank returns the same
+ *                         [Q,k] result.  All ranks must call it with the same Q, d, k.
+ * Handles need external locking; calls are asynchronous on `stream`.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct tfrs_comm* tfrs_comm_t;
+int tfrs_comm_unique_id(void* out128);
+int tfrs_comm_create(tfrs_comm_t* comm, int rank, int world, const void* unique_id128);
+int tfrs_comm_destroy(tfrs_comm_t comm);
+int tfrs_comm_rank(tfrs_comm_t comm);
+int tfrs_comm_world(tfrs_comm_t comm);
+int tfrs_topk_allgather(tfrs_comm_t comm, const float* s, const int64_t* i, int64_t Q, int k, float* all_s,
+                        int64_t* all_i, void* stream);
+size_t tfrs_topk_sharded_workspace_bytes(int world, int64_t Q, int64_t N_local, int d, int k);
+/* test introspection: out4 = {index byte offset inside a block, block bytes, send-block offset, receive-buffer offset} */
+int tfrs_topk_sharded_layout(int world, int64_t Q, int64_t N_local, int d, int k, int64_t* out4);
+int tfrs_topk_sharded_f32(tfrs_comm_t comm, const float* q, int64_t Q, const float* corpus_local, const void* index_buf,
+                          int64_t N_local, int d, int k, int64_t index_offset, float* out_scores, int64_t* out_idx,
+                          void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Score helpers (exact fp32, canonical fmaf chain, one owner thread per output).

@@ -34,19 +34,29 @@ _SIGNATURES = {
     "tfrs_index_build": (c_i, [c_p, c_l, c_i, c_p, c_sz, c_p]),
     "tfrs_topk_tc_workspace_bytes": (c_sz, [c_l, c_l, c_i, c_i]),
     "tfrs_topk_tc_f32": (c_i, [c_p, c_l, c_p, c_p, c_l, c_i, c_i, c_l, c_p, c_p, c_p, c_sz, c_p]),
+    "tfrs_topk_tc_exclude_f32": (c_i, [c_p, c_l, c_p, c_p, c_l, c_i, c_i, c_l, c_p, c_p, c_i, c_p, c_p, c_p, c_sz, c_p]),
+    "tfrs_topk_tc_count_f32": (c_i, [c_p, c_l, c_p, c_p, c_l, c_i, c_i, c_p, c_p, c_p, c_sz, c_p]),
+    "tfrs_topk_exclude_rerank_f32": (c_i, [c_p, c_p, c_l, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p]),
+    "tfrs_count_above_f32": (c_i, [c_p, c_l, c_i, c_p, c_l, c_p, c_p]),
+    "tfrs_topk_hits_accumulate": (c_i, [c_p, c_p, c_p, c_l, c_p, c_i, c_p, c_p]),
     "tfrs_topk_tc_layout": (c_i, [c_l, c_l, c_i, c_i, c_p]),
-    "tfrs_debug_umma_probe": (c_i, [c_p, c_p, ctypes.c_uint32, c_i, c_p, c_p]),
     "tfrs_dot_interaction_out_dim": (c_i, [c_i, c_i, c_i]),
     "tfrs_dot_interaction_fwd_f32": (c_i, [c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_p]),
     "tfrs_dot_interaction_bwd_f32": (c_i, [c_p, c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_p]),
-    "tfrs_debug_tc_rate_probe": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p]),
-    "tfrs_debug_set_gather_variant": (c_i, [c_i]),
-    "tfrs_debug_hbm_probe": (c_i, [c_i, c_p, c_l, c_p, c_l, c_l, c_l, c_p, c_p]),
     "tfrs_profile_enable": (c_i, [c_i]),
     "tfrs_profile_read": (c_i, [c_p, c_p]),
     "tfrs_topk_merge": (c_i, [c_p, c_p, c_i, c_l, c_i, c_i, c_p, c_p, c_p]),
     "tfrs_topk_merge_strided": (c_i, [c_p, c_p, c_l, c_l, c_i, c_l, c_i, c_i, c_p, c_p, c_p]),
     "tfrs_topk_merge_sorted_strided": (c_i, [c_p, c_p, c_l, c_l, c_i, c_l, c_i, c_i, c_p, c_p, c_p]),
+    "tfrs_comm_unique_id": (c_i, [c_p]),
+    "tfrs_comm_create": (c_i, [c_p, c_i, c_i, c_p]),
+    "tfrs_comm_destroy": (c_i, [c_p]),
+    "tfrs_comm_rank": (c_i, [c_p]),
+    "tfrs_comm_world": (c_i, [c_p]),
+    "tfrs_topk_allgather": (c_i, [c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p]),
+    "tfrs_topk_sharded_workspace_bytes": (c_sz, [c_i, c_l, c_l, c_i, c_i]),
+    "tfrs_topk_sharded_layout": (c_i, [c_i, c_l, c_l, c_i, c_i, c_p]),
+    "tfrs_topk_sharded_f32": (c_i, [c_p, c_p, c_l, c_p, c_p, c_l, c_i, c_i, c_l, c_p, c_p, c_p, c_sz, c_p]),
     "tfrs_sgemm_f32": (c_i, [c_i, c_i, c_l, c_l, c_l, c_p, c_l, c_p, c_l, c_p, c_l, c_i, c_p]),
     "tfrs_rowwise_dot_f32": (c_i, [c_p, c_p, c_l, c_i, c_p, c_p]),
     "tfrs_inbatch_softmax_workspace_bytes": (c_sz, [c_l, c_l, c_i]),
@@ -101,6 +111,8 @@ def check(rc: int, what: str = "") -> None:
     raise ValueError(msg)
   if rc == -2:
     raise NotImplementedError(msg)
+  if rc == -5:
+    raise RuntimeError("NCCL: " + msg)
   raise RuntimeError(msg)
 
 

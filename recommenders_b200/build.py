@@ -72,7 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
   with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
     objs = list(ex.map(compile_one, _sources()))
   cmd = [nvcc, *ccbin, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs,
-         "-Xcompiler", "-fPIC", "-cudart", "static"]
+         "-Xcompiler", "-fPIC", "-cudart", "static", "-ldl"]
   r = subprocess.run(cmd, capture_output=True, text=True)
   if r.returncode != 0:
     raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -119,8 +119,7 @@ extern "C" int tfrs_sparse_adagrad_f32(float* table, float* accum, int64_t rows,
   if (ids_dtype == TFRS_I32) ag_build_keys<int32_t><<<kb, 256, 0, st>>>((const int32_t*)ids, n, rows, P, keys);
   else ag_build_keys<int64_t><<<kb, 256, 0, st>>>((const int64_t*)ids, n, rows, P, keys);
   TFRS_LAUNCH_CHECK();
-  static bool attr = false;
-  if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(ag_bitonic_local, cudaFuncAttributeMaxDynamicSharedMemorySize, AG_TILE * 8)); attr = true; }
+  TFRS_DYN_SMEM(ag_bitonic_local, AG_TILE * 8);
   const unsigned tiles = (unsigned)ceil_div(P, AG_TILE);
   const long long local_max = P < AG_TILE ? P : AG_TILE;
   ag_bitonic_local<<<tiles, AG_THREADS, AG_TILE * 8, st>>>(keys, P, 2, local_max);

@@ -48,6 +48,23 @@ __host__ __device__ __forceinline__ bool better(float sa, long long ia, float sb
   return (sa > sb) || (sa == sb && ia < ib);
 }
 
-int sm_count();
+int sm_count();  // SMs of the CURRENT device (cached per device)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (call site, device): function attributes belong to
+// a device/context, so a process-wide "done" flag would leave the second GPU of a process at the 48 KB default.
+struct DeviceOnce {
+  unsigned char done_[64] = {};
+  int dev_ = 0;
+  bool need() { if (cudaGetDevice(&dev_) != cudaSuccess) dev_ = 0; dev_ &= 63; return __atomic_load_n(&done_[dev_], __ATOMIC_ACQUIRE) == 0; }
+  void done() { __atomic_store_n(&done_[dev_], (unsigned char)1, __ATOMIC_RELEASE); }
+};
+#define TFRS_DYN_SMEM(kernel, bytes)                                                                              \
+  do {                                                                                                            \
+    static ::tfrs::DeviceOnce once__;                                                                             \
+    if (once__.need()) {                                                                                          \
+      TFRS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));         \
+      once__.done();                                                                                              \
+    }                                                                                                             \
+  } while (0)
 
 }  // namespace tfrs

@@ -250,8 +250,7 @@ extern "C" int tfrs_cross_tc_fwd_f32(const float* x0, const float* x, const void
   p.x0 = x0; p.x = x; p.bias = bias; p.diag = diag_scale; p.out = out; p.prod = prod;
   p.B = B; p.D = D; p.ld = ld; p.kb = kb; p.n_mb = n_mb; p.n_nt = n_nt;
   const size_t smem = (size_t)CX_STAGES * CX_STAGE_BYTES + 1024 + 256;
-  static bool attr = false;
-  if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(cross_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  TFRS_DYN_SMEM(cross_tc_kernel, (int)smem);
   long long tiles = (long long)n_mb * n_nt;
   int grid = sm_count(); if (grid > tiles) grid = (int)tiles;
   cross_tc_kernel<<<grid, CX_THREADS, smem, st>>>(p);

@@ -265,12 +265,8 @@ size_t cross_tc_bwd_gemm_workspace(long long B, int D) {
 
 static int sg_launch(int mode, const SgParams& p, cudaStream_t st) {
   const size_t smem = (size_t)SG_STAGES2 * SG_STAGE_BYTES + 1024 + 256;
-  static bool attr = false;
-  if (!attr) {
-    TFRS_CUDA(cudaFuncSetAttribute(split_gemm_kernel<SG_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TFRS_CUDA(cudaFuncSetAttribute(split_gemm_kernel<SG_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  TFRS_DYN_SMEM(split_gemm_kernel<SG_DX>, (int)smem);
+  TFRS_DYN_SMEM(split_gemm_kernel<SG_DW>, (int)smem);
   const long long items = (long long)p.n_mb * p.n_nt * p.n_kc;
   int grid = sm_count(); if (grid > items) grid = (int)items;
   if (mode == SG_DX) split_gemm_kernel<SG_DX><<<grid, SG_THREADS2, smem, st>>>(p);

@@ -112,8 +112,7 @@ extern "C" int tfrs_dot_interaction_fwd_f32(const float* feats, int64_t B, int F
   if (B == 0 || od == 0) return TFRS_OK;  // nothing to write (a single feature without self-interaction has no pairs)
   TFRS_CHECK_ARG(out, "dot_interaction_fwd: NULL output");
   const size_t smem = (size_t)DI_WARPS * F * (d + 1) * 4;
-  static bool attr = false;
-  if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(dot_interaction_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+  TFRS_DYN_SMEM(dot_interaction_fwd_kernel, 200 * 1024);
   dot_interaction_fwd_kernel<<<(unsigned)ceil_div(B, DI_WARPS), DI_WARPS * 32, smem, (cudaStream_t)stream>>>(
       feats, B, F, d, self_interaction != 0, skip_gather != 0, od, out);
   TFRS_LAUNCH_CHECK();
@@ -128,8 +127,7 @@ extern "C" int tfrs_dot_interaction_bwd_f32(const float* feats, const float* gou
   if (B == 0) return TFRS_OK;
   const int od = di_out_dim(F, self_interaction, skip_gather);
   const size_t smem = (size_t)DI_WARPS * (F * (d + 1) + od) * 4;
-  static bool attr = false;
-  if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(dot_interaction_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+  TFRS_DYN_SMEM(dot_interaction_bwd_kernel, 200 * 1024);
   dot_interaction_bwd_kernel<<<(unsigned)ceil_div(B, DI_WARPS), DI_WARPS * 32, smem, (cudaStream_t)stream>>>(
       feats, gout, B, F, d, self_interaction != 0, skip_gather != 0, od, dfeats);
   TFRS_LAUNCH_CHECK();

@@ -107,7 +107,6 @@ gather_warpchunk_kernel(GatherParams p, long long n, float* __restrict__ out, lo
   }
 }
 
-static int g_gather_variant = 1;
 
 }  // namespace tfrs
 using namespace tfrs;
@@ -141,7 +140,7 @@ extern "C" int tfrs_gather_f32(const float* const* tables, const int64_t* rows, 
     if (blocks < 1) blocks = 1;
     if (blocks > 1 << 20) blocks = 1 << 20;
     dim3 grid((unsigned)blocks, (unsigned)nt);
-    bool chunkable = vec && g_gather_variant == 1;
+    bool chunkable = vec;
     for (int t = 0; t < nt && chunkable; ++t) {
       const int L = p.dim[t] / 4;
       chunkable = L >= 1 && L <= 32 && (L & (L - 1)) == 0;
@@ -164,6 +163,3 @@ extern "C" int tfrs_gather_f32(const float* const* tables, const int64_t* rows, 
   }
   return TFRS_OK;
 }
-
-// A/B switch for tools/bench_kernels.py: 0 = lane-per-item kernel, 1 = warp-chunk kernel (default).  Same results.
-extern "C" int tfrs_debug_set_gather_variant(int v) { g_gather_variant = v; return TFRS_OK; }

@@ -313,15 +313,11 @@ extern "C" int tfrs_inbatch_softmax_tc_fwd(const float* q, const float* c, int64
   SoftmaxTcParams p{};
   p.qimg = qimg; p.cimg = cimg; p.qst = qst; p.cst = cst; p.B = B; p.C = C; p.nqb = pl.nqb; p.parts = pl.parts; p.kb = pl.kb;
   p.n_ctiles = pl.n_ctiles; p.inv_t = inv_temperature; p.partial = partial; p.pos = pos;
-  static bool attr = false;
-  if (!attr) {
-    const int s1 = (int)((2 + sx_stages(1)) * 32768 + 1280), s2 = (int)((2 + sx_stages(2)) * 2 * 32768 + 1280);
-    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
-    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
-    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
-    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
-    attr = true;
-  }
+  const int s1 = (int)((2 + sx_stages(1)) * 32768 + 1280), s2 = (int)((2 + sx_stages(2)) * 2 * 32768 + 1280);
+  TFRS_DYN_SMEM((softmax_tc_kernel<1, false>), s1);
+  TFRS_DYN_SMEM((softmax_tc_kernel<2, false>), s2);
+  TFRS_DYN_SMEM((softmax_tc_kernel<1, true>), s1);
+  TFRS_DYN_SMEM((softmax_tc_kernel<2, true>), s2);
   const unsigned grid = (unsigned)(pl.nqb * pl.parts);
   if (candidate_bias) {
     float* cb2 = (float*)(w + pl.o_bias);

@@ -399,14 +399,10 @@ extern "C" int tfrs_inbatch_softmax_tc_bwd(const float* q, const float* c, int64
   sb_prep_kernel<<<(unsigned)ceil_div(pl.q_tiles * 128, 256), 256, 0, st>>>(lse, sample_weight, B, pl.q_tiles * 128, wst, lse_pad, w_pad);
   TFRS_LAUNCH_CHECK();
   const size_t smem = 32768 + (size_t)SB_STAGES * SB_STAGE_BYTES + 1024 + 256;
-  static bool attr = false;
-  if (!attr) {
-    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TFRS_CUDA(cudaFuncSetAttribute(softmax_tc_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  TFRS_DYN_SMEM((softmax_tc_bwd_kernel<false, false>), (int)smem);
+  TFRS_DYN_SMEM((softmax_tc_bwd_kernel<true, false>), (int)smem);
+  TFRS_DYN_SMEM((softmax_tc_bwd_kernel<false, true>), (int)smem);
+  TFRS_DYN_SMEM((softmax_tc_bwd_kernel<true, true>), (int)smem);
   SoftmaxBwdParams p{};
   p.xst = qst; p.yst = cst; p.wst = wst; p.lse_pad = lse_pad; p.w_pad = w_pad; p.grad_loss = grad_loss; p.d = d; p.inv_t = inv_temperature;
   // ---- dq: X = q, Y = c

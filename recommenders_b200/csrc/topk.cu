@@ -53,11 +53,7 @@ static int launch_row_topk(Prov prov, long long Q, int k, float* out_s, long lon
                            cudaStream_t st) {
   int cap = rowselect_cap(k);
   size_t smem = rowselect_smem(cap, 0);
-  static bool attr_set = false;
-  if (!attr_set) {
-    TFRS_CUDA(cudaFuncSetAttribute(row_topk_kernel<Prov>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_set = true;
-  }
+  TFRS_DYN_SMEM(row_topk_kernel<Prov>, 64 * 1024);
   row_topk_kernel<Prov><<<(unsigned)Q, RS_THREADS, smem, st>>>(prov, k, cap, out_s, out_i, out_ld);
   TFRS_LAUNCH_CHECK();
   return TFRS_OK;
@@ -260,11 +256,7 @@ extern "C" int tfrs_topk_merge_sorted_strided(const float* scores, const int64_t
   if (n_lists > MS_MAX_LISTS || region * 24 > 160 * 1024 || k_out > 2048)  // outside the tree merge: the sorting merge is always valid
     return tfrs_topk_merge_strided(scores, idx, list_stride_scores, list_stride_idx, n_lists, Q, k_in, k_out, out_scores, out_idx, stream);
   const size_t smem = (size_t)region * 24;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TFRS_CUDA(cudaFuncSetAttribute(merge_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
-  }
+  TFRS_DYN_SMEM(merge_sorted_kernel, 160 * 1024);
   merge_sorted_kernel<<<(unsigned)Q, MS_THREADS, smem, (cudaStream_t)stream>>>(scores, (const long long*)idx, list_stride_scores,
                                                                              list_stride_idx, n_lists, k_in, ko, (int)region,
                                                                              out_scores, (long long*)out_idx, k_out);

@@ -4,17 +4,22 @@
 // corpora.  The [Q,N] score matrix never exists in HBM:
 //
 //   index time   tfrs_index_build : corpus fp32 -> fp16 image (exact 2^e rescale), pre-tiled as 128-row UMMA SWIZZLE_128B
-//                K-major tiles (one contiguous 16 KB block per 64-wide K slab), + max row norm / max |element|.
-//   query time   (0) q stats/image: queries -> the same fp16 tile image; per-query error margin
-//                (1) tc_scan<SAMPLE> : screening GEMM over every 4th corpus tile; epilogue keeps only the
-//                    per-(query, 64-column bin) max  -> K-th largest bin max = a valid lower bound L_q of
-//                    the K-th best screening score (K distinct bins hold K distinct candidates >= it)
+//                K-major tiles (one contiguous 16 KB block per 64-wide K slab), + max row norm (scaled units).
+//   query time   (0) tc_qprep     : ONE kernel, a warp per query: per-ROW power-of-two rescale (scores of different
+//                    queries are never compared, so every query gets its own exponent), fp16 tile image, error margins
+//                (1) tc_scan<SAMPLE> : screening GEMM over every 4th corpus tile; each epilogue thread keeps the maximum
+//                    of a GROUP of tiles (a "bin") -> <= 1024 bins per query; tc_threshold (a warp per query, bins in
+//                    registers) takes the K-th largest bin maximum L_q: K distinct bins hold K distinct candidates
+//                    >= L_q, so L_q is a valid lower bound of the K-th best screening score
 //                (2) tc_scan<FILTER> : screening GEMM over the whole corpus; epilogue compares the fp32
 //                    accumulators (read from TMEM) with T_q = L_q - margin_q and appends the rare
-//                    survivors (score, index) to a per-query list -- nothing else leaves the SM
-//                (3) tc_finalize : per query: tau = K-th best screening score; survivors within the error
-//                    band of tau are re-scored EXACTLY (sequential fp32 fmaf chain on the fp32 corpus),
-//                    sorted by (score desc, index asc) -> bit-identical to the exact CUDA-core path.
+//                    survivors (octet records) to per-(query, part, half) lists -- nothing else leaves the SM
+//                (3) tc_finalize (a warp per query, no block barriers): tau = K-th best screening score; survivors
+//                    within the error band of tau are re-scored EXACTLY (sequential fp32 fmaf chain on the fp32
+//                    corpus) and ranked by (score desc, index asc) -> bit-identical to the exact CUDA-core path.
+//                    Variants of the same kernel: EXCLUDE (query_with_exclusions, :83-115,242-288: the k+E best are
+//                    re-ranked with excluded identifiers lowered by 1e5) and COUNT (the FactorizedTopK metric,
+//                    metrics/factorized_top_k.py:133-192: #{candidates scoring above the positive}, no top-K list).
 //                (4) overflow fallback (list capacity exceeded; adversarial inputs only): exact scan.
 //
 // Why the result is exact: |screen(q,c) - exact(q,c)| <= eps_q = E_REL*|q|*max|c| (fp16 rounding of both
@@ -22,15 +27,14 @@
 // of the exact top-K has screening score >= tau - 2*eps_q >= L_q - 2*eps_q, so it is in the list and in
 // the re-scored band.
 //
-// Kernel shape (per CTA, 1 CTA / SM, 384 threads): 256 queries (two 128-row A blocks, resident in smem)
+// Scan kernel shape (per CTA, 1 CTA / SM, 640 threads): 256 queries (two 128-row A blocks, resident in smem)
 // x a contiguous range of 128-row corpus tiles streamed through a 4-6 stage bulk-TMA ring; warp 0 = TMA
 // producer, warp 1 = MMA issuer (one thread, tcgen05.mma M=128 N=128 K=16, fp16 -> fp32 in TMEM),
-// warp 2 = TMEM allocator, warps 4-11 = epilogue (one query row per thread, tcgen05.ld 32x32b.x32).
+// warp 2 = TMEM allocator, warps 4-19 = epilogue (one query row x 64 columns per thread, tcgen05.ld 32x32b.x64).
 // TMEM holds 2 A-blocks x 2 buffers x 128 columns = all 512 columns, so tile t+1's MMAs overlap tile
 // t's epilogue.  Each B tile feeds two MMAs (both A blocks): 16 KB of L2->smem traffic per 512
 // tensor-core cycles keeps the chip under the ~6.3 KB/clk L2 fabric limit.
 #include <cuda_fp16.h>
-#include <cuda_bf16.h>
 #include <stdlib.h>
 #include "rowselect.cuh"
 #include "tc_ptx.cuh"
@@ -47,27 +51,21 @@ constexpr int HEADER_BYTES = 1024;
 constexpr int THREADS = 640;      // 4 control warps + 16 epilogue warps (4 per SM sub-partition)
 constexpr int EPI_WARPS = 16;
 constexpr int EPI_WARP0 = 4;
-constexpr int CAND_CAP = 2048;       // survivors kept per query
+constexpr int CAND_CAP = 2048;       // octet records kept per query across all segments (sizing of cap_part)
 constexpr int MAX_SAMPLE_STRIDE = 4;
 constexpr int FIN_MAX_PARTS = 2 * 148;  // survivor-list segments per query: (corpus part, column half)
-// Screening error model (operands: fp16 after an exact power-of-two rescale of each side so that the
-// largest magnitude lands in [2^14, 2^15); accumulate: fp32 in TMEM):
+constexpr int MAX_BINS = 1024;       // bin maxima per query (32 per lane of the threshold warp)
+constexpr int FP16_TARGET = 15;      // largest operand magnitude lands in [2^14, 2^15)
+// Screening error model (operands: fp16 after an exact power-of-two rescale -- one exponent for the whole corpus,
+// one per query row -- so that the largest magnitude lands in [2^14, 2^15); accumulate: fp32 in TMEM):
 //   |x^ - x| <= 2^-11 |x| (+2^-25 absolute below the fp16 normal range, negligible after the rescale)
 //   => |screen - exact| <= (2^-10 + 2^-22) sum|q_k c_k|  + accumulation slack (budget 2^-14) + fmaf-chain 2^-16
 //   <= E_REL * |q| * |c|   (Cauchy-Schwarz), E_REL = 0.00108 including the 0.1 % norm inflation.
 constexpr float E_REL = 0.00108f;
 constexpr float E_ACC = 0.00013f;    // run-to-run slack between the two passes (they are bit-identical in practice)
 
-// Debug A/B switch (env TFRS_TC_BF16=1): screen with unscaled bf16 operands instead of scaled fp16.
-static int use_bf16() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("TFRS_TC_BF16"); v = (e && atoi(e)) ? 1 : 0; }
-  return v;
-}
-constexpr float E_REL_BF16 = 0.0083f;
-
-struct SideStats {              // per operand side (corpus at index time, queries per call)
-  unsigned int max_norm2_bits;  // max_i |x_i|^2   (float bits; non-negative so uint order == float order)
+struct SideStats {              // corpus side, written at index time
+  unsigned int max_norm2_bits;  // max_i |x_i * 2^exp|^2  (SCALED units; float bits; non-negative so uint order == float order)
   unsigned int amax_bits;       // max_ij |x_ij|
   int exp;                      // rescale exponent e: x * 2^e has its largest magnitude in [2^14, 2^15)
   int pad;
@@ -78,14 +76,21 @@ struct IndexHeader {
   long long n, n_tiles;
 };
 
+__device__ __forceinline__ int rescale_exp(float amax) {
+  int x = 0;
+  if (!(amax > 0.f) || !(amax < INFINITY)) return 0;
+  (void)frexpf(amax, &x);      // amax = m * 2^x, m in [0.5, 1)
+  return FP16_TARGET - x;      // amax * 2^exp in [2^(target-1), 2^target)
+}
+
 // ------------------------------------------------------------------------------------------------
 // image builders: fp32 [rows, d] -> fp16 128-row tiles, each K slab of 64 as one swizzled 16 KB block
 //   byte offset of element (r, k) inside a tile = (k/64)*16384 + r*128 + (((k%64)/8) ^ (r%8))*16 + (k%8)*2
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 tile_image_kernel(const float* __restrict__ src, long long rows, int d, int kb, long long n_tiles,
-                  const SideStats* __restrict__ st, int bf16, unsigned char* __restrict__ img) {
-  const int scale_exp = bf16 ? 0 : st->exp;
+                  const SideStats* __restrict__ st, unsigned char* __restrict__ img) {
+  const int scale_exp = st->exp;
   const long long total = n_tiles * TILE_N * (long long)kb * 8;  // 16-byte chunks
   for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
     int chunk = (int)(e % (kb * 8));
@@ -99,69 +104,95 @@ tile_image_kernel(const float* __restrict__ src, long long rows, int d, int kb, 
     for (int j = 0; j < 8; ++j) {
       float f = (row < rows && k0 + j < d) ? src[row * d + k0 + j] : 0.f;
       v[j] = __float2half_rn(ldexpf(f, scale_exp));  // exact power-of-two rescale, then one rounding to fp16
-      if (bf16) { __nv_bfloat16 b = __float2bfloat16_rn(f); v[j] = *reinterpret_cast<__half*>(&b); }
     }
     unsigned char* dst = img + tile * ((long long)kb * SLAB_BYTES) + (long long)slab * SLAB_BYTES + r * 128 + ((cj ^ (r & 7)) * 16);
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
   }
 }
 
-// max row norm^2 and max |element| of a [rows, d] matrix (one warp per row -> coalesced)
+// corpus statistics, two passes (one warp per row -> coalesced): PASS 0 max |element| -> exponent; PASS 1 max row norm^2
+// of the SCALED rows (so tiny or huge corpora neither underflow nor overflow the fp32 norm)
+template <int PASS>
 __global__ void __launch_bounds__(256)
-side_stats_kernel(const float* __restrict__ src, long long rows, int d, SideStats* __restrict__ st,
-                  float* __restrict__ row_n2 /* nullable: per-row |x|^2 */) {
+corpus_stats_kernel(const float* __restrict__ src, long long rows, int d, SideStats* __restrict__ st) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * 256) >> 5;
-  float best_n2 = 0.f, best_a = 0.f;
+  const int e = PASS ? st->exp : 0;
+  float best = 0.f;
   for (long long row = warp; row < rows; row += nwarps) {
     const float* p = src + row * d;
-    float n2 = 0.f, a = 0.f;
-    for (int k = lane; k < d; k += 32) { float x = p[k]; n2 = fmaf(x, x, n2); a = fmaxf(a, fabsf(x)); }
+    float acc = 0.f;
+    for (int k = lane; k < d; k += 32) {
+      const float x = p[k];
+      if (PASS) { const float y = ldexpf(x, e); acc = fmaf(y, y, acc); } else acc = fmaxf(acc, fabsf(x));
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { n2 += __shfl_xor_sync(0xffffffffu, n2, o); a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o)); }
-    best_n2 = fmaxf(best_n2, n2); best_a = fmaxf(best_a, a);
-    if (row_n2 && lane == 0) row_n2[row] = n2;
+    for (int o = 16; o > 0; o >>= 1) {
+      const float other = __shfl_xor_sync(0xffffffffu, acc, o);
+      acc = PASS ? acc + other : fmaxf(acc, other);
+    }
+    best = fmaxf(best, acc);
   }
-  if (lane == 0) {
-    if (best_n2 > 0.f) atomicMax(&st->max_norm2_bits, __float_as_uint(best_n2 * 1.0001f));  // slack for the tree order
-    if (best_a > 0.f) atomicMax(&st->amax_bits, __float_as_uint(best_a));
+  if (lane == 0 && best > 0.f) {
+    if (PASS) atomicMax(&st->max_norm2_bits, __float_as_uint(best * 1.0001f));  // slack for the tree order
+    else atomicMax(&st->amax_bits, __float_as_uint(best));
   }
 }
-__global__ void side_exp_kernel(SideStats* st, int target) {
-  const float amax = __uint_as_float(st->amax_bits);
-  int x = 0;
-  if (amax > 0.f && amax < INFINITY) (void)frexpf(amax, &x);  // amax = m * 2^x, m in [0.5, 1)
-  st->exp = (amax > 0.f && amax < INFINITY) ? (target - x) : 0;  // amax * 2^exp in [2^(target-1), 2^target)
-}
-static int fp16_target() {
-  static int v = -100;
-  if (v == -100) { const char* e = getenv("TFRS_TC_FP16_TARGET"); v = e ? atoi(e) : 15; }
-  return v;
-}
-
+__global__ void side_exp_kernel(SideStats* st) { st->exp = rescale_exp(__uint_as_float(st->amax_bits)); }
 __global__ void header_kernel(IndexHeader* dst, IndexHeader h) { *dst = h; }
 
-// per-query margins from |q| and the corpus max norm, expressed in SCREENING units (scores scaled by
-// 2^(exp_q + exp_c), an exact power of two)
+// (0) query preparation, one warp per (padded) query row: per-row exponent, scaled norm -> margins, fp16 tile image.
+//   margin[row] = 2*eps + run-to-run slack  (filter threshold T = L - margin)
+//   cut[row]    = 2*eps                      (band below tau that is re-scored exactly)
+//   qexp[row]   = the row's exponent (COUNT mode converts the positive score to screening units with it)
+// All in SCREENING units: scores scaled by 2^(exp_corpus + exp_row), an exact power of two.
 __global__ void __launch_bounds__(256)
-qmargin_kernel(long long Q, long long Qp, const IndexHeader* __restrict__ hdr, const SideStats* __restrict__ qst, int bf16,
-               float* __restrict__ margin /* in: |q|^2 per row (rows < Q); out: filter margin */, float* __restrict__ cut) {
-  long long row = (long long)blockIdx.x * 256 + threadIdx.x;
+tc_qprep_kernel(const float* __restrict__ q, long long Q, long long Qp, int d, int kb, const IndexHeader* __restrict__ hdr,
+                unsigned char* __restrict__ qimg, float* __restrict__ margin, float* __restrict__ cut, int* __restrict__ qexp) {
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
   if (row >= Qp) return;
-  const float n2 = row < Q ? margin[row] * 1.0001f : 0.f;  // slack for the tree-order norm
-  const float cn = sqrtf(__uint_as_float(hdr->st.max_norm2_bits)) * 1.001f;
-  const float qn = sqrtf(n2) * 1.001f;
-  const int se = bf16 ? 0 : (hdr->st.exp + qst->exp);
-  const float e = ldexpf((bf16 ? E_REL_BF16 : E_REL) * qn * cn, se) + 1e-30f;
-  margin[row] = 2.f * e + ldexpf(E_ACC * qn * cn, se);
-  cut[row] = 2.f * e;
+  const bool real = row < Q;
+  const float* p = q + row * d;
+  float a = 0.f;
+  if (real) for (int k = lane; k < d; k += 32) a = fmaxf(a, fabsf(p[k]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+  const int e = rescale_exp(a);
+  float n2 = 0.f;
+  if (real) for (int k = lane; k < d; k += 32) { const float y = ldexpf(p[k], e); n2 = fmaf(y, y, n2); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+  if (lane == 0) {
+    const float cn = sqrtf(__uint_as_float(hdr->st.max_norm2_bits)) * 1.001f;   // scaled corpus norm bound
+    const float qn = sqrtf(n2 * 1.0001f) * 1.001f;                               // scaled query norm (+ tree-order slack)
+    const float eps = E_REL * qn * cn + 1e-30f;
+    margin[row] = 2.f * eps + E_ACC * qn * cn;
+    cut[row] = 2.f * eps;
+    qexp[row] = e;
+  }
+  // image: chunk (slab, cj) of this row; kb*8 <= 16 chunks, one lane each
+  const int r = (int)(row % TILE_N);
+  const long long tile = row / TILE_N;
+  if (lane < kb * 8) {
+    const int slab = lane >> 3, cj = lane & 7;
+    const int k0 = slab * KSLAB + cj * 8;
+    __align__(16) __half v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float f = (real && k0 + j < d) ? p[k0 + j] : 0.f;
+      v[j] = __float2half_rn(ldexpf(f, e));
+    }
+    unsigned char* dst = qimg + tile * ((long long)kb * SLAB_BYTES) + (long long)slab * SLAB_BYTES + r * 128 + ((cj ^ (r & 7)) * 16);
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // the screening GEMM
 // ------------------------------------------------------------------------------------------------
-enum { MODE_SAMPLE = 0, MODE_FILTER = 1, MODE_DBG_LDONLY = 2, MODE_DBG_NOLD = 3 };  // 2,3: sample-pass experiments
+enum { MODE_SAMPLE = 0, MODE_FILTER = 1 };
 
 struct ScanParams {
   const unsigned char* qimg;    // query tile image  [2*nqb tiles][KB][16 KB]
@@ -169,11 +200,12 @@ struct ScanParams {
   long long Q, N;
   int nqb, parts, n_seq, stride;  // tile sequence: tile(u) = u * stride, u in [0, n_seq)
   long long n_tiles;
-  // SAMPLE
-  float* binmax; int bins_ld;     // [Qp, bins_ld], 2 bins per sampled tile
+  // SAMPLE: a bin = the maximum over `group` consecutive sampled tiles x 64 columns of one epilogue thread
+  float* binmax; int bins_ld;     // [Qp, bins_ld]; bin = (part * bins_per_part + it / group) * 2 + half
+  int group, bins_per_part;
   // FILTER
   const float* thr;               // [Qp]
-  unsigned int* count;            // [Qp, parts]   survivors found by each (query, corpus part)
+  unsigned int* count;            // [Qp, parts, 2]   records written by each (query, corpus part, half)
   // Survivor RECORDS: when any of 8 consecutive columns of a row passes the threshold, the whole octet is
   // appended (two 16-byte stores + the index of its first column); finalize drops the non-survivors.
   // One private segment per (query row, corpus part, column half): a single writer thread, no atomics.
@@ -278,6 +310,10 @@ tc_scan_kernel(const ScanParams p) {
       const long long seg = (((long long)row * p.parts + part) * 2 + half) * p.cap_part;
       my_s = p.cand_s + seg * 8; my_i = p.cand_i + seg;
     }
+    float binm = -INFINITY;
+    int in_group = 0, bin_out = 0;
+    float* my_bins = nullptr;
+    if (MODE == MODE_SAMPLE) my_bins = p.binmax + row * p.bins_ld + (long long)part * p.bins_per_part * 2 + half;
     for (int it = 0; it < n_iter; ++it) {
       const int buf = it & 1;
       const uint32_t tphase = (it >> 1) & 1;
@@ -287,23 +323,15 @@ tc_scan_kernel(const ScanParams p) {
       mbar_wait(&t_full[buf], tphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ab * 2 + buf) * TILE_N);
-      float binm = -INFINITY;
       {
         const int h = half;
         uint32_t r[64];
-        if (MODE != MODE_DBG_NOLD) {
-          tmem_ld64(taddr + h * 64, r);
-          tmem_ld_wait64(r);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 64; ++j) r[j] = (uint32_t)(it * 131 + j * 7 + h + lane);
-        }
+        tmem_ld64(taddr + h * 64, r);
+        tmem_ld_wait64(r);
         // this warp's TMEM reads of the accumulator buffer are complete: release it before the math
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[buf]);
-        if (MODE == MODE_DBG_LDONLY) binm = fmaxf(binm, __uint_as_float(r[0] ^ r[63]));
-        else {
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
           float v[32];
@@ -344,11 +372,19 @@ tc_scan_kernel(const ScanParams p) {
             }
           }
         }
+      }
+      if (MODE == MODE_SAMPLE) {   // close the bin after `group` tiles (loop-uniform)
+        if (++in_group == p.group || it == n_iter - 1) {
+          if (row_ok) my_bins[2 * bin_out] = binm;
+          ++bin_out; in_group = 0; binm = -INFINITY;
         }
       }
-      if (MODE != MODE_FILTER && row_ok) p.binmax[row * p.bins_ld + 2 * u + half] = binm;
     }
-    if (MODE == MODE_FILTER) p.count[((long long)row * p.parts + part) * 2 + half] = my_ovf ? (cap + 1u) : my_cnt;
+    if (MODE == MODE_SAMPLE) {
+      if (row_ok) for (; bin_out < p.bins_per_part; ++bin_out) my_bins[2 * bin_out] = -INFINITY;  // bins this part did not fill
+    } else {
+      p.count[((long long)row * p.parts + part) * 2 + half] = my_ovf ? (cap + 1u) : my_cnt;
+    }
   }
 
   tc_fence_before();
@@ -359,7 +395,7 @@ tc_scan_kernel(const ScanParams p) {
 // ------------------------------------------------------------------------------------------------
 // threshold from the bin maxima; finalize; fallback
 // ------------------------------------------------------------------------------------------------
-// orderable key: larger float <=> larger unsigned (NaN sorts above +inf; -0 < +0 is harmless here)
+// orderable key: larger float <=> larger unsigned (NaN sorts above +inf; -0 < +0, callers canonicalise zeros)
 __device__ __forceinline__ unsigned int f2key(float f) {
   unsigned int u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -367,237 +403,314 @@ __device__ __forceinline__ unsigned int f2key(float f) {
 __device__ __forceinline__ float key2f(unsigned int k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+  return v;
+}
 
-// Block-wide k-th largest of n keys by 4 passes of 8-bit radix histograms (256 threads).
-// `key_at(i)` must be cheap and repeatable.  Returns the k-th largest key (1-based k <= n) to all threads.
-template <class KeyAt>
-__device__ unsigned int block_kth_largest(KeyAt key_at, int n, int k, unsigned int* hist /*[256] smem*/, unsigned int* bcast /*[2] smem*/) {
-  unsigned int prefix = 0, mask = 0;
-  int remaining = k;
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int t = threadIdx.x; t < 256; t += blockDim.x) hist[t] = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      unsigned int key = key_at(i);
-      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      // lane l owns buckets [8l, 8l+8); walk from the top bucket down until `remaining` is covered
-      const int lane = threadIdx.x;
-      unsigned int loc[8], tot = 0;
+// k-th largest of the keys a warp holds in registers (KPL per lane, unused slots = 0 = below every float key):
+// bitwise binary search for the largest v with #{key >= v} >= k, one REDUX.SUM per bit.
+template <int KPL>
+__device__ __forceinline__ unsigned int warp_kth_largest_regs(const unsigned int (&key)[KPL], int k) {
+  unsigned int prefix = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const unsigned int cand = prefix | (1u << bit);
+    int c = 0;
 #pragma unroll
-      for (int b = 0; b < 8; ++b) { loc[b] = hist[lane * 8 + b]; tot += loc[b]; }
-      // suffix sum over lanes above
-      unsigned int above = 0;
-#pragma unroll
-      for (int l = 31; l >= 0; --l) {  // every lane executes every shuffle
-        const unsigned int tl = __shfl_sync(0xffffffffu, tot, l);
-        if (l > lane) above += tl;
-      }
-      unsigned int run = above;
-      int found = -1; unsigned int before = 0;
-#pragma unroll
-      for (int b = 7; b >= 0; --b) {
-        if (found < 0 && run + loc[b] >= (unsigned)remaining) { found = lane * 8 + b; before = run; }
-        run += loc[b];
-      }
-      const bool mine = (found >= 0) && (above < (unsigned)remaining);
-      if (mine) { bcast[0] = (unsigned int)found; bcast[1] = before; }
-    }
-    __syncthreads();
-    const unsigned int bucket = bcast[0];
-    remaining -= (int)bcast[1];
-    prefix |= bucket << shift;
-    mask |= 255u << shift;
-    __syncthreads();
+    for (int j = 0; j < KPL; ++j) c += (key[j] >= cand) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= k) prefix = cand;
+  }
+  return prefix;
+}
+// the same over n keys in shared memory
+__device__ __forceinline__ unsigned int warp_kth_largest_smem(const unsigned int* keys, int n, int k, int lane) {
+  unsigned int prefix = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const unsigned int cand = prefix | (1u << bit);
+    int c = 0;
+    for (int t = lane; t < n; t += 32) c += (keys[t] >= cand) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= k) prefix = cand;
   }
   return prefix;
 }
 
-// k-th largest bin maximum of the sampled pass -> filter threshold T = L - margin.
-// The row of bin maxima is staged once in shared memory (when it fits) and radix-selected there.
-constexpr int THR_SMEM_BINS = 12288;
+// (1b) K-th largest bin maximum of the sampled pass -> filter threshold T = L - margin.  One warp per query, the
+// query's <= 32*KPL bin maxima live in registers.
+template <int KPL>
 __global__ void __launch_bounds__(256)
 tc_threshold_kernel(const float* __restrict__ binmax, int bins_ld, int n_bins, int k, const float* __restrict__ margin,
-                    float* __restrict__ thr, unsigned int* __restrict__ overflow) {
-  extern __shared__ unsigned int thr_keys[];
-  __shared__ unsigned int hist[256];
-  __shared__ unsigned int bcast[2];
-  const int row = blockIdx.x;
-  const float* src = binmax + (long long)row * bins_ld;
-  unsigned int kth;
-  if (n_bins <= THR_SMEM_BINS) {
-    for (int i = threadIdx.x; i < n_bins; i += 256) thr_keys[i] = f2key(__ldg(src + i));
-    __syncthreads();
-    kth = block_kth_largest([&](int i) { return thr_keys[i]; }, n_bins, k, hist, bcast);
-  } else {
-    kth = block_kth_largest([&](int i) { return f2key(__ldg(src + i)); }, n_bins, k, hist, bcast);
-  }
-  if (threadIdx.x == 0) { thr[row] = key2f(kth) - margin[row]; overflow[row] = 0; }
+                    float* __restrict__ thr, unsigned int* __restrict__ overflow, long long Q) {
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+  if (row >= Q) return;
+  const float* src = binmax + row * bins_ld;
+  unsigned int key[KPL];
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) { const int i = j * 32 + lane; key[j] = i < n_bins ? f2key(__ldg(src + i)) : 0u; }
+  const unsigned int kth = warp_kth_largest_regs<KPL>(key, k);
+  if (lane == 0) { thr[row] = key2f(kth) - margin[row]; overflow[row] = 0; }
 }
 
-constexpr int FIN_MAXM = 1024;  // survivors re-scored exactly per query (band around tau)
+// (3) finalize: one WARP per query, no block-wide barriers.
+enum { FIN_TOPK = 0, FIN_EXCLUDE = 1, FIN_COUNT = 2 };
+constexpr int FW_WARPS = 4;                       // queries per CTA
+constexpr int FW_SOFF = 304;                      // >= FIN_MAX_PARTS + 1 segment offsets
+constexpr int FW_KEYS_SMALL = 1024, FW_BAND_SMALL = 512;    // first try
+constexpr int FW_KEYS_BIG = 4096, FW_BAND_BIG = 1024;       // retry of the rows that overflowed the first try
+// overflow[row]: 0 = done, 1 = retry with the big capacities, 2 = exact fallback
+static size_t fin_warp_bytes(int cap_keys, int cap_band) { return (size_t)cap_keys * 8 + (size_t)cap_band * 8 + FW_SOFF * 4 + 512; }
 
-__global__ void __launch_bounds__(256, 5)
-tc_finalize_kernel(const float* __restrict__ q, const float* __restrict__ corpus, int d, int k, long long index_offset,
-                   const unsigned int* __restrict__ count, const float* __restrict__ cand_s,
-                   const unsigned int* __restrict__ cand_i, int parts, int cap_part,
-                   const float* __restrict__ cut, const float* __restrict__ thr, long long N,
-                   unsigned int* __restrict__ overflow, float* __restrict__ out_s, long long* __restrict__ out_i) {
-  extern __shared__ __align__(16) unsigned char fsm[];
-  long long* ei = reinterpret_cast<long long*>(fsm);                       // [FIN_MAXM]  exact stage indices
-  float* es = reinterpret_cast<float*>(fsm + (size_t)FIN_MAXM * 8);         // [FIN_MAXM]  exact scores
-  float* as = es + FIN_MAXM;                                                // [CAND_CAP]  screening scores
-  unsigned int* ai = reinterpret_cast<unsigned int*>(as + CAND_CAP);        // [CAND_CAP]  local indices
-  float* qs = reinterpret_cast<float*>(ai + CAND_CAP);                      // [d]
-  __shared__ unsigned int hist[256];
-  __shared__ unsigned int bcast[2];
-  __shared__ int m_sh;
-  const int row = blockIdx.x, tid = threadIdx.x;
-  // gather this query's per-(part, half) segments: counts -> exclusive prefix (parts <= 296, one thread each)
-  __shared__ int seg_off[FIN_MAX_PARTS + 1];
-  __shared__ int seg_bad;
-  if (tid == 0) seg_bad = 0;
-  __syncthreads();
-  for (int pt = tid; pt < parts; pt += 256) {
-    unsigned int c = count[(long long)row * parts + pt];
-    if (c > (unsigned)cap_part) { seg_bad = 1; c = 0; }
-    seg_off[pt + 1] = (int)c;
+struct FinParams {
+  const float* q; const float* corpus; int d; int k; long long index_offset; long long N; long long Q;
+  const unsigned int* count; const float* cand_s; const unsigned int* cand_i; int segs; int cap_part;
+  const float* cut; const float* thr; unsigned int* overflow;
+  int cap_keys, cap_band; unsigned int pass;     // pass 0: every row; pass 1: rows flagged 1
+  float* out_s; long long* out_i;                // TOPK: [Q, k];  EXCLUDE: [Q, k_out]
+  // EXCLUDE (k = k_out + n_excl candidates are fetched, then re-ranked)
+  const long long* identifiers; const long long* exclusions; int n_excl; int k_out;
+  // COUNT
+  const float* pos; const int* qexp; const IndexHeader* hdr; int* out_count;
+};
+
+// exact score: the canonical sequential fmaf chain on the fp32 corpus row (bit-identical to the oracle)
+__device__ __forceinline__ float exact_score(const float* __restrict__ qs, const float* __restrict__ c, int d) {
+  float acc = 0.f;
+  if ((d & 31) == 0) {  // 8 loads (128 B) in flight per step, then the canonical chain on them
+    for (int kk = 0; kk < d; kk += 32) {
+      float4 cv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) cv[u] = __ldg(reinterpret_cast<const float4*>(c + kk) + u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        acc = fmaf(qs[kk + 4 * u], cv[u].x, acc); acc = fmaf(qs[kk + 4 * u + 1], cv[u].y, acc);
+        acc = fmaf(qs[kk + 4 * u + 2], cv[u].z, acc); acc = fmaf(qs[kk + 4 * u + 3], cv[u].w, acc);
+      }
+    }
+  } else if ((d & 3) == 0) {
+    for (int kk = 0; kk < d; kk += 4) {
+      const float4 cv = __ldg(reinterpret_cast<const float4*>(c + kk));
+      acc = fmaf(qs[kk], cv.x, acc); acc = fmaf(qs[kk + 1], cv.y, acc);
+      acc = fmaf(qs[kk + 2], cv.z, acc); acc = fmaf(qs[kk + 3], cv.w, acc);
+    }
+  } else {
+    for (int kk = 0; kk < d; ++kk) acc = fmaf(qs[kk], __ldg(c + kk), acc);
   }
-  if (tid == 0) seg_off[0] = 0;
-  __syncthreads();
-  if (tid == 0) { int a = 0; for (int pt = 1; pt <= parts; ++pt) { a += seg_off[pt]; seg_off[pt] = a; } }
-  __syncthreads();
-  if (seg_bad) {  // a segment overflowed: exact fallback
-    if (tid == 0) overflow[row] = 1;
+  return acc + 0.0f;  // -0 -> +0: the key order must agree with the float order
+}
+
+// _exclude (layers/factorized_top_k.py:83-115) on a query's kf best candidates, sorted in `srt` as
+// (key(score) << 32 | ~local index): identifiers in `exclusions[row]` get score - 1e5, the k_out best ADJUSTED scores
+// win (ties -> lower position), the ORIGINAL scores and indices are written.  One warp; akey = kf words of scratch.
+__device__ __forceinline__ void exclude_rerank(const unsigned long long* srt, int kf, unsigned long long* akey, long long row,
+                                               const FinParams& p, int lane) {
+  for (int t = lane; t < kf; t += 32) {
+    const unsigned long long e = srt[t];
+    const float s = key2f((unsigned int)(e >> 32));
+    const long long gi = (long long)(0xFFFFFFFFu - (unsigned int)e) + p.index_offset;
+    const long long ident = p.identifiers ? __ldg(p.identifiers + gi) : gi;
+    bool isin = false;
+    for (int x = 0; x < p.n_excl; ++x) isin |= (__ldg(p.exclusions + row * p.n_excl + x) == ident);
+    const float adj = (isin ? s - 1.0e5f : s) + 0.0f;   // scores - isin * 1e5 (:104-107)
+    akey[t] = ((unsigned long long)f2key(adj) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)t);
+  }
+  __syncwarp();
+  for (int t = lane; t < kf; t += 32) {
+    const unsigned long long mine = akey[t];
+    int rank = 0;
+    for (int j = 0; j < kf; ++j) rank += (akey[j] > mine) ? 1 : 0;
+    if (rank < p.k_out) {
+      const unsigned long long e = srt[t];
+      p.out_s[row * p.k_out + rank] = key2f((unsigned int)(e >> 32));
+      p.out_i[row * p.k_out + rank] = (long long)(0xFFFFFFFFu - (unsigned int)e) + p.index_offset;
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(FW_WARPS * 32)
+tc_finalize_kernel(const FinParams p) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * FW_WARPS + warp;
+  if (row >= p.Q) return;
+  if (p.overflow[row] != p.pass) return;                 // pass 0 takes the rows the threshold kernel reset, pass 1 the retries
+  const unsigned int retry_flag = (p.pass == 0 && (p.cap_keys < FW_KEYS_BIG || p.cap_band < FW_BAND_BIG)) ? 1u : 2u;
+  unsigned char* base = fsm + (size_t)warp * ((size_t)p.cap_keys * 8 + (size_t)p.cap_band * 8 + FW_SOFF * 4 + 512);
+  unsigned int* keys = reinterpret_cast<unsigned int*>(base);                           // [cap_keys] screening keys
+  unsigned int* sidx = keys + p.cap_keys;                                                // [cap_keys] local indices
+  unsigned long long* band = reinterpret_cast<unsigned long long*>(sidx + p.cap_keys);   // [cap_band]
+  int* soff = reinterpret_cast<int*>(band + p.cap_band);                                 // [segs + 1]
+  float* qs = reinterpret_cast<float*>(soff + FW_SOFF);                                  // [d]
+  const unsigned int lt_mask = (1u << lane) - 1u;
+
+  // segment counts -> exclusive prefix
+  int carry = 0; bool bad = false;
+  for (int s0 = 0; s0 < p.segs; s0 += 32) {
+    const int s = s0 + lane;
+    int c = 0;
+    if (s < p.segs) {
+      const unsigned int cc = __ldg(p.count + row * p.segs + s);
+      if (cc > (unsigned int)p.cap_part) bad = true; else c = (int)cc;
+    }
+    const int inc = warp_incl_scan(c, lane);
+    if (s < p.segs) soff[s + 1] = carry + inc;
+    carry += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (lane == 0) soff[0] = 0;
+  if (__any_sync(0xffffffffu, bad)) {  // a segment overflowed in the filter pass: records are missing -> exact fallback
+    if (lane == 0) p.overflow[row] = 2;
     return;
   }
-  for (int t = tid; t < d; t += 256) qs[t] = q[(long long)row * d + t];
-  // All octet records of all segments as one flat list: a thread takes a record (one segment lookup, one index
-  // load, two 16-byte score loads), keeps the true survivors (>= filter threshold, real row) and the warp
-  // reserves its output slots with a shuffle prefix sum + ONE shared atomic.
-  __shared__ int n_sh;
-  if (tid == 0) n_sh = 0;
-  __syncthreads();
-  const float thr_row = thr[row];
-  const int total_rec = seg_off[parts];
-  const int lane_id = tid & 31;
-  for (int rb = 0; rb < total_rec; rb += 256) {  // block-uniform trip count (warp shuffles inside)
-    const int rec = rb + tid;
-    float sc[8]; unsigned int ix0 = 0; int cnt = 0; unsigned int keep = 0;
+  for (int t = lane; t < p.d; t += 32) qs[t] = p.q[row * p.d + t];
+  __syncwarp();
+  const int total_rec = soff[p.segs];
+  const float thr_row = p.thr[row];
+
+  if (MODE == FIN_COUNT) {
+    // metrics/factorized_top_k.py:181-192: in_top_k(target = the positive, k) <=> #{candidates scoring > positive} < k.
+    // screen > pos + eps => exact > pos (counted as is); |screen - pos| <= eps => re-scored exactly.  When the positive
+    // lies below the listed range, at least K listed candidates are definite (L_q > pos + eps), so min(k, count) is exact.
+    const float eps = 0.5f * p.cut[row];
+    const float pos = p.pos[row];
+    const float pos_s = ldexpf(pos, p.hdr->st.exp + p.qexp[row]);
+    int definite = 0, m = 0;
+    for (int rb = 0; rb < total_rec; rb += 32) {
+      const int rec = rb + lane;
+      unsigned int ix0 = 0, amb = 0; int cnt = 0;
+      if (rec < total_rec) {
+        int lo = 0, hi = p.segs;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (soff[mid] <= rec) lo = mid; else hi = mid; }
+        const long long at = (row * p.segs + lo) * p.cap_part + (rec - soff[lo]);
+        ix0 = __ldg(p.cand_i + at);
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.cand_s + at * 8));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.cand_s + at * 8) + 1);
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if ((unsigned long long)(ix0 + j) < (unsigned long long)p.N) {
+            if (sc[j] > pos_s + eps) ++definite;
+            else if (sc[j] > pos_s - eps) { amb |= 1u << j; ++cnt; }
+          }
+        }
+      }
+      const int incl = warp_incl_scan(cnt, lane);
+      int at_pos = m + incl - cnt;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (amb & (1u << j)) { if (at_pos < p.cap_band) band[at_pos] = (unsigned long long)(ix0 + j); ++at_pos; }
+      m += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    definite = __reduce_add_sync(0xffffffffu, definite);
+    if (definite >= p.k) { if (lane == 0) { p.out_count[row] = p.k; p.overflow[row] = 0; } return; }
+    if (m > p.cap_band) { if (lane == 0) p.overflow[row] = retry_flag; return; }
+    __syncwarp();
+    int greater = 0;
+    for (int t = lane; t < m; t += 32)
+      greater += (exact_score(qs, p.corpus + (long long)(unsigned int)band[t] * p.d, p.d) > pos) ? 1 : 0;
+    greater = __reduce_add_sync(0xffffffffu, greater);
+    if (lane == 0) { const int c = definite + greater; p.out_count[row] = c < p.k ? c : p.k; p.overflow[row] = 0; }
+    return;
+  }
+
+  // ---- TOPK / EXCLUDE: survivors (score >= filter threshold, real row) -> keys/sidx
+  int n = 0;
+  for (int rb = 0; rb < total_rec; rb += 32) {
+    const int rec = rb + lane;
+    float sc[8]; unsigned int ix0 = 0, keep = 0; int cnt = 0;
     if (rec < total_rec) {
-      int lo = 0, hi = parts;  // largest pt with seg_off[pt] <= rec
-      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_off[mid] <= rec) lo = mid; else hi = mid; }
-      const long long at = ((long long)row * parts + lo) * cap_part + (rec - seg_off[lo]);
-      ix0 = __ldg(cand_i + at);
-      const float4 s0 = __ldg(reinterpret_cast<const float4*>(cand_s + at * 8));
-      const float4 s1 = __ldg(reinterpret_cast<const float4*>(cand_s + at * 8) + 1);
+      int lo = 0, hi = p.segs;  // largest segment with soff[seg] <= rec
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (soff[mid] <= rec) lo = mid; else hi = mid; }
+      const long long at = (row * p.segs + lo) * p.cap_part + (rec - soff[lo]);
+      ix0 = __ldg(p.cand_i + at);
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.cand_s + at * 8));
+      const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.cand_s + at * 8) + 1);
       sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (sc[j] >= thr_row && (unsigned long long)(ix0 + j) < (unsigned long long)N) { keep |= 1u << j; ++cnt; }
+        if (sc[j] >= thr_row && (unsigned long long)(ix0 + j) < (unsigned long long)p.N) { keep |= 1u << j; ++cnt; }
     }
-    int incl = cnt;  // warp inclusive prefix sum of the per-lane survivor counts
+    const int incl = warp_incl_scan(cnt, lane);
+    int at_pos = n + incl - cnt;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane_id >= o) incl += v; }
-    const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
-    int base = 0;
-    if (lane_id == 0 && warp_total) base = atomicAdd(&n_sh, warp_total);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    int pos = base + incl - cnt;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (keep & (1u << j)) {
-        if (pos < CAND_CAP) { as[pos] = sc[j]; ai[pos] = ix0 + j; }
-        ++pos;
-      }
-    }
+    for (int j = 0; j < 8; ++j)
+      if (keep & (1u << j)) { if (at_pos < p.cap_keys) { keys[at_pos] = f2key(sc[j]); sidx[at_pos] = ix0 + j; } ++at_pos; }
+    n += __shfl_sync(0xffffffffu, incl, 31);
   }
-  __syncthreads();
-  const int n = n_sh;
-  if (n > CAND_CAP || n < k) {
-    if (tid == 0) overflow[row] = 1;
-    return;
-  }
-  if (tid == 0) m_sh = 0;
-  __syncthreads();
+  if (n > p.cap_keys) { if (lane == 0) p.overflow[row] = retry_flag; return; }
+  if (n < p.k) { if (lane == 0) p.overflow[row] = 2; return; }
+  __syncwarp();
   // tau = k-th best screening score; keep the survivors inside its error band
-  const unsigned int tau_key = block_kth_largest([&](int i) { return f2key(as[i]); }, n, k, hist, bcast);
-  const float lim = key2f(tau_key) - cut[row];
+  const unsigned int tau_key = warp_kth_largest_smem(keys, n, p.k, lane);
+  const float lim = key2f(tau_key) - p.cut[row];
   // Self-check that makes the threshold choice a pure performance matter: the whole band [lim, inf) must
   // lie above the filter threshold, otherwise survivors could be missing -> exact fallback.
-  if (!(lim >= thr[row]) || !(lim > -INFINITY)) {
-    if (tid == 0) overflow[row] = 1;
-    return;
-  }
-  for (int tb = 0; tb < n; tb += 256) {
-    const int t = tb + tid;
-    const bool keep = t < n && as[t] >= lim;
+  if (!(lim >= thr_row) || !(lim > -INFINITY)) { if (lane == 0) p.overflow[row] = 2; return; }
+  int m = 0;
+  for (int tb = 0; tb < n; tb += 32) {
+    const int t = tb + lane;
+    const bool keep = t < n && key2f(keys[t]) >= lim;
     const unsigned int vote = __ballot_sync(0xffffffffu, keep);
-    if (vote) {
-      int base = 0;
-      if ((tid & 31) == 0) base = atomicAdd(&m_sh, __popc(vote));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      const int pos = base + __popc(vote & ((1u << (tid & 31)) - 1u));
-      if (keep && pos < FIN_MAXM) ei[pos] = (long long)ai[t];
+    if (keep) { const int at_pos = m + __popc(vote & lt_mask); if (at_pos < p.cap_band) band[at_pos] = (unsigned long long)sidx[t]; }
+    m += __popc(vote);
+  }
+  if (m > p.cap_band) { if (lane == 0) p.overflow[row] = retry_flag; return; }  // band too crowded (massive ties)
+  __syncwarp();
+  // exact re-scoring; band[t] becomes the composite key (score desc, index asc) == larger is better
+  for (int t = lane; t < m; t += 32) {
+    const unsigned int idx = (unsigned int)band[t];
+    const float s = exact_score(qs, p.corpus + (long long)idx * p.d, p.d);
+    band[t] = ((unsigned long long)f2key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+  }
+  __syncwarp();
+  // rank sort: every lane ranks up to 4 own entries per sweep over the band (broadcast reads); ranks are unique
+  unsigned long long* srt = reinterpret_cast<unsigned long long*>(keys);  // EXCLUDE: the k best in order (keys/sidx are dead)
+  for (int t0 = 0; t0 < m; t0 += 128) {
+    unsigned long long mine[4]; int rank[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int t = t0 + u * 32 + lane; mine[u] = t < m ? band[t] : ~0ull; rank[u] = 0; }
+    for (int j = 0; j < m; ++j) {
+      const unsigned long long o = band[j];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rank[u] += (o > mine[u]) ? 1 : 0;
     }
-  }
-  __syncthreads();
-  const int m = m_sh;
-  if (m > FIN_MAXM) {  // band too crowded (massive ties): exact fallback
-    if (tid == 0) overflow[row] = 1;
-    return;
-  }
-  // exact re-scoring: the canonical sequential fmaf chain on the fp32 corpus
-  for (int t = tid; t < m; t += 256) {
-    const float* c = corpus + ei[t] * d;
-    float acc = 0.f;
-    if ((d & 31) == 0) {  // 8 loads (128 B) in flight per step, then the canonical chain on them
-      for (int kk = 0; kk < d; kk += 32) {
-        float4 cv[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) cv[u] = __ldg(reinterpret_cast<const float4*>(c + kk) + u);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          acc = fmaf(qs[kk + 4 * u], cv[u].x, acc); acc = fmaf(qs[kk + 4 * u + 1], cv[u].y, acc);
-          acc = fmaf(qs[kk + 4 * u + 2], cv[u].z, acc); acc = fmaf(qs[kk + 4 * u + 3], cv[u].w, acc);
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * 32 + lane;
+      if (t < m && rank[u] < p.k) {
+        if (MODE == FIN_TOPK) {
+          p.out_s[row * p.k + rank[u]] = key2f((unsigned int)(mine[u] >> 32));
+          p.out_i[row * p.k + rank[u]] = (long long)(0xFFFFFFFFu - (unsigned int)mine[u]) + p.index_offset;
+        } else {
+          srt[rank[u]] = mine[u];
         }
       }
-    } else if ((d & 3) == 0) {
-      for (int kk = 0; kk < d; kk += 4) {
-        float4 cv = __ldg(reinterpret_cast<const float4*>(c + kk));
-        acc = fmaf(qs[kk], cv.x, acc); acc = fmaf(qs[kk + 1], cv.y, acc);
-        acc = fmaf(qs[kk + 2], cv.z, acc); acc = fmaf(qs[kk + 3], cv.w, acc);
-      }
-    } else {
-      for (int kk = 0; kk < d; ++kk) acc = fmaf(qs[kk], __ldg(c + kk), acc);
     }
-    es[t] = acc;
   }
-  __syncthreads();
-  if (m <= 512) {
-    // rank sort: the band is small, so each thread ranks its entry against all others (broadcast reads, no
-    // barriers) and writes it straight to its output slot.  Ranks are unique: (score, index) is a total order.
-    for (int t = tid; t < m; t += 256) {
-      const float s_t = es[t]; const long long i_t = ei[t];
-      int rank = 0;
-      for (int j = 0; j < m; ++j) rank += better(es[j], ei[j], s_t, i_t) ? 1 : 0;
-      if (rank < k) {
-        out_s[(long long)row * k + rank] = s_t;
-        out_i[(long long)row * k + rank] = i_t + index_offset;
-      }
-    }
-    return;
+  if (MODE == FIN_EXCLUDE) {
+    __syncwarp();
+    exclude_rerank(srt, p.k, band, row, p, lane);   // band (>= k words) is dead after the ranking
   }
-  int P2 = 2; while (P2 < m) P2 <<= 1;
-  for (int t = m + tid; t < P2; t += 256) { es[t] = -INFINITY; ei[t] = LLONG_MAX; }
-  __syncthreads();
-  bitonic_sort_desc(es, ei, P2);  // (exact score desc, index asc)
-  for (int t = tid; t < k; t += 256) {
-    out_s[(long long)row * k + t] = es[t];
-    out_i[(long long)row * k + t] = ei[t] + index_offset;
-  }
+  if (lane == 0) p.overflow[row] = 0;
+}
+
+// EXCLUDE for the rows the exact fallback produced: tmp_[s,i] [Q, k] sorted lists -> the same re-ranking
+__global__ void __launch_bounds__(FW_WARPS * 32)
+tc_exclude_fallback_kernel(const FinParams p, const float* __restrict__ tmp_s, const long long* __restrict__ tmp_i,
+                           const unsigned int* __restrict__ was_fallback) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * FW_WARPS + warp;
+  if (row >= p.Q || was_fallback[row] != 2) return;
+  unsigned long long* srt = reinterpret_cast<unsigned long long*>(fsm) + (size_t)warp * 2 * p.k;
+  unsigned long long* akey = srt + p.k;
+  for (int t = lane; t < p.k; t += 32)
+    srt[t] = ((unsigned long long)f2key(tmp_s[row * p.k + t] + 0.0f) << 32) |
+             (unsigned long long)(0xFFFFFFFFu - (unsigned int)(tmp_i[row * p.k + t] - p.index_offset));
+  __syncwarp();
+  exclude_rerank(srt, p.k, akey, row, p, lane);
 }
 
 struct FallbackProvider {
@@ -605,22 +718,47 @@ struct FallbackProvider {
   float* qs;
   __device__ void begin(int row, void* extra) {
     qs = reinterpret_cast<float*>(extra);
-    if (overflow[row]) for (int t = threadIdx.x; t < d; t += blockDim.x) qs[t] = q[(long long)row * d + t];
+    if (overflow[row] == 2) for (int t = threadIdx.x; t < d; t += blockDim.x) qs[t] = q[(long long)row * d + t];
   }
-  __device__ long long count(int row) const { return overflow[row] ? N : 0; }
+  __device__ long long count(int row) const { return overflow[row] == 2 ? N : 0; }
   __device__ void get(int, long long t, float& s, long long& i) const {
     const float* c = corpus + t * d;
     float acc = 0.f;
     for (int kk = 0; kk < d; ++kk) acc = fmaf(qs[kk], __ldg(c + kk), acc);
-    s = acc; i = index_offset + t;
+    s = acc + 0.0f; i = index_offset + t;
   }
 };
+
+// COUNT for the rows that overflowed: exact #{candidates scoring above the positive}, clipped at k
+__global__ void __launch_bounds__(256)
+tc_count_fallback_kernel(const float* __restrict__ q, const float* __restrict__ corpus, long long N, int d, int k,
+                         const float* __restrict__ pos, const unsigned int* __restrict__ overflow, int* __restrict__ out_count) {
+  __shared__ float qs[128];
+  __shared__ int total;
+  const int row = blockIdx.x;
+  if (overflow[row] != 2) return;
+  for (int t = threadIdx.x; t < d; t += 256) qs[t] = q[(long long)row * d + t];
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  const float ps = pos[row];
+  int c = 0;
+  for (long long t = threadIdx.x; t < N; t += 256) {
+    const float* cr = corpus + t * d;
+    float acc = 0.f;
+    for (int kk = 0; kk < d; ++kk) acc = fmaf(qs[kk], __ldg(cr + kk), acc);
+    c += (acc + 0.0f > ps) ? 1 : 0;
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&total, c);
+  __syncthreads();
+  if (threadIdx.x == 0) out_count[row] = total < k ? total : k;
+}
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 // Optional per-stage device timing (bench.py's roofline leg): CUDA events recorded on the launch stream
-// around the stages of tfrs_topk_tc_f32.  Off by default; adds two event records per stage when on.
+// around the stages of the call.  Off by default; adds two event records per stage when on.
 struct Prof {
   bool on = false;
   static constexpr int MAXC = 512, STAGES_ = 4;  // 0 prep, 1 sample(+threshold), 2 filter, 3 finalize(+fallback)
@@ -641,39 +779,46 @@ static void prof_mark(cudaStream_t st, int stage) {
 
 struct Plan {
   int kb, stages; long long n_tiles; int nqb; long long Qp;
-  int stride, n_sample, n_bins, bins_ld, parts_sample, parts_full, cap_part;
+  int stride, n_sample, group, bins_per_part, n_bins, bins_ld, parts_sample, parts_full, cap_part;
   size_t smem;
   // workspace offsets
-  size_t o_qstats, o_qimg, o_margin, o_cut, o_thr, o_count, o_ovf, o_binmax, o_cand, total;
+  size_t o_qimg, o_margin, o_cut, o_thr, o_qexp, o_count, o_ovf, o_binmax, o_cand, o_tmp, total;
 };
 
 static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
-  if (d <= 0 || d > 256 || Q <= 0 || N <= 0 || k <= 0) return false;
+  if (d <= 0 || d > 128 || Q <= 0 || N <= 0 || k <= 0) return false;   // d > 128: smem budget (A blocks + ring) not laid out
   pl.kb = (d + KSLAB - 1) / KSLAB;
   pl.stages = pl.kb == 1 ? 6 : 4;
   pl.n_tiles = ceil_div(N, TILE_N);
   pl.nqb = (int)ceil_div(Q, QBLK);
   pl.Qp = (long long)pl.nqb * QBLK;
-  if (pl.kb > 2) return false;          // d > 128: smem budget (A blocks + ring) not laid out yet
-  if (k > 256 || N >= (1ll << 31)) return false;   // survivor capacity (CAND_CAP) is sized for ~4k + band entries per query
-  // sample every stride-th tile; keep at least 4k bins so the k-th largest bin max is a tight bound
+  if (k > 256 || N >= (1ll << 31)) return false;   // finalize capacities are sized for ~4k survivors + band entries per query
+  // sample every stride-th tile; keep at least 4k raw (tile, half) bins so the k-th largest bin max is a tight bound
   const long long full_tiles = N / TILE_N;  // the zero-padded last tile is never sampled (its 0 scores are not candidates)
   if (full_tiles < 1) return false;
   pl.stride = MAX_SAMPLE_STRIDE;
-  {
-    static int ov = -1;
-    if (ov < 0) { const char* e = getenv("TFRS_TC_SAMPLE_STRIDE"); ov = e ? atoi(e) : 0; }
-    if (ov >= 1 && ov <= 16) pl.stride = ov;
-  }
+#ifdef TFRS_DEBUG_SWITCHES
+  { static int ov = getenv("TFRS_TC_SAMPLE_STRIDE") ? atoi(getenv("TFRS_TC_SAMPLE_STRIDE")) : 0; if (ov >= 1 && ov <= 16) pl.stride = ov; }
+#endif
   while (pl.stride > 1 && 2 * ceil_div(full_tiles, pl.stride) < 4ll * k) pl.stride >>= 1;
   pl.n_sample = (int)ceil_div(full_tiles, pl.stride);
-  pl.n_bins = pl.n_sample * 2;
-  pl.bins_ld = (pl.n_bins + 3) / 4 * 4;
-  if (pl.n_bins < 4 * k) return false;  // too few bins for a useful threshold -> caller uses the exact path
+  if (2ll * pl.n_sample < 4ll * k) return false;  // too few bins for a useful threshold -> caller uses the exact path
   const int sms = sm_count();
   int parts = sms / pl.nqb; if (parts < 1) parts = 1; if (parts > FIN_MAX_PARTS / 2) parts = FIN_MAX_PARTS / 2;
   pl.parts_sample = parts < pl.n_sample ? parts : pl.n_sample;
   pl.parts_full = (long long)parts < pl.n_tiles ? parts : (int)pl.n_tiles;
+  {
+    // one bin = `group` consecutive sampled tiles x 64 columns of an epilogue thread; <= max(512, 4k) <= MAX_BINS per query
+    const int iters_max = (int)ceil_div(pl.n_sample, pl.parts_sample);
+    const int target = 4 * k > 512 ? 4 * k : 512;
+    int g = 1;
+    while ((long long)pl.parts_sample * ceil_div(iters_max, g) * 2 > target && g < iters_max) ++g;
+    pl.group = g;
+    pl.bins_per_part = (int)ceil_div(iters_max, g);
+    pl.n_bins = pl.parts_sample * pl.bins_per_part * 2;
+    if (pl.n_bins > MAX_BINS || pl.n_bins < 2 * k) return false;
+    pl.bins_ld = (pl.n_bins + 31) / 32 * 32;
+  }
   {
     int cp = 2 * CAND_CAP / (pl.parts_full * 2);  // octet records: (part, column-half) segments add up to ~2x the per-query capacity
     int p2 = 32; while (p2 * 2 <= cp && p2 < 512) p2 <<= 1;   // 32..512 records per segment
@@ -682,15 +827,16 @@ static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
   pl.smem = (size_t)(2 + pl.stages) * pl.kb * SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 1024); return r; };
-  pl.o_qstats = take(sizeof(SideStats));
   pl.o_qimg = take((size_t)pl.nqb * 2 * pl.kb * SLAB_BYTES);
   pl.o_margin = take((size_t)pl.Qp * 4);
   pl.o_cut = take((size_t)pl.Qp * 4);
   pl.o_thr = take((size_t)pl.Qp * 4);
+  pl.o_qexp = take((size_t)pl.Qp * 4);
   pl.o_count = take((size_t)pl.Qp * pl.parts_full * 2 * 4);
   pl.o_ovf = take((size_t)pl.Qp * 4);
   pl.o_binmax = take((size_t)pl.Qp * pl.bins_ld * 4);
   pl.o_cand = take((size_t)pl.Qp * pl.parts_full * 2 * pl.cap_part * (8 * 4 + 4));
+  pl.o_tmp = take((size_t)Q * k * 12);   // EXCLUDE: the exact fallback's [Q, k] lists before the re-ranking
   pl.total = o;
   return true;
 }
@@ -699,25 +845,10 @@ template <int KB, int STAGES>
 static int launch_scans(const Plan& pl, ScanParams sp, cudaStream_t st, int mode) {
   auto ks = tc_scan_kernel<KB, STAGES, MODE_SAMPLE>;
   auto kf = tc_scan_kernel<KB, STAGES, MODE_FILTER>;
-  static bool attr = false;
-  if (!attr) {
-    TFRS_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    TFRS_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    attr = true;
-  }
+  TFRS_DYN_SMEM(ks, (int)pl.smem);
+  TFRS_DYN_SMEM(kf, (int)pl.smem);
   if (mode == MODE_SAMPLE) {
     sp.parts = pl.parts_sample; sp.n_seq = pl.n_sample; sp.stride = pl.stride;
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("TFRS_TC_DEBUG_MODE"); dbg = e ? atoi(e) : 0; }
-    if (dbg == 2) {
-      auto k2 = tc_scan_kernel<KB, STAGES, MODE_DBG_LDONLY>;
-      TFRS_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-      k2<<<(unsigned)(pl.nqb * sp.parts), THREADS, pl.smem, st>>>(sp);
-    } else if (dbg == 3) {
-      auto k3 = tc_scan_kernel<KB, STAGES, MODE_DBG_NOLD>;
-      TFRS_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-      k3<<<(unsigned)(pl.nqb * sp.parts), THREADS, pl.smem, st>>>(sp);
-    } else
     ks<<<(unsigned)(pl.nqb * sp.parts), THREADS, pl.smem, st>>>(sp);
   } else {
     sp.parts = pl.parts_full; sp.n_seq = (int)pl.n_tiles; sp.stride = 1;
@@ -730,6 +861,111 @@ static int launch_scans(const Plan& pl, ScanParams sp, cudaStream_t st, int mode
 static int launch_scan_mode(const Plan& pl, const ScanParams& sp, cudaStream_t st, int mode) {
   if (pl.kb == 1) return launch_scans<1, 6>(pl, sp, st, mode);
   return launch_scans<2, 4>(pl, sp, st, mode);
+}
+
+template <int MODE>
+static int launch_finalize(FinParams fp, cudaStream_t st) {
+  auto kern = tc_finalize_kernel<MODE>;
+  const size_t big = FW_WARPS * fin_warp_bytes(FW_KEYS_BIG, FW_BAND_BIG);
+  TFRS_DYN_SMEM(kern, (int)big);
+  const unsigned grid = (unsigned)ceil_div(fp.Q, FW_WARPS);
+  fp.cap_keys = FW_KEYS_SMALL; fp.cap_band = FW_BAND_SMALL; fp.pass = 0;
+  kern<<<grid, FW_WARPS * 32, FW_WARPS * fin_warp_bytes(FW_KEYS_SMALL, FW_BAND_SMALL), st>>>(fp);
+  TFRS_LAUNCH_CHECK();
+  fp.cap_keys = FW_KEYS_BIG; fp.cap_band = FW_BAND_BIG; fp.pass = 1;   // rows that overflowed the first try (none, normally)
+  kern<<<grid, FW_WARPS * 32, big, st>>>(fp);
+  TFRS_LAUNCH_CHECK();
+  return TFRS_OK;
+}
+
+// One call = qprep -> sampled pass -> threshold -> filter pass -> finalize (+ retry, + exact fallback).
+struct Call {
+  int mode;  // FIN_*
+  const float* q; long long Q; const float* corpus; const void* index_buf; long long N; int d; int k; long long index_offset;
+  void* ws; size_t ws_bytes; cudaStream_t st;
+  float* out_s; long long* out_i;                                                       // TOPK / EXCLUDE
+  const long long* identifiers; const long long* exclusions; int n_excl; int k_out;     // EXCLUDE
+  const float* pos; int* out_count;                                                     // COUNT
+};
+
+static int run_call(const Call& c) {
+  Plan pl;
+  if (!make_plan(c.Q, c.N, c.d, c.k, pl)) {
+    set_error("topk_tc: shape (Q=%lld N=%lld d=%d k=%d) is outside the tensor-core path; use tfrs_topk_scan_f32",
+              c.Q, c.N, c.d, c.k);
+    return TFRS_ERR_UNSUPPORTED;
+  }
+  if (!c.ws || c.ws_bytes < pl.total + 16) { set_error("topk_tc: workspace too small (%zu < %zu)", c.ws_bytes, pl.total + 16); return TFRS_ERR_WORKSPACE_TOO_SMALL; }
+  cudaStream_t st = c.st;
+  unsigned char* w = (unsigned char*)(((uintptr_t)c.ws + 15) & ~(uintptr_t)15);
+  unsigned char* qimg = w + pl.o_qimg;
+  float* margin = (float*)(w + pl.o_margin);
+  float* cut = (float*)(w + pl.o_cut);
+  float* thr = (float*)(w + pl.o_thr);
+  int* qexp = (int*)(w + pl.o_qexp);
+  unsigned int* count = (unsigned int*)(w + pl.o_count);
+  unsigned int* ovf = (unsigned int*)(w + pl.o_ovf);
+  float* binmax = (float*)(w + pl.o_binmax);
+  float* cand_s = (float*)(w + pl.o_cand);
+  unsigned int* cand_i = (unsigned int*)(w + pl.o_cand + (size_t)pl.Qp * pl.parts_full * 2 * pl.cap_part * 32);
+  float* tmp_s = (float*)(w + pl.o_tmp);
+  long long* tmp_i = (long long*)(w + pl.o_tmp + align_up((size_t)c.Q * c.k * 4, 8));
+  const IndexHeader* hdr = (const IndexHeader*)c.index_buf;
+  const unsigned char* cimg = (const unsigned char*)c.index_buf + HEADER_BYTES;
+
+  prof_mark(st, 0);
+  // (0) per-row exponent, image and margins: one launch
+  tc_qprep_kernel<<<(unsigned)ceil_div(pl.Qp * 32, 256), 256, 0, st>>>(c.q, c.Q, pl.Qp, c.d, pl.kb, hdr, qimg, margin, cut, qexp);
+  TFRS_LAUNCH_CHECK();
+  ScanParams sp{};
+  sp.qimg = qimg; sp.cimg = cimg; sp.Q = c.Q; sp.N = c.N; sp.nqb = pl.nqb; sp.n_tiles = pl.n_tiles;
+  sp.binmax = binmax; sp.bins_ld = pl.bins_ld; sp.group = pl.group; sp.bins_per_part = pl.bins_per_part;
+  sp.thr = thr; sp.count = count; sp.cand_s = cand_s; sp.cand_i = cand_i; sp.cap_part = pl.cap_part;
+  sp.idesc = IDESC_F16_M128_N128;
+  prof_mark(st, 1);
+  // (1) sampled pass -> bin maxima -> k-th largest -> threshold
+  int rc = launch_scan_mode(pl, sp, st, MODE_SAMPLE);
+  if (rc) return rc;
+  if (pl.n_bins <= 512)
+    tc_threshold_kernel<16><<<(unsigned)ceil_div(c.Q * 32, 256), 256, 0, st>>>(binmax, pl.bins_ld, pl.n_bins, c.k, margin, thr, ovf, c.Q);
+  else
+    tc_threshold_kernel<32><<<(unsigned)ceil_div(c.Q * 32, 256), 256, 0, st>>>(binmax, pl.bins_ld, pl.n_bins, c.k, margin, thr, ovf, c.Q);
+  TFRS_LAUNCH_CHECK();
+  prof_mark(st, 2);
+  // (2) full pass with the fused threshold filter
+  rc = launch_scan_mode(pl, sp, st, MODE_FILTER);
+  if (rc) return rc;
+  prof_mark(st, 3);
+  // (3) exact re-scoring + final order (a warp per query); (4) exact fallback for the rows that asked for it
+  FinParams fp{};
+  fp.q = c.q; fp.corpus = c.corpus; fp.d = c.d; fp.k = c.k; fp.index_offset = c.index_offset; fp.N = c.N; fp.Q = c.Q;
+  fp.count = count; fp.cand_s = cand_s; fp.cand_i = cand_i; fp.segs = pl.parts_full * 2; fp.cap_part = pl.cap_part;
+  fp.cut = cut; fp.thr = thr; fp.overflow = ovf; fp.out_s = c.out_s; fp.out_i = c.out_i;
+  fp.identifiers = c.identifiers; fp.exclusions = c.exclusions; fp.n_excl = c.n_excl; fp.k_out = c.k_out;
+  fp.pos = c.pos; fp.qexp = qexp; fp.hdr = hdr; fp.out_count = c.out_count;
+  if (c.mode == FIN_TOPK) rc = launch_finalize<FIN_TOPK>(fp, st);
+  else if (c.mode == FIN_EXCLUDE) rc = launch_finalize<FIN_EXCLUDE>(fp, st);
+  else rc = launch_finalize<FIN_COUNT>(fp, st);
+  if (rc) return rc;
+  if (c.mode == FIN_COUNT) {
+    tc_count_fallback_kernel<<<(unsigned)c.Q, 256, 0, st>>>(c.q, c.corpus, c.N, c.d, c.k, c.pos, ovf, c.out_count);
+    TFRS_LAUNCH_CHECK();
+  } else {
+    // CTAs of non-flagged queries exit immediately
+    FallbackProvider prov{c.q, c.corpus, c.N, c.d, c.index_offset, ovf, nullptr};
+    int cap = rowselect_cap(c.k);
+    TFRS_DYN_SMEM(row_topk_kernel<FallbackProvider>, 64 * 1024);
+    float* fs = c.mode == FIN_TOPK ? c.out_s : tmp_s;
+    long long* fi = c.mode == FIN_TOPK ? c.out_i : tmp_i;
+    row_topk_kernel<FallbackProvider><<<(unsigned)c.Q, RS_THREADS, rowselect_smem(cap, (size_t)c.d * 4), st>>>(prov, c.k, cap, fs, fi, c.k);
+    TFRS_LAUNCH_CHECK();
+    if (c.mode == FIN_EXCLUDE) {
+      tc_exclude_fallback_kernel<<<(unsigned)ceil_div(c.Q, FW_WARPS), FW_WARPS * 32, (size_t)FW_WARPS * 2 * c.k * 8, st>>>(fp, tmp_s, tmp_i, ovf);
+      TFRS_LAUNCH_CHECK();
+    }
+  }
+  prof_mark(st, 4);
+  return TFRS_OK;
 }
 
 }  // namespace tc
@@ -756,13 +992,16 @@ extern "C" int tfrs_index_build(const float* corpus, int64_t N, int d, void* ind
   header_kernel<<<1, 1, 0, st>>>(reinterpret_cast<IndexHeader*>(index_buf), h);
   TFRS_LAUNCH_CHECK();
   SideStats* cst = &reinterpret_cast<IndexHeader*>(index_buf)->st;
-  side_stats_kernel<<<(unsigned)(148 * 8), 256, 0, st>>>(corpus, N, d, cst, nullptr);
+  const unsigned sgrid = (unsigned)(sm_count() * 8);
+  corpus_stats_kernel<0><<<sgrid, 256, 0, st>>>(corpus, N, d, cst);
   TFRS_LAUNCH_CHECK();
-  side_exp_kernel<<<1, 1, 0, st>>>(cst, fp16_target());
+  side_exp_kernel<<<1, 1, 0, st>>>(cst);
+  TFRS_LAUNCH_CHECK();
+  corpus_stats_kernel<1><<<sgrid, 256, 0, st>>>(corpus, N, d, cst);
   TFRS_LAUNCH_CHECK();
   long long chunks = h.n_tiles * TILE_N * (long long)h.kb * 8;
   unsigned blocks = (unsigned)(ceil_div(chunks, 256) < (1 << 20) ? ceil_div(chunks, 256) : (1 << 20));
-  tile_image_kernel<<<blocks, 256, 0, st>>>(corpus, N, d, h.kb, h.n_tiles, cst, use_bf16(), (unsigned char*)index_buf + HEADER_BYTES);
+  tile_image_kernel<<<blocks, 256, 0, st>>>(corpus, N, d, h.kb, h.n_tiles, cst, (unsigned char*)index_buf + HEADER_BYTES);
   TFRS_LAUNCH_CHECK();
   return TFRS_OK;
 }
@@ -770,7 +1009,7 @@ extern "C" int tfrs_index_build(const float* corpus, int64_t N, int d, void* ind
 extern "C" size_t tfrs_topk_tc_workspace_bytes(int64_t Q, int64_t N, int d, int k) {
   Plan pl;
   if (!make_plan(Q, N, d, k, pl)) return 0;
-  return pl.total;
+  return pl.total + 16;
 }
 
 extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, const void* index_buf, int64_t N, int d,
@@ -778,83 +1017,36 @@ extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, 
                                 void* stream) {
   TFRS_CHECK_ARG(q && corpus && index_buf && out_scores && out_idx, "topk_tc: NULL pointer");
   TFRS_CHECK_ARG(k <= N, "input must have at least k columns. Had %lld, needed %d", (long long)N, k);
-  Plan pl;
-  if (!make_plan(Q, N, d, k, pl)) {
-    set_error("topk_tc: shape (Q=%lld N=%lld d=%d k=%d) is outside the tensor-core path; use tfrs_topk_scan_f32",
-              (long long)Q, (long long)N, d, k);
-    return TFRS_ERR_UNSUPPORTED;
-  }
-  if (!ws || ws_bytes < pl.total) { set_error("topk_tc: workspace too small (%zu < %zu)", ws_bytes, pl.total); return TFRS_ERR_WORKSPACE_TOO_SMALL; }
-  cudaStream_t st = (cudaStream_t)stream;
-  unsigned char* w = (unsigned char*)(((uintptr_t)ws + 15) & ~(uintptr_t)15);
-  unsigned char* qimg = w + pl.o_qimg;
-  float* margin = (float*)(w + pl.o_margin);
-  float* cut = (float*)(w + pl.o_cut);
-  float* thr = (float*)(w + pl.o_thr);
-  unsigned int* count = (unsigned int*)(w + pl.o_count);
-  unsigned int* ovf = (unsigned int*)(w + pl.o_ovf);
-  float* binmax = (float*)(w + pl.o_binmax);
-  float* cand_s = (float*)(w + pl.o_cand);
-  unsigned int* cand_i = (unsigned int*)(w + pl.o_cand + (size_t)pl.Qp * pl.parts_full * 2 * pl.cap_part * 32);
-  const IndexHeader* hdr = (const IndexHeader*)index_buf;
-  const unsigned char* cimg = (const unsigned char*)index_buf + HEADER_BYTES;
+  Call c{};
+  c.mode = FIN_TOPK; c.q = q; c.Q = Q; c.corpus = corpus; c.index_buf = index_buf; c.N = N; c.d = d; c.k = k;
+  c.index_offset = index_offset; c.ws = ws; c.ws_bytes = ws_bytes; c.st = (cudaStream_t)stream;
+  c.out_s = out_scores; c.out_i = (long long*)out_idx;
+  return run_call(c);
+}
 
-  prof_mark(st, 0);
-  // (0) query statistics, image and margins
-  {
-    SideStats* qst = (SideStats*)(w + pl.o_qstats);
-    TFRS_CUDA(cudaMemsetAsync(qst, 0, sizeof(SideStats), st));
-    side_stats_kernel<<<(unsigned)ceil_div(Q * 32, 256), 256, 0, st>>>(q, Q, d, qst, margin /* scratch: |q|^2 per row */);
-    TFRS_LAUNCH_CHECK();
-    side_exp_kernel<<<1, 1, 0, st>>>(qst, fp16_target());
-    TFRS_LAUNCH_CHECK();
-    long long chunks = (long long)pl.nqb * 2 * TILE_N * pl.kb * 8;
-    tile_image_kernel<<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(q, Q, d, pl.kb, (long long)pl.nqb * 2, qst, use_bf16(), qimg);
-    TFRS_LAUNCH_CHECK();
-    qmargin_kernel<<<(unsigned)ceil_div(pl.Qp, 256), 256, 0, st>>>(Q, pl.Qp, hdr, qst, use_bf16(), margin, cut);
-    TFRS_LAUNCH_CHECK();
-  }
-  ScanParams sp{};
-  sp.qimg = qimg; sp.cimg = cimg; sp.Q = Q; sp.N = N; sp.nqb = pl.nqb; sp.n_tiles = pl.n_tiles;
-  sp.binmax = binmax; sp.bins_ld = pl.bins_ld; sp.thr = thr; sp.count = count; sp.cand_s = cand_s; sp.cand_i = cand_i; sp.cap_part = pl.cap_part;
-  sp.idesc = IDESC_F16_M128_N128 | (use_bf16() ? ((1u << 7) | (1u << 10)) : 0u);
-  prof_mark(st, 1);
-  // (1) sampled pass -> bin maxima -> k-th largest -> threshold
-  int rc = launch_scan_mode(pl, sp, st, MODE_SAMPLE);
-  if (rc) return rc;
-  {
-    size_t smem = pl.n_bins <= THR_SMEM_BINS ? (size_t)pl.n_bins * 4 : 0;
-    static bool attr = false;
-    if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(tc_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, THR_SMEM_BINS * 4)); attr = true; }
-    tc_threshold_kernel<<<(unsigned)Q, 256, smem, st>>>(binmax, pl.bins_ld, pl.n_bins, k, margin, thr, ovf);
-  }
-  TFRS_LAUNCH_CHECK();
-  prof_mark(st, 2);
-  // (2) full pass with the fused threshold filter
-  rc = launch_scan_mode(pl, sp, st, MODE_FILTER);
-  if (rc) return rc;
-  prof_mark(st, 3);
-  // (3) exact re-scoring + final order
-  {
-    size_t smem = (size_t)FIN_MAXM * 12 + (size_t)CAND_CAP * 8 + (size_t)d * 4 + 16;
-    static bool attr = false;
-    if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
-    tc_finalize_kernel<<<(unsigned)Q, 256, smem, st>>>(q, corpus, d, k, index_offset, count, cand_s, cand_i, pl.parts_full * 2, pl.cap_part,
-                                                     cut, thr, N, ovf, out_scores, (long long*)out_idx);
-    TFRS_LAUNCH_CHECK();
-  }
-  // (4) exact fallback for overflowed queries (CTAs of non-flagged queries exit immediately)
-  {
-    FallbackProvider fp{q, corpus, N, d, index_offset, ovf, nullptr};
-    int cap = rowselect_cap(k);
-    static bool attr = false;
-    if (!attr) { TFRS_CUDA(cudaFuncSetAttribute(row_topk_kernel<FallbackProvider>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
-    row_topk_kernel<FallbackProvider><<<(unsigned)Q, RS_THREADS, rowselect_smem(cap, (size_t)d * 4), st>>>(
-        fp, k, cap, out_scores, (long long*)out_idx, k);
-    TFRS_LAUNCH_CHECK();
-  }
-  prof_mark(st, 4);
-  return TFRS_OK;
+extern "C" int tfrs_topk_tc_exclude_f32(const float* q, int64_t Q, const float* corpus, const void* index_buf, int64_t N, int d,
+                                        int k, int64_t index_offset, const int64_t* identifiers, const int64_t* exclusions,
+                                        int n_excl, float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes, void* stream) {
+  TFRS_CHECK_ARG(q && corpus && index_buf && out_scores && out_idx && exclusions && n_excl > 0, "topk_tc_exclude: bad argument");
+  TFRS_CHECK_ARG((long long)k + n_excl <= N, "input must have at least k columns. Had %lld, needed %d", (long long)N, k + n_excl);
+  Call c{};
+  c.mode = FIN_EXCLUDE; c.q = q; c.Q = Q; c.corpus = corpus; c.index_buf = index_buf; c.N = N; c.d = d; c.k = k + n_excl;
+  c.index_offset = index_offset; c.ws = ws; c.ws_bytes = ws_bytes; c.st = (cudaStream_t)stream;
+  c.out_s = out_scores; c.out_i = (long long*)out_idx;
+  c.identifiers = (const long long*)identifiers; c.exclusions = (const long long*)exclusions; c.n_excl = n_excl; c.k_out = k;
+  return run_call(c);
+}
+
+extern "C" int tfrs_topk_tc_count_f32(const float* q, int64_t Q, const float* corpus, const void* index_buf, int64_t N, int d,
+                                      int k, const float* positive_scores, int32_t* out_count, void* ws, size_t ws_bytes,
+                                      void* stream) {
+  TFRS_CHECK_ARG(q && corpus && index_buf && positive_scores && out_count, "topk_tc_count: NULL pointer");
+  TFRS_CHECK_ARG(k <= N, "input must have at least k columns. Had %lld, needed %d", (long long)N, k);
+  Call c{};
+  c.mode = FIN_COUNT; c.q = q; c.Q = Q; c.corpus = corpus; c.index_buf = index_buf; c.N = N; c.d = d; c.k = k;
+  c.ws = ws; c.ws_bytes = ws_bytes; c.st = (cudaStream_t)stream;
+  c.pos = positive_scores; c.out_count = out_count;
+  return run_call(c);
 }
 
 // Debug/test introspection: where the per-query survivor counts / fallback flags of the last call live

@@ -51,7 +51,12 @@ def _exclude(scores: Tensor, identifiers, exclude, k: int):
   """Removes a subset of candidates from top K candidates (factorized_top_k.py:83-115).
 
   Scores of excluded identifiers are lowered by 1e5, the top min(k, cols) of the adjusted scores are
-  taken, and the ORIGINAL scores / identifiers at those positions are returned."""
+  taken, and the ORIGINAL scores / identifiers at those positions are returned.  Integer tensor identifiers run
+  in one kernel (`tfrs_topk_exclude_rerank_f32`); other identifier types (e.g. NumPy strings) are matched on the
+  host and ranked by the merge kernel."""
+  if isinstance(identifiers, torch.Tensor) and not identifiers.dtype.is_floating_point and identifiers.is_cuda:
+    out_s, out_i = ops.exclude_rerank(scores, identifiers, exclude, k)  # the identifier matrix is its own "index"
+    return out_s, out_i.to(identifiers.dtype)
   if isinstance(identifiers, torch.Tensor):
     exclude_t = exclude if isinstance(exclude, torch.Tensor) else torch.as_tensor(np.asarray(exclude))
     isin = (identifiers.unsqueeze(-1) == exclude_t.to(identifiers.device).unsqueeze(1)).any(-1)
@@ -92,24 +97,35 @@ def shard_bounds(num_rows: int, rank: int, world: int) -> Tuple[int, int]:
   return lo, min(lo + per, num_rows)
 
 
-def allgather_topk(scores: Tensor, idx: Tensor, k: int, group=None) -> Tuple[Tensor, Tensor]:
-  """The single collective of the sharded scan: one all-gather of every rank's packed [Q,k] (score, index)
-  list -> ([world,Q,k] f32, [world,Q,k] i64).  Short shards are padded with (-inf, INT64_MAX)."""
-  import torch.distributed as dist
-  world = dist.get_world_size(group)
-  if scores.shape[1] < k:
-    pad = k - scores.shape[1]
-    scores = torch.cat([scores, torch.full((scores.shape[0], pad), float("-inf"), device=scores.device)], 1)
-    idx = torch.cat([idx, torch.full((idx.shape[0], pad), torch.iinfo(torch.int64).max, device=idx.device,
-                                     dtype=torch.int64)], 1)
-  # scores ride as raw bits in an int64 lane next to the indices: one buffer, one collective
-  packed = torch.stack([scores.contiguous().view(torch.int32).to(torch.int64), idx.to(torch.int64)], 0).contiguous()
-  flat = torch.empty((world * 2,) + tuple(packed.shape[1:]), dtype=torch.int64, device=packed.device)
-  dist.all_gather_into_tensor(flat, packed, group=group)
-  gathered = flat.view((world, 2) + tuple(packed.shape[1:]))
-  all_s = gathered[:, 0].to(torch.int32).view(torch.float32).contiguous()
-  all_i = gathered[:, 1].contiguous()
-  return all_s, all_i
+class ShardComm:
+  """The C-ABI communicator of the sharded scan (`tfrs_comm_*`, include/tfrs_b200.h).  torch.distributed (any backend)
+  is used ONCE, as the control plane that hands rank 0's 128-byte NCCL id to the other ranks; every collective on the
+  data path is issued by libtfrs_b200.so itself."""
+
+  def __init__(self, group=None):
+    import ctypes
+    import torch.distributed as dist
+    from .. import _ffi
+    self.rank = dist.get_rank(group)
+    self.world = dist.get_world_size(group)
+    uid = (ctypes.c_char * 128)()
+    if self.rank == 0:
+      _ffi.check(_ffi.lib().tfrs_comm_unique_id(uid), "comm_unique_id")
+    box = [bytes(uid)]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    self._handle = ctypes.c_void_p()
+    raw = (ctypes.c_char * 128).from_buffer_copy(box[0])
+    _ffi.check(_ffi.lib().tfrs_comm_create(ctypes.byref(self._handle), self.rank, self.world, raw), "comm_create")
+
+  @property
+  def handle(self):
+    return self._handle
+
+  def close(self):
+    from .. import _ffi
+    if self._handle:
+      _ffi.lib().tfrs_comm_destroy(self._handle)
+      self._handle = None
 
 
 class TopK(torch.nn.Module, abc.ABC):
@@ -165,11 +181,70 @@ class TopK(torch.nn.Module, abc.ABC):
     return ops.scores(queries, candidates)
 
 
+class _HostStager:
+  """Pinned, double-buffered host->device staging for corpora that do not live in HBM: chunk i+1 is copied
+  (cudaMemcpyAsync from pinned memory on a side stream) while chunk i is being scanned."""
+
+  def __init__(self, device: torch.device, rows: int, d: int):
+    self.device, self.rows, self.d = device, rows, d
+    self.pinned = [torch.empty((rows, d), dtype=torch.float32).pin_memory() for _ in range(2)]
+    self.dev = [torch.empty((rows, d), dtype=torch.float32, device=device) for _ in range(2)]
+    self.copy_stream = torch.cuda.Stream(device=device)
+    self.h2d_done = [torch.cuda.Event(), torch.cuda.Event()]     # the pinned buffer may be refilled after this
+    self.scan_done = [torch.cuda.Event(), torch.cuda.Event()]    # the device buffer may be overwritten after this
+    self.used = [False, False]
+    self.slot = 0
+    self.h2d_bytes = 0
+
+  def stage(self, pieces) -> Tensor:
+    """pieces: host/device [r_i, d] tensors of one chunk -> one device tensor [sum r_i, d] (valid on the CURRENT stream)."""
+    s = self.slot
+    self.slot ^= 1
+    n = sum(int(p.shape[0]) for p in pieces)
+    if self.used[s]:
+      self.h2d_done[s].synchronize()            # host: the previous copy out of pinned[s] has finished
+      self.copy_stream.wait_event(self.scan_done[s])   # device: the scan that read dev[s] has finished
+    at = 0
+    for p in pieces:                              # host pieces -> one pinned run; device pieces copied on the side stream
+      r = int(p.shape[0])
+      if not p.is_cuda:
+        self.pinned[s][at:at + r].copy_(p)
+      at += r
+    with torch.cuda.stream(self.copy_stream):
+      at = 0
+      run0 = None
+      for p in pieces + [None]:
+        host = p is not None and not p.is_cuda
+        if host and run0 is None:
+          run0 = at
+        if (not host) and run0 is not None:       # flush the contiguous host run [run0, at)
+          self.dev[s][run0:at].copy_(self.pinned[s][run0:at], non_blocking=True)
+          self.h2d_bytes += (at - run0) * self.d * 4
+          run0 = None
+        if p is not None:
+          if p.is_cuda:
+            self.dev[s][at:at + int(p.shape[0])].copy_(p, non_blocking=True)
+          at += int(p.shape[0])
+      self.h2d_done[s].record(self.copy_stream)
+    torch.cuda.current_stream().wait_event(self.h2d_done[s])
+    self.used[s] = True
+    self._last = s
+    return self.dev[s][:n]
+
+  def release(self) -> None:
+    """Call after enqueuing the scan of the chunk returned by the last stage()."""
+    self.scan_done[self._last].record(torch.cuda.current_stream())
+
+
 class Streaming(TopK):
   """Retrieves K highest scoring items and their ids from a large dataset (factorized_top_k.py:336-512).
 
-  Each dataset batch is scanned on the GPU and merged into the carried [Q,k] state by the same kernel
-  (state entries compete with their own indices), so the result equals BruteForce's."""
+  Dataset batches (the README uses 128 rows) are coalesced into chunks of `_coalesce_rows`; every chunk is scanned by
+  the tcgen05 screening kernel (its fp16 image is built on the fly) with the running row counter as index offset and
+  merged into the carried [Q,k] state -- ties resolve to the lower running index, i.e. state first (:462-463), so the
+  result equals BruteForce's.  Batches that live in host memory are staged through pinned double buffers so the copy of
+  chunk i+1 overlaps the scan of chunk i (corpora larger than HBM).  Small chunks use the exact CUDA-core scan, which
+  takes the carried state directly."""
 
   def __init__(self, query_model: Optional[torch.nn.Module] = None, k: int = 10,
                handle_incomplete_batches: bool = True, num_parallel_calls: Optional[int] = None,
@@ -180,7 +255,9 @@ class Streaming(TopK):
     self._handle_incomplete_batches = handle_incomplete_batches
     self._num_parallel_calls = num_parallel_calls
     self._sorted = sorted_order
-    self._coalesce_rows = 65536
+    self._coalesce_rows = 262144
+    self.use_tensor_cores = True
+    self._stager = None
     self.register_buffer("_counter", torch.zeros((), dtype=torch.int32), persistent=False)
 
   def index_from_dataset(self, candidates) -> "TopK":
@@ -193,28 +270,50 @@ class Streaming(TopK):
     raise NotImplementedError("The streaming top k class only accepts datasets. "
                               "Please call `index_from_dataset` instead.")
 
-  def call(self, queries, k: Optional[int] = None):
-    k = k if k is not None else self._k
+  def _scan_chunk(self, queries: Tensor, emb: Tensor, k: int, counter: int, state):
+    """state + top-k of one chunk -> new state."""
+    rows, d = int(emb.shape[0]), int(emb.shape[1])
+    if (self.use_tensor_cores and rows >= ops.TC_MIN_N and d <= 128 and state[0].shape[1] in (0, k) and
+        ops.tc_supported(queries.shape[0], rows, d, k)):
+      image = ops.index_build(emb, reuse_slot="stream_index")
+      s, i = ops.topk_tc(queries, emb, image, k, index_offset=counter)
+      if state[0].shape[1] == 0:
+        return s, i
+      return ops.topk_merge_sorted(torch.stack([state[0], s]), torch.stack([state[1], i]), k)
+    # the exact scan kernel takes the carried state and numbers the rows with the running counter
+    # (enumerate_rows, :474-485)
+    return ops.topk_scan(queries, emb, k, index_offset=counter, state=state)
+
+  def _run(self, queries, k: int):
+    """-> (scores [Q,k'], running row indices [Q,k'] i64, identifier chunks or None)."""
     if self._candidates is None:
       raise ValueError("The `index` method must be called first to create the retrieval index.")
     if self.query_model is not None:
       queries = self.query_model(queries)
+    queries = ops.f32c(queries, "queries")
     Q = queries.shape[0]
     state = (torch.zeros((Q, 0), dtype=torch.float32, device=queries.device),
              torch.zeros((Q, 0), dtype=torch.int64, device=queries.device))
     counter = 0
     id_chunks = []
-    has_ids = False
     pending, pending_rows = [], 0
 
     def flush():
       nonlocal state, counter, pending, pending_rows
       if not pending:
         return
-      emb = pending[0] if len(pending) == 1 else torch.cat(pending, 0)
-      # the scan kernel takes the carried state and numbers the rows with the running counter
-      # (enumerate_rows, :474-485); ties resolve to the lower running index == state first (:462-463).
-      state = ops.topk_scan(queries, emb, k, index_offset=counter, state=state)
+      staged = any(not p.is_cuda for p in pending)
+      if staged:   # host-resident corpus: pinned double-buffered H2D, one chunk ahead of the scan
+        d = int(pending[0].shape[1])
+        st = self._stager
+        if st is None or st.d != d or st.device != queries.device or st.rows < pending_rows:
+          st = self._stager = _HostStager(queries.device, max(self._coalesce_rows + 65536, pending_rows), d)
+        emb = st.stage([p if p.is_cuda else p.to(torch.float32) for p in pending])
+      else:
+        emb = pending[0] if len(pending) == 1 else torch.cat(pending, 0)
+      state = self._scan_chunk(queries, ops.f32c(emb, "candidates"), k, counter, state)
+      if staged:
+        self._stager.release()
       counter += int(emb.shape[0])
       pending, pending_rows = [], 0
 
@@ -222,23 +321,39 @@ class Streaming(TopK):
       _check_candidates_with_identifiers(el)
       if isinstance(el, tuple):
         ids, emb = el
-        has_ids = True
         id_chunks.append(ids)
       else:
         emb = el
       if not self._handle_incomplete_batches and emb.shape[0] < k:
         raise _wrap_batch_too_small_error(k)
-      # Dataset batches are tiny (README uses 128): coalesce them into >= 64K-row scans.  The result is the
-      # same as merging per batch -- indices are the running row numbers either way.
+      # Dataset batches are tiny (README uses 128): coalesce them.  The result is the same as merging per
+      # batch -- indices are the running row numbers either way.
       pending.append(emb); pending_rows += int(emb.shape[0])
       if pending_rows >= self._coalesce_rows:
         flush()
     flush()
     self._counter.fill_(counter)
-    scores, idx = state
-    if has_ids:
+    return state[0], state[1], (id_chunks if id_chunks else None)
+
+  def call(self, queries, k: Optional[int] = None):
+    k = k if k is not None else self._k
+    scores, idx, id_chunks = self._run(queries, k)
+    if id_chunks is not None:
       return scores, _gather_identifiers(_concat_ids(id_chunks), idx)
     return scores, idx.to(torch.int32)
+
+  def query_with_exclusions(self, queries, exclusions, k: Optional[int] = None):
+    """:242-288 -- scan for k + E with the carried state, then `_exclude` in one kernel (integer identifiers)."""
+    k = k if k is not None else self._k
+    scores, idx, id_chunks = self._run(queries, k + exclusions.shape[1])
+    if id_chunks is None:
+      s, i = ops.exclude_rerank(scores, idx, exclusions, k)
+      return s, i.to(torch.int32)
+    ids = _concat_ids(id_chunks)
+    if isinstance(ids, torch.Tensor) and not ids.dtype.is_floating_point and ids.is_cuda:
+      s, i = ops.exclude_rerank(scores, idx, exclusions, k, identifiers=ids)
+      return s, ids[i]
+    return _exclude(scores, _gather_identifiers(ids, idx), exclude=exclusions, k=k)
 
   def is_exact(self) -> bool:
     return True
@@ -247,10 +362,10 @@ class Streaming(TopK):
 class BruteForce(TopK):
   """Brute force retrieval (factorized_top_k.py:515-610).
 
-  `index` keeps the fp32 corpus and, for large corpora, builds the bf16 tensor-core screening image;
+  `index` keeps the fp32 corpus and, for large corpora, builds the fp16 tensor-core screening image;
   `call` returns exactly the top-k of the fp32 scores either way.  `index_shard` adds the row-sharded
-  multi-GPU mode: every rank scans its contiguous shard and one all-gather of the per-shard (score,
-  index) lists is merged on every rank."""
+  multi-GPU mode: every rank scans its contiguous shard, ONE all-gather of the per-shard (score, index)
+  lists (issued by libtfrs_b200.so through its own NCCL communicator) is merged on every rank."""
 
   def __init__(self, query_model: Optional[torch.nn.Module] = None, k: int = 10, name: Optional[Text] = None):
     super().__init__(k=k, name=name)
@@ -258,7 +373,7 @@ class BruteForce(TopK):
     self._candidates = None
     self._identifiers = None
     self._tc_index = None
-    self._shard = None  # (global_offset, group)
+    self._shard = None  # (global_offset, ShardComm)
     self.use_tensor_cores = True
 
   def index(self, candidates: Tensor, identifiers: Optional[Identifiers] = None) -> "BruteForce":
@@ -280,25 +395,33 @@ class BruteForce(TopK):
     return self
 
   def index_shard(self, local_candidates: Tensor, global_offset: int, identifiers: Optional[Identifiers] = None,
-                  group=None) -> "BruteForce":
+                  group=None, comm: Optional[ShardComm] = None, copy: bool = True) -> "BruteForce":
     """Row-sharded index: this rank owns corpus rows [global_offset, global_offset + len(local_candidates)).
-    `identifiers`, when given, covers the WHOLE corpus (it is only used to map the merged indices)."""
+    `identifiers`, when given, covers the WHOLE corpus (it is only used to map the merged indices).  Collective:
+    every rank of `group` must call it (the C-ABI communicator is created here unless `comm` is passed)."""
     if local_candidates.dim() != 2:
       raise ValueError(f"The candidates tensor must be 2D (got {tuple(local_candidates.shape)}).")
-    self._set_index(ops.f32c(local_candidates, "candidates").detach(), identifiers)
-    self._shard = (int(global_offset), group)
+    self._set_index(ops.f32c(local_candidates, "candidates").detach(), identifiers, copy=copy)
+    self._shard = (int(global_offset), comm if comm is not None else ShardComm(group))
     return self
 
-  def _set_index(self, cands: Tensor, identifiers) -> None:
+  def _set_index(self, cands: Tensor, identifiers, copy: bool = True) -> None:
+    # the index OWNS its corpus (the reference copies with .assign(), :571-580): later in-place updates of the
+    # caller's tensor (e.g. an Embedding.weight that keeps training) must not desynchronise the fp32 rows from
+    # the fp16 screening image built from them
+    if copy:
+      cands = cands.clone()
     self._candidates = cands
     self._identifiers = identifiers
     self._tc_index = None
     if self.use_tensor_cores and cands.shape[0] >= ops.TC_MIN_N and cands.shape[1] <= 128:
       self._tc_index = ops.index_build(cands)
 
+  def _tc_ok(self, Q: int, k: int) -> bool:
+    return self._tc_index is not None and ops.tc_supported(Q, self._candidates.shape[0], self._candidates.shape[1], k)
+
   def _local_topk(self, queries: Tensor, k: int, offset: int, out=None):
-    if self._tc_index is not None and ops.tc_supported(queries.shape[0], self._candidates.shape[0],
-                                                       self._candidates.shape[1], k):
+    if self._tc_ok(queries.shape[0], k):
       return ops.topk_tc(queries, self._candidates, self._tc_index, k, index_offset=offset, out=out)
     return ops.topk_scan(queries, self._candidates, k, index_offset=offset, out=out)
 
@@ -319,27 +442,28 @@ class BruteForce(TopK):
       return values, indices.to(torch.int32)  # default identifiers = range(N) int32 (:544-545)
     return values, _gather_identifiers(self._identifiers, indices)
 
+  def query_with_exclusions(self, queries, exclusions, k: Optional[int] = None):
+    """:242-288.  On the tensor-core path the exclusion test runs inside the scan's finalize step
+    (`tfrs_topk_tc_exclude_f32`): no [Q, k+E] list round trip, no eager ops."""
+    k = k if k is not None else self._k
+    E = int(exclusions.shape[1])
+    ids = self._identifiers
+    int_ids = ids is None or (isinstance(ids, torch.Tensor) and not ids.dtype.is_floating_point)
+    if (self._candidates is not None and self._shard is None and int_ids and E > 0 and
+        k + E <= self._candidates.shape[0]):
+      q = self.query_model(queries) if self.query_model is not None else queries
+      if self._tc_ok(q.shape[0], k + E):
+        s, i = ops.topk_tc_exclude(q, self._candidates, self._tc_index, k, exclusions, identifiers=ids)
+        if ids is None:
+          return s, i.to(torch.int32)
+        return s, _gather_identifiers(ids, i)
+    return super().query_with_exclusions(queries, exclusions, k)
+
   def _sharded_topk(self, queries: Tensor, k: int):
-    """Local scan -> ONE all-gather of every rank's packed [scores | indices] block -> merge kernel reading the
-    receive buffer in place.  The local scan writes straight into the send block (no packing kernels)."""
-    import torch.distributed as dist
-    offset, group = self._shard
-    world = dist.get_world_size(group)
-    Q = queries.shape[0]
-    k_local = min(k, self._candidates.shape[0])
-    if k_local < k:  # a shard smaller than k: rectangular lists via the generic (padding) path
-      s, i = self._local_topk(queries, k_local, offset)
-      all_s, all_i = allgather_topk(s, i, k, group)
-      return ops.topk_merge(all_s, all_i, k)
-    idx_off = (Q * k * 4 + 7) // 8 * 8
-    block = idx_off + Q * k * 8
-    send = torch.empty(block, dtype=torch.uint8, device=queries.device)
-    out_s = send[:Q * k * 4].view(torch.float32).view(Q, k)
-    out_i = send[idx_off:].view(torch.int64).view(Q, k)
-    self._local_topk(queries, k, offset, out=(out_s, out_i))
-    recv = torch.empty(world * block, dtype=torch.uint8, device=queries.device)
-    dist.all_gather_into_tensor(recv, send, group=group)
-    return ops.topk_merge_packed(recv, world, Q, k, k, idx_off, block)
+    """The whole sharded call is ONE C-ABI entry point (`tfrs_topk_sharded_f32`): local scan written straight into the
+    send block -> one NCCL all-gather -> sorted-list merge reading the receive buffer in place."""
+    offset, comm = self._shard
+    return ops.topk_sharded(comm, queries, self._candidates, self._tc_index, k, offset)
 
   def is_exact(self) -> bool:
     return True

@@ -92,14 +92,15 @@ def topk_scan(q: torch.Tensor, corpus: torch.Tensor, k: int, index_offset: int =
   return out_s[:, :k_out], out_i[:, :k_out]
 
 
-def index_build(corpus: torch.Tensor) -> torch.Tensor:
-  """Builds the tensor-core screening image (bf16 UMMA tiles + norm bound) of a corpus."""
+def index_build(corpus: torch.Tensor, reuse_slot: Optional[str] = None) -> torch.Tensor:
+  """Builds the tensor-core screening image (fp16 UMMA tiles + norm bound) of a corpus.  `reuse_slot` builds it in a
+  per-stream scratch buffer instead of a fresh allocation (Streaming's per-chunk images)."""
   corpus = f32c(corpus, "candidates")
   N, d = corpus.shape
   nb = lib().tfrs_index_bytes(N, d)
   if nb == 0:
     raise NotImplementedError("tensor-core index not available for this shape")
-  buf = torch.empty(nb, dtype=torch.uint8, device=corpus.device)
+  buf = torch.empty(nb, dtype=torch.uint8, device=corpus.device) if reuse_slot is None else workspace(nb, corpus.device, reuse_slot)
   check(lib().tfrs_index_build(ptr(corpus), N, d, ptr(buf), nb, stream()), "index_build")
   return buf
 
@@ -125,6 +126,118 @@ def topk_tc(q: torch.Tensor, corpus: torch.Tensor, index_buf: torch.Tensor, k: i
   ws = workspace(wsb, q.device, "tc")
   check(lib().tfrs_topk_tc_f32(ptr(q), Q, ptr(corpus), ptr(index_buf), N, d, k, index_offset, ptr(out_s),
                                ptr(out_i), ptr(ws), ws.numel(), stream()), "topk_tc")
+  return out_s, out_i
+
+
+def _i64(t, name: str, device) -> torch.Tensor:
+  if not isinstance(t, torch.Tensor):
+    t = torch.as_tensor(t)
+  return t.to(device=device, dtype=torch.int64).contiguous()
+
+
+def topk_tc_exclude(q: torch.Tensor, corpus: torch.Tensor, index_buf: torch.Tensor, k: int, exclusions: torch.Tensor,
+                    identifiers: Optional[torch.Tensor] = None, index_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+  """`query_with_exclusions` fused into the tensor-core scan's finalize step: ([Q,k] f32 original scores,
+  [Q,k] i64 global indices).  `identifiers` (integer tensor covering the corpus, or None = the row index) and
+  `exclusions` [Q,E] are compared as int64."""
+  q = f32c(q, "queries"); corpus = f32c(corpus, "candidates")
+  Q, d = q.shape; N = corpus.shape[0]
+  ex = _i64(exclusions, "exclusions", q.device)
+  E = int(ex.shape[1])
+  ids = None if identifiers is None else _i64(identifiers, "identifiers", q.device)
+  out_s = torch.empty((Q, k), dtype=torch.float32, device=q.device)
+  out_i = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+  if Q == 0:
+    return out_s, out_i
+  for lo in range(0, Q, TC_MAX_Q_PER_CALL):
+    hi = min(Q, lo + TC_MAX_Q_PER_CALL)
+    wsb = lib().tfrs_topk_tc_workspace_bytes(hi - lo, N, d, k + E)
+    ws = workspace(wsb, q.device, "tc")
+    check(lib().tfrs_topk_tc_exclude_f32(ptr(q[lo:hi]), hi - lo, ptr(corpus), ptr(index_buf), N, d, k, index_offset, ptr(ids),
+                                         ptr(ex[lo:hi]), E, ptr(out_s[lo:hi]), ptr(out_i[lo:hi]), ptr(ws), ws.numel(), stream()),
+          "topk_tc_exclude")
+  return out_s, out_i
+
+
+def topk_tc_count(q: torch.Tensor, corpus: torch.Tensor, index_buf: torch.Tensor, k: int, positive_scores: torch.Tensor
+                  ) -> torch.Tensor:
+  """min(k, #{candidates scoring strictly above the positive}) per query, int32 [Q] -- the fused score branch of
+  FactorizedTopK (no top-K list is produced)."""
+  q = f32c(q, "queries"); corpus = f32c(corpus, "candidates")
+  pos = f32c(positive_scores, "positive_scores").view(-1)
+  Q, d = q.shape; N = corpus.shape[0]
+  out = torch.empty((Q,), dtype=torch.int32, device=q.device)
+  for lo in range(0, Q, TC_MAX_Q_PER_CALL):
+    hi = min(Q, lo + TC_MAX_Q_PER_CALL)
+    wsb = lib().tfrs_topk_tc_workspace_bytes(hi - lo, N, d, k)
+    ws = workspace(wsb, q.device, "tc")
+    check(lib().tfrs_topk_tc_count_f32(ptr(q[lo:hi]), hi - lo, ptr(corpus), ptr(index_buf), N, d, k, ptr(pos[lo:hi]),
+                                       ptr(out[lo:hi]), ptr(ws), ws.numel(), stream()), "topk_tc_count")
+  return out
+
+
+def exclude_rerank(scores: torch.Tensor, idx: torch.Tensor, exclusions: torch.Tensor, k: int,
+                   identifiers: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+  """`_exclude` (factorized_top_k.py:83-115) on a fetched [Q, kf] list of (score, global index): returns the original
+  scores / indices of the min(k, kf) best after lowering excluded identifiers by 1e5."""
+  scores = f32c(scores, "scores"); idx = _i64(idx, "idx", scores.device)
+  Q, kf = scores.shape
+  ex = _i64(exclusions, "exclusions", scores.device)
+  ids = None if identifiers is None else _i64(identifiers, "identifiers", scores.device)
+  k_out = min(k, kf)
+  out_s = torch.empty((Q, k_out), dtype=torch.float32, device=scores.device)
+  out_i = torch.empty((Q, k_out), dtype=torch.int64, device=scores.device)
+  if Q and k_out:
+    check(lib().tfrs_topk_exclude_rerank_f32(ptr(scores), ptr(idx), Q, kf, ptr(ids), ptr(ex), int(ex.shape[1]), k_out,
+                                             ptr(out_s), ptr(out_i), stream()), "exclude_rerank")
+  return out_s, out_i
+
+
+def count_above(scores: torch.Tensor, positive_scores: torch.Tensor) -> torch.Tensor:
+  """#{t : scores[q, t] > positive[q]}, int32 [Q] (tf.math.in_top_k's count on a retrieved list)."""
+  scores = f32c(scores, "scores"); pos = f32c(positive_scores, "positive_scores").view(-1)
+  Q, k = scores.shape
+  out = torch.empty((Q,), dtype=torch.int32, device=scores.device)
+  check(lib().tfrs_count_above_f32(ptr(scores), scores.stride(0), k, ptr(pos), Q, ptr(out), stream()), "count_above")
+  return out
+
+
+def hits_accumulate(count: torch.Tensor, positive_scores: torch.Tensor, sample_weight: Optional[torch.Tensor],
+                    ks: Sequence[int], acc: torch.Tensor) -> None:
+  """acc[j] += sum_q w_q [count_q < ks[j], positive finite]; acc[len(ks)] += sum_q w_q.  acc: float64 [len(ks)+1] on
+  the device; nothing is synchronised."""
+  Q = count.numel()
+  w = None if sample_weight is None else f32c(sample_weight, "sample_weight").view(-1)
+  if w is not None and w.numel() != Q:
+    raise ValueError(f"sample_weight must have one entry per query (got {w.numel()}, expected {Q})")
+  karr = (ctypes.c_int32 * len(ks))(*[int(x) for x in ks])
+  check(lib().tfrs_topk_hits_accumulate(ptr(count), ptr(f32c(positive_scores, "positive_scores").view(-1)), ptr(w), Q, karr,
+                                        len(ks), ptr(acc), stream()), "hits_accumulate")
+
+
+def topk_merge_sorted(scores: torch.Tensor, idx: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+  """Merge [L,Q,k_in] lists that are each sorted (score desc, index asc): rank by binary search, no sort."""
+  scores = f32c(scores, "scores"); idx = require_cuda(idx, "idx").to(torch.int64).contiguous()
+  L, Q, k_in = scores.shape
+  k_out = min(k, L * k_in)
+  out_s = torch.empty((Q, k_out), dtype=torch.float32, device=scores.device)
+  out_i = torch.empty((Q, k_out), dtype=torch.int64, device=scores.device)
+  check(lib().tfrs_topk_merge_sorted_strided(ptr(scores), ptr(idx), Q * k_in, Q * k_in, L, Q, k_in, k_out, ptr(out_s), ptr(out_i),
+                                             stream()), "topk_merge_sorted")
+  return out_s, out_i
+
+
+def topk_sharded(comm, q: torch.Tensor, corpus_local: torch.Tensor, index_buf: Optional[torch.Tensor], k: int,
+                 index_offset: int) -> Tuple[torch.Tensor, torch.Tensor]:
+  """The row-sharded BruteForce call through the C ABI: local scan -> one NCCL all-gather -> merge, on every rank."""
+  q = f32c(q, "queries"); corpus_local = f32c(corpus_local, "candidates")
+  Q, d = q.shape; N = corpus_local.shape[0]
+  out_s = torch.empty((Q, k), dtype=torch.float32, device=q.device)
+  out_i = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+  wsb = lib().tfrs_topk_sharded_workspace_bytes(comm.world, Q, N, d, k)
+  ws = workspace(wsb + 1024, q.device, "sharded")
+  check(lib().tfrs_topk_sharded_f32(comm.handle, ptr(q), Q, ptr(corpus_local), ptr(index_buf), N, d, k, index_offset,
+                                    ptr(out_s), ptr(out_i), ptr(ws), ws.numel(), stream()), "topk_sharded")
   return out_s, out_i
 
 
@@ -162,7 +275,7 @@ def tc_last_call_stats(Q: int, N: int, d: int, k: int, device=None) -> dict:
   counts = ws[base + o_count: base + o_count + Qp * parts * 4].view(torch.int32).view(Qp, parts)[:Q]
   ovf = ws[base + o_ovf: base + o_ovf + Q * 4].view(torch.int32)
   per_query = counts.sum(1)
-  return {"fallback_queries": int((ovf != 0).sum()), "survivors_mean": float(per_query.float().mean()),
+  return {"fallback_queries": int((ovf == 2).sum()), "retried_queries": int((ovf == 1).sum()), "survivors_mean": float(per_query.float().mean()),
           "survivors_max": int(per_query.max()), "parts": parts, "cap_part": cap,
           "part_max": int(counts.max())}
 
@@ -404,20 +517,14 @@ def sparse_adagrad_(table: torch.Tensor, accum: torch.Tensor, ids: torch.Tensor,
 # Cross layers at least this large run their forward GEMM on the tensor cores (fp16 hi/lo split, fp32 accumulate).
 CROSS_TC_MIN_B = 1024
 CROSS_TC_MIN_D = 64
-_cross_w_cache = {}
-
-
 def cross_weight_image(W: torch.Tensor) -> torch.Tensor:
-  """K-major fp16 hi/lo image of W^T for the tensor-core Cross kernel; cached per (storage, version)."""
-  key = (W.data_ptr(), W._version, tuple(W.shape), W.device.index)
-  hit = _cross_w_cache.get(W.data_ptr())
-  if hit is not None and hit[0] == key:
-    return hit[1]
+  """K-major fp16 hi/lo image of W^T for the tensor-core Cross kernel, rebuilt on every call: the split is
+  O(D^2) against the O(B*D^2) GEMM (2.9 MB at D=845), and a cache keyed on (data_ptr, _version) can serve a stale
+  image after the allocator recycles an address or after an in-place `.data` update."""
   D = W.shape[0]
   nb = lib().tfrs_cross_tc_weight_bytes(D)
-  buf = torch.empty(nb, dtype=torch.uint8, device=W.device)
+  buf = workspace(nb, W.device, f"cross_w{D}")
   check(lib().tfrs_cross_tc_weight_build(ptr(W), D, ptr(buf), nb, stream()), "cross_tc_weight_build")
-  _cross_w_cache[W.data_ptr()] = (key, buf)
   return buf
 
 

@@ -22,24 +22,38 @@ class Adagrad:
     self.initial_accumulator_value = initial_accumulator_value
     self.epsilon = epsilon
     self.eps_inside_sqrt = eps_inside_sqrt
+    self._module = None
     self._dense: List[torch.nn.Parameter] = []
     self._tables: List[Embedding] = []
     self._acc = {}
 
   def bind(self, module: torch.nn.Module) -> "Adagrad":
-    self._tables = [m for m in module.modules() if isinstance(m, Embedding)]
-    anchors = {id(t._anchor) for t in self._tables}
-    self._dense = [p for p in module.parameters() if p.requires_grad and id(p) not in anchors]
+    """Attach to a model.  The variable lists are re-read on every step (`_refresh`), like the reference's
+    `self.trainable_variables` at models/base.py:77: layers that create their weights lazily on the first
+    forward (Cross, MultiLayerDCN) are picked up even when compile() ran before the first batch."""
+    self._module = module
+    self._refresh()
     return self
 
-  def _accum(self, key, like: torch.Tensor) -> torch.Tensor:
-    a = self._acc.get(key)
-    if a is None:
+  def _refresh(self) -> None:
+    if self._module is None:
+      return
+    self._tables = [m for m in self._module.modules() if isinstance(m, Embedding)]
+    anchors = {id(t._anchor) for t in self._tables}
+    self._dense = [p for p in self._module.parameters() if p.requires_grad and id(p) not in anchors]
+
+  def _accum(self, owner, like: torch.Tensor) -> torch.Tensor:
+    """Accumulator slot of a variable, stored ON its owner object (an Embedding module or a Parameter) so it
+    lives and dies with it -- an id()-keyed dict would hand a recycled id the previous owner's state."""
+    a = getattr(owner, "_tfrs_adagrad_acc", None)
+    if a is None or a.shape != like.shape or a.device != like.device:
       a = torch.full_like(like, self.initial_accumulator_value)
-      self._acc[key] = a
+      owner._tfrs_adagrad_acc = a
+      self._acc[id(owner)] = a
     return a
 
   def zero_grad(self):
+    self._refresh()
     for p in self._dense:
       p.grad = None
     for t in self._tables:
@@ -49,18 +63,19 @@ class Adagrad:
   @torch.no_grad()
   def apply_gradients(self):
     """optimizer.apply_gradients(zip(grads, vars)) -- models/base.py:78."""
+    self._refresh()
     for t in self._tables:
       grads = t.pop_sparse_grads()
       if not grads:
         continue
       ids = torch.cat([i.reshape(-1) for i, _ in grads], 0)
       rows = torch.cat([g.reshape(-1, t.output_dim) for _, g in grads], 0)
-      ops.sparse_adagrad_(t.weight, self._accum(id(t), t.weight), ids, rows, self.learning_rate, self.epsilon,
+      ops.sparse_adagrad_(t.weight, self._accum(t, t.weight), ids, rows, self.learning_rate, self.epsilon,
                           self.eps_inside_sqrt)
     for p in self._dense:
       if p.grad is None:
         continue
-      a = self._accum(id(p), p)
+      a = self._accum(p, p)
       g = p.grad
       a.addcmul_(g, g)
       den = (a + self.epsilon).sqrt_() if self.eps_inside_sqrt else a.sqrt().add_(self.epsilon)

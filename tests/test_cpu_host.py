@@ -111,22 +111,50 @@ def test_shard_bounds_cover_the_corpus():
 
 
 _WORKER = r"""
-import os, sys
+import ctypes, os, sys
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["TFRS_ROOT"])
 from oracle import oracle as orc
-from recommenders_b200.layers.factorized_top_k import allgather_topk, shard_bounds
+from recommenders_b200 import _ffi
+from recommenders_b200.layers.factorized_top_k import shard_bounds
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["TFRS_PORT"],
                         rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
 rank, world = dist.get_rank(), dist.get_world_size()
+lib = _ffi.lib()
+# (1) control plane of ShardComm: rank 0's 128-byte NCCL id reaches every rank unchanged (tfrs_comm_create itself needs GPUs)
+uid = (ctypes.c_char * 128)()
+if rank == 0:
+  assert lib.tfrs_comm_unique_id(uid) == 0, _ffi.last_error()
+box = [bytes(uid)]
+dist.broadcast_object_list(box, src=0)
+digest = torch.tensor([sum(box[0]) + 1000003 * box[0][5]], dtype=torch.int64)
+ref = digest.clone(); dist.broadcast(ref, src=0)
+assert len(box[0]) == 128 and int(ref) == int(digest), "unique id differs between ranks"
+# (2) the data path of tfrs_topk_sharded_f32, byte for byte: every rank writes its local top-k into the packed send
+# block [scores f32 [Q,k] | pad | indices i64 [Q,k]] at the offsets the C ABI reports (short shards padded with
+# (-inf, INT64_MAX)), ONE all-gather of the blocks, merge reading the receive buffer in place.
 rng = np.random.RandomState(0)
-N, Q, d, k = 1003, 9, 16, 300     # k > rows of a shard for world=4 would pad; here shard 0 has 502 rows
+N, Q, d, k = 1003, 9, 16, 502      # shard 0 has 502 rows (== k), shard 1 has 501 (< k): the padded case
 c = rng.normal(size=(N, d)).astype(np.float32); q = rng.normal(size=(Q, d)).astype(np.float32)
 c[700] = c[3]                      # a cross-shard exact tie: the lower global index must win
 lo, hi = shard_bounds(N, rank, world)
-s, i = orc.topk_scan(q, c[lo:hi], min(k, hi - lo), index_offset=lo)   # the local scan (CUDA kernel on a GPU box)
-all_s, all_i = allgather_topk(torch.from_numpy(s), torch.from_numpy(i), k)
-ms, mi = orc.topk_merge(all_s.numpy(), all_i.numpy(), k)               # the merge kernel's oracle
+lay = (ctypes.c_int64 * 4)()
+assert lib.tfrs_topk_sharded_layout(world, Q, hi - lo, d, k, lay) == 0
+idx_off, block = int(lay[0]), int(lay[1])
+blocks = torch.tensor([block], dtype=torch.int64); mx = blocks.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+assert int(mx) == block, "block size must not depend on the shard"
+k_local = min(k, hi - lo)
+s, i = orc.topk_scan(q, c[lo:hi], k_local, index_offset=lo)   # the local scan (CUDA kernel on a GPU box)
+send = np.zeros(block, dtype=np.uint8)
+ss = send[:Q * k * 4].view(np.float32).reshape(Q, k); si = send[idx_off:idx_off + Q * k * 8].view(np.int64).reshape(Q, k)
+ss[:] = -np.inf; si[:] = np.iinfo(np.int64).max
+ss[:, :k_local] = s; si[:, :k_local] = i
+recv = torch.empty(world * block, dtype=torch.uint8)
+dist.all_gather_into_tensor(recv, torch.from_numpy(send))
+r = recv.numpy()
+all_s = np.stack([r[g * block: g * block + Q * k * 4].view(np.float32).reshape(Q, k) for g in range(world)])
+all_i = np.stack([r[g * block + idx_off: g * block + idx_off + Q * k * 8].view(np.int64).reshape(Q, k) for g in range(world)])
+ms, mi = orc.topk_merge(all_s, all_i, k)               # the merge kernel's oracle
 es, ei = orc.topk_scan(q, c, k)
 assert np.array_equal(mi, ei) and np.array_equal(ms, es), "sharded result differs from the unsharded scan"
 dist.barrier()

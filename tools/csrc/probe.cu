@@ -1,8 +1,8 @@
 // probe.cu -- hardware probe: one CTA, one 128x128x64 UMMA tile with a caller-chosen instruction
 // descriptor, raw TMEM dump.  Used to pin down undocumented layouts (e.g. fp16 accumulators) before the
 // production kernels rely on them.  Not on any product path.
-#include "common.cuh"
-#include "tc_ptx.cuh"
+#include "../../recommenders_b200/csrc/common.cuh"
+#include "../../recommenders_b200/csrc/tc_ptx.cuh"
 
 namespace tfrs {
 namespace tc {

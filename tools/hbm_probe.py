@@ -7,9 +7,17 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 
 from recommenders_b200 import _ffi
+import _probe  # tools/libtfrs_b200_probe.so: the probes are not in the product library
+
+
+def _rc(rc, what="probe"):
+  if rc:
+    raise RuntimeError(f"{what}: rc={rc}")
+
 
 dev = torch.device("cuda", 0)
 SRC_ROWS = 26_000_000          # 3.3 GB of 128-byte rows (the 26 cfg5 tables)
@@ -22,7 +30,7 @@ st = _ffi.stream()
 
 def run(mode, iters=20):
   def f():
-    _ffi.check(_ffi.lib().tfrs_debug_hbm_probe(mode, _ffi.ptr(src), SRC_ROWS, _ffi.ptr(dst), N, 65536, 848, _ffi.ptr(sink), st), "probe")
+    _rc(_probe.lib().tfrs_debug_hbm_probe(mode, _ffi.ptr(src), SRC_ROWS, _ffi.ptr(dst), N, 65536, 848, _ffi.ptr(sink), st), "probe")
   for _ in range(3):
     f()
   torch.cuda.synchronize()

@@ -3,8 +3,16 @@ Builds two 128x64 fp16 tiles with the library's own image builder, runs one UMMA
 D=f16, dumps raw TMEM and tests layout hypotheses."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np, torch
 from recommenders_b200 import ops, _ffi
+import _probe  # tools/libtfrs_b200_probe.so: the probes are not in the product library
+
+
+def _rc(rc, what="probe"):
+  if rc:
+    raise RuntimeError(f"{what}: rc={rc}")
+
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 a = torch.randn((128, 64), device=dev); b = torch.randn((128, 64), device=dev)
@@ -18,7 +26,7 @@ IDESC_F32 = (1 << 4) | ((128 >> 3) << 17) | ((128 >> 4) << 24)
 IDESC_F16 = (0 << 4) | ((128 >> 3) << 17) | ((128 >> 4) << 24)
 for name, idesc in (("D=f32", IDESC_F32), ("D=f16", IDESC_F16)):
   out = torch.zeros((128, 128), dtype=torch.int32, device=dev)
-  _ffi.check(_ffi.lib().tfrs_debug_umma_probe(ctypes.c_void_p(ia[1024:].data_ptr()), ctypes.c_void_p(ib[1024:].data_ptr()),
+  _rc(_probe.lib().tfrs_debug_umma_probe(ctypes.c_void_p(ia[1024:].data_ptr()), ctypes.c_void_p(ib[1024:].data_ptr()),
                                               idesc, 128, ctypes.c_void_p(out.data_ptr()), None), "probe")
   torch.cuda.synchronize()
   raw = out.cpu().numpy().view(np.uint32)

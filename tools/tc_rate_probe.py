@@ -7,9 +7,17 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 
 from recommenders_b200 import _ffi
+import _probe  # tools/libtfrs_b200_probe.so: the probes are not in the product library
+
+
+def _rc(rc, what="probe"):
+  if rc:
+    raise RuntimeError(f"{what}: rc={rc}")
+
 
 rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 dev = torch.device("cuda", 0)
@@ -21,7 +29,7 @@ names = {0: "tcgen05.ld x64 (16 warps x 8 KB per round)", 1: "tcgen05.ld x64 pac
 out = {}
 for mode in range(6):
   for _ in range(2):
-    _ffi.check(_ffi.lib().tfrs_debug_tc_rate_probe(mode, rounds, n_ctas, _ffi.ptr(cyc), _ffi.ptr(sink), _ffi.stream()), "probe")
+    _rc(_probe.lib().tfrs_debug_tc_rate_probe(mode, rounds, n_ctas, _ffi.ptr(cyc), _ffi.ptr(sink), _ffi.stream()), "probe")
   torch.cuda.synchronize()
   c = cyc.float()
   per_round = float(c.median()) / rounds
