@@ -6,7 +6,9 @@
 
 A "step" = one BruteForce.call: 4096 queries x (1M x 64) corpus -> top-100 (BASELINE configs[1]).  At N>1
 the same corpus is row-sharded over the ranks (strong scaling): every rank scans its shard, ONE all-gather
-of the per-shard (score, index) top-K, merge on every rank.  Prints ONE JSON line (rank 0).
+of the per-shard (score, index) top-K (issued by libtfrs_b200.so's own NCCL communicator), merge on every rank.
+Prints ONE JSON line (rank 0): value / e2e / roofline / cpu_baseline, plus `gather_gbs` and `adagrad_us` (the second
+half of the BASELINE metric) at N = 1.
 """
 from __future__ import annotations
 
@@ -81,8 +83,22 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_arm_step(orc, q, c, k):
-  """The reference's CPU op sequence (matmul -> top_k -> gather ids, factorized_top_k.py:603-607) via BLAS."""
-  return orc.brute_force_blas(q, c, k)
+  """The reference's CPU op sequence (matmul -> top_k -> gather ids, factorized_top_k.py:603-607) under SURVEY 8d's
+  protocol: torch CPU sgemm on all host threads + torch.topk(sorted=True), queries chunked by 512."""
+  return orc.brute_force_torch(q, c, k, chunk=512)
+
+
+def gen_corpus_block(torch, dev, b0, rows, d):
+  """The synthetic corpus is defined block-wise (1M-row blocks, seed 1 + first row): every rank and the oracle leg
+  regenerate exactly the same rows."""
+  g = torch.Generator(device=dev)
+  g.manual_seed(1 + b0)
+  return torch.randn((rows, d), generator=g, device=dev)
+
+
+def workload_string(name, N, d, Q, k, world):
+  return (f"{name}: BruteForce top-{k}, {Q} queries x {N}x{d} corpus (N(0,1), seeds 1/2), "
+          f"row-sharded over {world} GPU(s)")
 
 
 def run_reference(args):
@@ -90,28 +106,35 @@ def run_reference(args):
   if rank != 0:
     return 0
   import numpy as np
+  import torch
   from oracle import oracle as orc
   N, d, Q, k = WORKLOADS[args.workload]
-  sample_q = args.cpu_queries
+  threads = os.cpu_count() or 1
+  torch.set_num_threads(threads)
+  # the same synthetic corpus / queries as the GPU arm (generated on the host: same distribution and seeds' role)
   c = np.random.default_rng(1).standard_normal((N, d), dtype=np.float32)
-  q = np.random.RandomState(2).normal(size=(sample_q, d)).astype(np.float32)
+  q = np.random.default_rng(2).standard_normal((Q, d), dtype=np.float32)
+  sample_q = Q if args.cpu_queries <= 0 else min(Q, args.cpu_queries)
+  qs = q[:sample_q]
   for _ in range(max(1, min(args.warmup, 2))):
-    cpu_arm_step(orc, q, c, k)
+    cpu_arm_step(orc, qs, c, k)
   t0 = time.perf_counter()
   for _ in range(args.steps):
-    cpu_arm_step(orc, q, c, k)
+    cpu_arm_step(orc, qs, c, k)
   dt = time.perf_counter() - t0
   value = sample_q * args.steps / dt
-  cores = os.cpu_count() or 1
+  world = int(os.environ.get("WORLD_SIZE", "1"))
   line = {
       "impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
       "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
       "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-      "config": {"workload": f"{args.workload}: N={N} d={d} K={k}; each step scores a {sample_q}-query sample of the 4096-query batch "
-                             "against the full corpus", "note": "TensorFlow is not installable here; this is the reference's op "
-                             "sequence (sgemm -> top_k -> gather) restated on NumPy/BLAS (oracle port)"},
-      "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
-                       "sample": f"{sample_q} queries x {N} candidates x {args.steps} steps"},
+      "config": {"workload": workload_string(args.workload, N, d, Q, k, world),
+                 "path": "CPU: torch sgemm (MKL/oneDNN) -> torch.topk(sorted) -> ids, 512-query chunks, all host threads "
+                         "(SURVEY 8d protocol; TensorFlow is not installable here, so this is the reference's op sequence "
+                         "factorized_top_k.py:603-607 restated on torch CPU)",
+                 "queries_per_step": sample_q},
+      "cpu_baseline": {"value": value, "unit": "queries/s", "cores": threads, "kind": "port",
+                       "sample": f"{sample_q} of {Q} queries x {N} candidates x {args.steps} steps, {threads} threads"},
       "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "gpu_launches": 0,
   }
@@ -126,7 +149,9 @@ def main():
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-  ap.add_argument("--cpu-queries", type=int, default=64, help="queries per CPU-arm step (bounded sample)")
+  ap.add_argument("--cpu-queries", type=int, default=0,
+                  help="queries per CPU-arm step (0 = the whole batch; the in-line cpu_baseline leg uses a bounded sample)")
+  ap.add_argument("--no-secondary", action="store_true", help="skip the gather / Adagrad / training-step figures")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-tensor-cores", action="store_true", help="force the exact CUDA-core path (debug)")
   args = ap.parse_args()
@@ -153,24 +178,26 @@ def main():
   N, d, Q, k = WORKLOADS[args.workload]
   lo, hi = shard_bounds(N, rank, world)
   # synthetic corpus: every rank generates the SAME full-corpus stream in 1M-row blocks and keeps its rows
-  g = torch.Generator(device=dev)
   blocks = []
   for b0 in range(0, N, 1_000_000):
-    g.manual_seed(1 + b0)
-    blk = torch.randn((min(1_000_000, N - b0), d), generator=g, device=dev)
-    s0, s1 = max(lo, b0), min(hi, b0 + blk.shape[0])
+    s0, s1 = max(lo, b0), min(hi, b0 + min(1_000_000, N - b0))
     if s1 > s0:
+      blk = gen_corpus_block(torch, dev, b0, min(1_000_000, N - b0), d)
       blocks.append(blk[s0 - b0:s1 - b0].clone())
-    del blk
+      del blk
   corpus_local = torch.cat(blocks, 0) if len(blocks) > 1 else blocks[0]
   del blocks
+  # NQ different query batches, rotated step by step (the timed steps never see the batch of the step before)
+  NQ = 8
+  g = torch.Generator(device=dev)
   g.manual_seed(2)
-  queries = torch.randn((Q, d), generator=g, device=dev)
+  query_batches = [torch.randn((Q, d), generator=g, device=dev) for _ in range(NQ)]
+  queries = query_batches[0]
 
   layer = tfrs.layers.factorized_top_k.BruteForce(k=k)
   layer.use_tensor_cores = not args.no_tensor_cores
   if world > 1:
-    layer.index_shard(corpus_local, lo)
+    layer.index_shard(corpus_local, lo, copy=False)
   else:
     layer.index(corpus_local)
   used_tc = layer._tc_index is not None and ops.tc_supported(Q, corpus_local.shape[0], d, k)
@@ -180,21 +207,23 @@ def main():
       dist.barrier()
     torch.cuda.synchronize()
 
+  sampler = ClockSampler(local_rank) if rank == 0 else None
+  if sampler is not None:
+    sampler.start()   # runs across all timed legs (nvidia-smi needs a few hundred ms before its first sample)
+
   # ---------------- device-resident throughput (`value`) ----------------
-  for _ in range(args.warmup):
-    out = layer(queries)
+  for w in range(args.warmup):
+    out = layer(query_batches[w % NQ])
   sync_all()
-  sampler = ClockSampler(local_rank)
-  sampler.start()
-  time.sleep(0.15)
   launches0 = ops.launch_count()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   sync_all()
   e0.record()
-  for _ in range(args.steps):
-    out = layer(queries)
+  for st in range(args.steps):
+    out = layer(query_batches[st % NQ])
   e1.record()
   torch.cuda.synchronize()
+  last_batch = (args.steps - 1) % NQ
   launches = ops.launch_count() - launches0
   ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
   if world > 1:
@@ -203,47 +232,46 @@ def main():
   value = Q * args.steps / (ms_total * 1e-3)
 
   # ---------------- end-to-end through the public API with host buffers (`e2e`) ----------------
-  q_host = queries.cpu().pin_memory()
+  q_hosts = [qb.cpu().pin_memory() for qb in query_batches]
   s_host = torch.empty((Q, k), dtype=torch.float32).pin_memory()
   i_host = torch.empty((Q, k), dtype=torch.int32).pin_memory()
   q_dev = torch.empty_like(queries)
 
-  def e2e_step():
-    q_dev.copy_(q_host, non_blocking=True)
+  def e2e_step(j):
+    q_dev.copy_(q_hosts[j % NQ], non_blocking=True)
     s, i = layer(q_dev)
     s_host.copy_(s, non_blocking=True)
     i_host.copy_(i, non_blocking=True)
     torch.cuda.current_stream().synchronize()  # the caller reads the result every step
 
-  for _ in range(args.warmup):
-    e2e_step()
+  for w in range(args.warmup):
+    e2e_step(w)
   sync_all()
   e0.record()
-  for _ in range(args.steps):
-    e2e_step()
+  for st in range(args.steps):
+    e2e_step(st)
   e1.record()
   torch.cuda.synchronize()
   ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
   if world > 1:
     dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
   e2e_value = Q * args.steps / (float(ms2) * 1e-3)
-  sampler.stop()
 
   # ---------------- roofline of the dominant kernel (full filter pass), CUDA events inside the ABI ----------------
   roofline = None
+  peaks = {}
+  try:
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+  except Exception:
+    pass
   if used_tc:
     ops.profile_enable(True)
-    for _ in range(args.steps):
-      layer(queries)
+    for st in range(args.steps):
+      layer(query_batches[st % NQ])
     stage_ms, calls = ops.profile_read()
     ops.profile_enable(False)
-    peaks = {}
-    try:
-      peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-      pass
     peak = peaks.get("bf16_tflops", 1590.0)
-    which = "measured bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback 1590"
+    which = "measured bf16_tflops (burst; the filter pass is timed alone)" if "bf16_tflops" in peaks else "fallback 1590"
     n_local = corpus_local.shape[0]
     flops = 2.0 * Q * n_local * d  # algorithmic: 2*Q*N*d per launch (128 MFLOP/query at N=1M,d=64)
     t_filter = stage_ms[2] / max(calls, 1) * 1e-3
@@ -251,36 +279,53 @@ def main():
     roofline = {"bound": "tensor", "kernel": "tc_scan_kernel<FILTER>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "peak_source": which,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, from the committed ncu
-                # --set full capture (profiles/r01_tc_scan_v5_metrics.csv: 131.3 MB + 39.7 MB); only for that shape
-                "traffic": 170.9e6 if (args.workload == "cfg2" and world == 1) else None, "traffic_unit": "bytes/launch",
+                # --set full capture (profiles/, see profiles/README.md); only for the cfg2 single-GPU shape
+                "traffic": TRAFFIC_CFG2_FILTER if (args.workload == "cfg2" and world == 1) else None, "traffic_unit": "bytes/launch",
+                "whole_call_frac": (flops / (ms_total / args.steps * 1e-3) / 1e12) / peak,
                 "stage_ms_per_call": {"qprep": stage_ms[0] / calls, "sample_pass+threshold": stage_ms[1] / calls,
                                       "filter_pass": stage_ms[2] / calls, "rescore+finalize": stage_ms[3] / calls}}
 
-  # ---------------- parity of the timed outputs against the oracle (rank 0, a few rows) ----------------
+  # ---------------- parity of the timed outputs against the oracle (rank 0, a few rows, at EVERY N) ----------------
   checked = None
   if rank == 0:
     from oracle import oracle as orc
     rows = [0, Q // 2, Q - 1]
     s, i = out
     if world == 1:
-      es, ei = orc.topk_scan(queries[rows].cpu().numpy(), corpus_local.cpu().numpy(), k)
-      checked = bool(np.array_equal(i[rows].cpu().numpy(), ei) and np.array_equal(s[rows].cpu().numpy(), es))
-    else:
-      checked = bool((s[:, :-1] >= s[:, 1:]).all())  # full oracle needs the whole corpus on one host; see tests
+      full = corpus_local.cpu().numpy()
+    else:  # regenerate the whole corpus (same block-wise stream) for the oracle
+      full = np.concatenate([gen_corpus_block(torch, dev, b0, min(1_000_000, N - b0), d).cpu().numpy()
+                             for b0 in range(0, N, 1_000_000)], 0)
+    es, ei = orc.topk_scan(query_batches[last_batch][rows].cpu().numpy(), full, k)
+    checked = bool(np.array_equal(i[rows].cpu().numpy(), ei) and np.array_equal(s[rows].cpu().numpy(), es))
+    del full
+
+  # ---------------- second half of the BASELINE metric + training-step pieces (rank 0, N = 1) ----------------
+  secondary = None
+  if rank == 0 and world == 1 and not args.no_secondary:
+    del layer, corpus_local
+    torch.cuda.empty_cache()
+    secondary = secondary_figures(torch, tfrs, ops, dev, peaks)
+  if sampler is not None:
+    sampler.stop()
 
   # ---------------- CPU baseline beside it (rank 0, N=1 only, bounded sample) ----------------
   cpu_baseline = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     from oracle import oracle as orc
-    cq = args.cpu_queries
-    c_np = corpus_local.cpu().numpy(); q_np = queries[:cq].cpu().numpy()
-    cpu_arm_step(orc, q_np, c_np, k)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cq = 1024
+    c_np = np.concatenate([gen_corpus_block(torch, dev, b0, min(1_000_000, N - b0), d).cpu().numpy() for b0 in range(0, N, 1_000_000)], 0)
+    q_np = queries[:cq].cpu().numpy()
+    cpu_arm_step(orc, q_np[:512], c_np, k)
     reps, t0 = 0, time.perf_counter()
-    while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 50):
+    while reps < 2 or (time.perf_counter() - t0 < 12.0 and reps < 50):
       cpu_arm_step(orc, q_np, c_np, k); reps += 1
     dt = time.perf_counter() - t0
-    cpu_baseline = {"value": cq * reps / dt, "unit": "queries/s", "cores": os.cpu_count() or 1, "kind": "port",
-                    "sample": f"{cq} queries x {N} candidates, {reps} reps (NumPy/BLAS sgemm -> top_k, the reference's op sequence)"}
+    cpu_baseline = {"value": cq * reps / dt, "unit": "queries/s", "cores": threads, "kind": "port",
+                    "sample": f"{cq} queries x {N} candidates, {reps} reps (torch CPU sgemm -> topk, 512-query chunks, {threads} threads: "
+                              "the reference's op sequence under SURVEY 8d's protocol)"}
 
   if rank == 0:
     line = {
@@ -288,12 +333,13 @@ def main():
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 (fp16 tcgen05 screening, fp32 accumulate + exact fp32 re-scoring)" if used_tc else "f32",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: BruteForce top-{k}, {Q} queries x {N}x{d} corpus (N(0,1), seeds 1/2), "
-                               f"row-sharded over {world} GPU(s)",
+        "config": {"workload": workload_string(args.workload, N, d, Q, k, world),
                    "path": "tcgen05 screening + exact rescoring" if used_tc else "exact CUDA-core scan",
-                   "l2": "inputs (fp16 image 128 MB + fp32 corpus 256 MB per 1M rows) exceed the 126 MB L2 between steps",
-                   "parallelism": f"corpus-shard x{world}"},
-        "clocks": sampler.summary(),
+                   "l2": "inputs (fp16 image 128 MB + fp32 corpus 256 MB per 1M rows) exceed the 126 MB L2 between steps; "
+                         f"{NQ} query batches rotate",
+                   "parallelism": f"corpus-shard x{world}",
+                   "collective": "tfrs_topk_sharded_f32: one ncclAllGather issued by libtfrs_b200.so" if world > 1 else None},
+        "clocks": sampler.summary() if sampler is not None else None,
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": Q * d * 4, "d2h_bytes_per_step": Q * k * 8,
                 "ms_per_step": float(ms2) / args.steps},
         "gpu_launches": int(launches),
@@ -301,6 +347,8 @@ def main():
     }
     if roofline is not None:
       line["roofline"] = roofline
+    if secondary is not None:
+      line.update(secondary)
     if cpu_baseline is not None:
       line["cpu_baseline"] = cpu_baseline
     print(json.dumps(line))
@@ -308,6 +356,76 @@ def main():
     dist.barrier()
     dist.destroy_process_group()
   return 0
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of tc_scan_kernel<FILTER> at cfg2 on one GPU (ncu --set full, per launch)
+TRAFFIC_CFG2_FILTER = 170.9e6
+
+
+def _time_ms(torch, fn, iters=20, warm=3):
+  for _ in range(warm):
+    fn()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  torch.cuda.synchronize()
+  e0.record()
+  for _ in range(iters):
+    fn()
+  e1.record()
+  torch.cuda.synchronize()
+  return e0.elapsed_time(e1) / iters
+
+
+def secondary_figures(torch, tfrs, ops, dev, peaks):
+  """HBM GB/s of the embedding gather (the second half of BASELINE.json's metric: cfg5 and cfg3 shapes, uniform and
+  Zipf ids) and the sparse-Adagrad / in-batch-softmax times of a cfg3 training step.  Algorithmic bytes per SURVEY 8d."""
+  hbm = peaks.get("hbm_gbs", 6650.0)
+  out = {}
+  g = torch.Generator(device=dev); g.manual_seed(7)
+  # cfg5: 26 tables [1M, 32], B = 65536 -> [B, 845 (ld 848)]
+  tables = [torch.rand((1_000_000, 32), generator=g, device=dev) * 0.1 - 0.05 for _ in range(26)]
+  ids = [torch.randint(0, 1_000_000, (65536,), generator=g, device=dev, dtype=torch.int32) for _ in range(26)]
+  act = torch.zeros((65536, 848), device=dev)
+  ms5 = _time_ms(torch, lambda: ops.gather(tables, ids, out=act))
+  bytes5 = 65536 * 26 * 32 * 4 * 2 + 26 * 65536 * 4
+  out["gather_gbs"] = bytes5 / ms5 / 1e6
+  out["gather"] = {"cfg5_uniform": {"gbs": bytes5 / ms5 / 1e6, "us": ms5 * 1e3, "frac_of_hbm_peak": bytes5 / ms5 / 1e6 / hbm,
+                                    "algorithmic_bytes": bytes5},
+                   "hbm_peak_gbs": hbm, "peak_source": "measured hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"}
+  del tables, ids, act
+  torch.cuda.empty_cache()
+  # cfg3: user table [10M, 64], item table [1M, 64], B = 16384; ids uniform and Zipf(1.05)
+  ut = torch.rand((10_000_000, 64), generator=g, device=dev) * 0.1 - 0.05
+  it = torch.rand((1_000_000, 64), generator=g, device=dev) * 0.1 - 0.05
+  B = 16384
+  def zipf(n_rows, n):
+    u = torch.rand((n,), generator=g, device=dev, dtype=torch.float64)
+    # inverse-CDF of a bounded Zipf(s = 1.05) on ranks 1..n_rows (continuous approximation), rank r -> row r - 1
+    s = 1.05
+    r = ((u * (n_rows ** (1 - s) - 1) + 1) ** (1 / (1 - s))).clamp(1, n_rows)
+    return (r.to(torch.int64) - 1).to(torch.int32)
+  for name, uid, iid in (("cfg3_uniform", torch.randint(0, 10_000_000, (B,), generator=g, device=dev, dtype=torch.int32),
+                          torch.randint(0, 1_000_000, (B,), generator=g, device=dev, dtype=torch.int32)),
+                         ("cfg3_zipf", zipf(10_000_000, B), zipf(1_000_000, B))):
+    ms3 = _time_ms(torch, lambda: (ops.gather([ut], [uid]), ops.gather([it], [iid])))
+    b3 = 2 * B * 64 * 4 * 2 + 2 * B * 4
+    out["gather"][name] = {"gbs": b3 / ms3 / 1e6, "us": ms3 * 1e3, "frac_of_hbm_peak": b3 / ms3 / 1e6 / hbm, "algorithmic_bytes": b3,
+                           "unique_ids": [int(uid.unique().numel()), int(iid.unique().numel())]}
+    acc = torch.full_like(it, 0.1)
+    grows = torch.randn((B, 64), generator=g, device=dev) * 1e-3
+    msa = _time_ms(torch, lambda: ops.sparse_adagrad_(it, acc, iid, grows, 0.1))
+    uniq = int(iid.unique().numel())
+    ba = uniq * 64 * 4 * 4 + B * 64 * 4 + B * 4
+    out["gather"][name]["adagrad_us"] = msa * 1e3
+    out["gather"][name]["adagrad_gbs"] = ba / msa / 1e6
+    if name == "cfg3_uniform":
+      out["adagrad_us"] = msa * 1e3
+    del acc
+  q = ops.gather([ut], [uid]).requires_grad_(True); c = ops.gather([it], [iid]).requires_grad_(True)
+  def step():
+    q.grad = None; c.grad = None
+    ops.inbatch_softmax_loss(q, c).backward()
+  out["inbatch_softmax_fwd_bwd_us"] = _time_ms(torch, step, iters=10) * 1e3
+  return out
 
 
 if __name__ == "__main__":

@@ -390,3 +390,21 @@ def brute_force_blas(q: np.ndarray, c: np.ndarray, k: int) -> Tuple[np.ndarray, 
   ps = np.take_along_axis(s, part, 1)
   order = np.lexsort((part, -ps), axis=1)
   return np.take_along_axis(ps, order, 1), np.take_along_axis(part, order, 1)
+
+
+def brute_force_torch(q: np.ndarray, c: np.ndarray, k: int, chunk: int = 512, threads: Optional[int] = None):
+  """SURVEY 8d's CPU protocol for the reference's BruteForce.call (factorized_top_k.py:603-607): torch CPU sgemm
+  (MKL/oneDNN, all cores) -> torch.topk(sorted=True) -> indices, queries chunked by 512 to bound the [Q,N] buffer (the
+  reference's own tutorial chunks by 1000).  A SPEED baseline: torch.topk does not promise the lowest-index tie rule, so
+  this is never used as the checker."""
+  import torch
+  if threads:
+    torch.set_num_threads(int(threads))
+  qt = torch.from_numpy(np.ascontiguousarray(q, np.float32)); ct = torch.from_numpy(np.ascontiguousarray(c, np.float32))
+  vs, ix = [], []
+  with torch.no_grad():
+    for lo in range(0, qt.shape[0], chunk):
+      s = qt[lo:lo + chunk] @ ct.T
+      v, i = torch.topk(s, k, dim=1, sorted=True)
+      vs.append(v); ix.append(i)
+  return torch.cat(vs).numpy(), torch.cat(ix).numpy()

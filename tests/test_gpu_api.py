@@ -352,7 +352,7 @@ def test_dot_interaction_layer_known_answers_and_parity():
         edf = orc.dot_interaction_grads(feats, g, si, sg)
         for f in range(F):
           err = np.abs(ts[f].grad.cpu().numpy().astype(np.float64) - edf[:, f, :]).max()
-          assert err <= 1e-5 * max(1.0, np.abs(edf).max())
+          assert err <= 1e-5 * np.abs(edf).max()
 
 
 def test_multi_layer_dcn_known_answers_and_parity():

@@ -140,7 +140,7 @@ def test_inbatch_softmax_loss_and_grads(ops, B, C, d, temp, weighted):
   assert abs(float(loss) - exp) <= 1e-5 * abs(exp)
   for got, ref in ((tq.grad, edq), (tc.grad, edc)):
     err = np.abs(got.cpu().numpy().astype(np.float64) - ref).max()
-    assert err <= 1e-5 * max(1.0, np.abs(ref).max())
+    assert err <= 1e-5 * np.abs(ref).max()
 
 
 @pytest.mark.parametrize("B,D,diag,bias", [(1, 3, 0.0, False), (257, 845, 0.0, True), (100, 64, 1.0, True), (5000, 130, 0.5, False),
@@ -161,7 +161,7 @@ def test_cross_fwd_bwd(ops, B, D, diag, bias):
   out.backward(cu(g))
   for got, ref in ((t[0].grad, edx0), (t[1].grad, edx), (t[2].grad, edW)) + (((tb.grad, edb),) if bias else ()):
     err = np.abs(got.cpu().numpy().astype(np.float64) - ref).max()
-    assert err <= 1e-5 * max(1.0, np.abs(ref).max()), err
+    assert err <= 1e-5 * np.abs(ref).max(), err
 
 
 def test_errors_cross_the_abi(ops):
@@ -237,7 +237,7 @@ def test_inbatch_softmax_tensor_core_forward(ops, B, C, d, temp, weighted, scale
     assert float(l2) == float(loss)
     for got, ref in ((tq.grad, edq), (tc.grad, edc)):
       err = np.abs(got.cpu().numpy().astype(np.float64) - ref).max()
-      assert err <= 1e-5 * max(1.0, np.abs(ref).max())
+      assert err <= 1e-5 * np.abs(ref).max()
 
 
 @pytest.mark.parametrize("B,C,d,temp,weighted,scale", [(2, 2, 3, None, False, 0.5), (128, 128, 64, None, False, 0.5),
@@ -259,13 +259,14 @@ def test_inbatch_softmax_tensor_core_backward(ops, B, C, d, temp, weighted, scal
   dq, dc = ops.inbatch_softmax_tc_bwd(cu(q), cu(c), lse, None if w is None else cu(w), inv_t, torch.tensor([gl], device="cuda"))
   for got, ref in ((dq, edq * gl), (dc, edc * gl)):
     err = np.abs(got.cpu().numpy().astype(np.float64) - ref).max()
-    assert err <= 1e-5 * max(1.0, np.abs(ref).max()), (err, np.abs(ref).max())
+    assert err <= 1e-5 * np.abs(ref).max(), (err, np.abs(ref).max())
 
 
 def test_inbatch_softmax_tensor_core_backward_full_size(ops):
   """cfg3 size (B = C = 16384, d = 64): the tensor-core backward against the exact CUDA-core backward with the same
-  lse.  Both are fp32 paths with their own accumulation error, so the bar is 2e-5 of the gradient scale (the dX
-  accumulator is drained every 8 tiles; without that the tensor core's truncating adder drifts to 5e-5 here)."""
+  lse -- a consistency check between two fp32 paths, each with its own accumulation error, hence 2e-5 of the
+  gradient scale here; the parity bar proper (1e-5 against float64) is
+  tests/test_gpu_round2.py::test_cfg3_full_size_loss_and_gradients_vs_float64."""
   g = torch.Generator(device="cuda"); g.manual_seed(11)
   B, d = 16384, 64
   q = (torch.rand((B, d), generator=g, device="cuda") - 0.5) * 0.6
@@ -302,7 +303,7 @@ def test_inbatch_softmax_with_sampling_probability_correction(ops, B, C, d, temp
   assert abs(float(loss) - exp) <= 1e-5 * abs(exp)
   for got, ref in ((tq.grad, edq), (tc.grad, edc)):
     err = np.abs(got.cpu().numpy().astype(np.float64) - ref).max()
-    assert err <= 1e-5 * max(1.0, np.abs(ref).max())
+    assert err <= 1e-5 * np.abs(ref).max()
   # the fused op itself, and the materialised path of the task on the same data (forced by a tiny batch-metric-free slice)
   direct = ops.inbatch_softmax_loss(cu(q), cu(c), None if w is None else cu(w), temp, cu(bias.astype(np.float32)))
   assert abs(float(direct) - exp) <= 1e-5 * abs(exp)
