@@ -57,6 +57,38 @@ ag_bitonic_local(unsigned long long* __restrict__ keys, long long P, long long f
   for (int t = threadIdx.x; t < tile; t += AG_THREADS) keys[base + t] = sk[t];
 }
 
+// n <= AG_SINGLE: keys are built and fully sorted by ONE CTA in shared memory (one launch instead of build + tile sorts
+// + global merge stages); the batch sizes of the training step (cfg3: 16384 ids) take this path.
+constexpr int AG_SINGLE = 16384;   // 128 KB of 64-bit keys
+template <typename IdT>
+__global__ void __launch_bounds__(AG_THREADS)
+ag_sort_single(const IdT* __restrict__ ids, long long n, long long rows, int P, unsigned long long* __restrict__ keys) {
+  extern __shared__ unsigned long long sk[];
+  for (int i = threadIdx.x; i < P; i += AG_THREADS) {
+    unsigned long long k = AG_INVALID;
+    if (i < n) {
+      const long long r = (long long)ids[i];
+      if (r >= 0 && r < rows) k = ((unsigned long long)r << 24) | (unsigned long long)i;
+    }
+    sk[i] = k;
+  }
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += AG_THREADS) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool asc = ((lo & size) == 0);
+        unsigned long long a = sk[lo], b = sk[hi];
+        ag_cmpswap(a, b, asc);
+        sk[lo] = a; sk[hi] = b;
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < P; i += AG_THREADS) keys[i] = sk[i];
+}
+
 __global__ void ag_bitonic_global(unsigned long long* __restrict__ keys, long long P, long long size, long long stride) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (P >> 1)) return;
@@ -115,6 +147,19 @@ extern "C" int tfrs_sparse_adagrad_f32(float* table, float* accum, int64_t rows,
   if (!ws || ws_bytes < (size_t)P * 8) { set_error("sparse_adagrad: workspace too small"); return TFRS_ERR_WORKSPACE_TOO_SMALL; }
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* keys = (unsigned long long*)ws;
+  if (P <= AG_SINGLE) {
+    if (ids_dtype == TFRS_I32) {
+      TFRS_DYN_SMEM(ag_sort_single<int32_t>, AG_SINGLE * 8);
+      ag_sort_single<int32_t><<<1, AG_THREADS, (size_t)P * 8, st>>>((const int32_t*)ids, n, rows, (int)P, keys);
+    } else {
+      TFRS_DYN_SMEM(ag_sort_single<int64_t>, AG_SINGLE * 8);
+      ag_sort_single<int64_t><<<1, AG_THREADS, (size_t)P * 8, st>>>((const int64_t*)ids, n, rows, (int)P, keys);
+    }
+    TFRS_LAUNCH_CHECK();
+    ag_apply<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(keys, n, grad_rows, d, table, accum, lr, eps, eps_inside_sqrt);
+    TFRS_LAUNCH_CHECK();
+    return TFRS_OK;
+  }
   unsigned kb = (unsigned)ceil_div(P, 256);
   if (ids_dtype == TFRS_I32) ag_build_keys<int32_t><<<kb, 256, 0, st>>>((const int32_t*)ids, n, rows, P, keys);
   else ag_build_keys<int64_t><<<kb, 256, 0, st>>>((const int64_t*)ids, n, rows, P, keys);

@@ -35,6 +35,7 @@
 // t's epilogue.  Each B tile feeds two MMAs (both A blocks): 16 KB of L2->smem traffic per 512
 // tensor-core cycles keeps the chip under the ~6.3 KB/clk L2 fabric limit.
 #include <cuda_fp16.h>
+#include <math.h>
 #include <stdlib.h>
 #include "rowselect.cuh"
 #include "tc_ptx.cuh"
@@ -458,16 +459,15 @@ tc_threshold_kernel(const float* __restrict__ binmax, int bins_ld, int n_bins, i
 enum { FIN_TOPK = 0, FIN_EXCLUDE = 1, FIN_COUNT = 2 };
 constexpr int FW_WARPS = 4;                       // queries per CTA
 constexpr int FW_SOFF = 304;                      // >= FIN_MAX_PARTS + 1 segment offsets
-constexpr int FW_KEYS_SMALL = 1024, FW_BAND_SMALL = 512;    // first try
-constexpr int FW_KEYS_BIG = 4096, FW_BAND_BIG = 1024;       // retry of the rows that overflowed the first try
-// overflow[row]: 0 = done, 1 = retry with the big capacities, 2 = exact fallback
+// Capacities per query come from the plan (they grow with k); a row that overflows them takes the exact fallback.
+// overflow[row]: 0 = done, 1 = exact fallback
 static size_t fin_warp_bytes(int cap_keys, int cap_band) { return (size_t)cap_keys * 8 + (size_t)cap_band * 8 + FW_SOFF * 4 + 512; }
 
 struct FinParams {
   const float* q; const float* corpus; int d; int k; long long index_offset; long long N; long long Q;
   const unsigned int* count; const float* cand_s; const unsigned int* cand_i; int segs; int cap_part;
   const float* cut; const float* thr; unsigned int* overflow;
-  int cap_keys, cap_band; unsigned int pass;     // pass 0: every row; pass 1: rows flagged 1
+  int cap_keys, cap_band;                        // per-query capacities of the survivor / band lists (shared memory)
   float* out_s; long long* out_i;                // TOPK: [Q, k];  EXCLUDE: [Q, k_out]
   // EXCLUDE (k = k_out + n_excl candidates are fetched, then re-ranked)
   const long long* identifiers; const long long* exclusions; int n_excl; int k_out;
@@ -499,6 +499,30 @@ __device__ __forceinline__ float exact_score(const float* __restrict__ qs, const
     for (int kk = 0; kk < d; ++kk) acc = fmaf(qs[kk], __ldg(c + kk), acc);
   }
   return acc + 0.0f;  // -0 -> +0: the key order must agree with the float order
+}
+
+// two independent chains at once (same arithmetic per chain as exact_score)
+__device__ __forceinline__ void exact_score2(const float* __restrict__ qs, const float* __restrict__ c0, const float* __restrict__ c1,
+                                             int d, float& s0, float& s1) {
+  if ((d & 31) == 0) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int kk = 0; kk < d; kk += 32) {
+      float4 u0[8], u1[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { u0[u] = __ldg(reinterpret_cast<const float4*>(c0 + kk) + u); u1[u] = __ldg(reinterpret_cast<const float4*>(c1 + kk) + u); }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float q0 = qs[kk + 4 * u], q1 = qs[kk + 4 * u + 1], q2 = qs[kk + 4 * u + 2], q3 = qs[kk + 4 * u + 3];
+        a0 = fmaf(q0, u0[u].x, a0); a1 = fmaf(q0, u1[u].x, a1);
+        a0 = fmaf(q1, u0[u].y, a0); a1 = fmaf(q1, u1[u].y, a1);
+        a0 = fmaf(q2, u0[u].z, a0); a1 = fmaf(q2, u1[u].z, a1);
+        a0 = fmaf(q3, u0[u].w, a0); a1 = fmaf(q3, u1[u].w, a1);
+      }
+    }
+    s0 = a0 + 0.0f; s1 = a1 + 0.0f;
+  } else {
+    s0 = exact_score(qs, c0, d); s1 = exact_score(qs, c1, d);
+  }
 }
 
 // _exclude (layers/factorized_top_k.py:83-115) on a query's kf best candidates, sorted in `srt` as
@@ -536,8 +560,7 @@ tc_finalize_kernel(const FinParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * FW_WARPS + warp;
   if (row >= p.Q) return;
-  if (p.overflow[row] != p.pass) return;                 // pass 0 takes the rows the threshold kernel reset, pass 1 the retries
-  const unsigned int retry_flag = (p.pass == 0 && (p.cap_keys < FW_KEYS_BIG || p.cap_band < FW_BAND_BIG)) ? 1u : 2u;
+  const unsigned int retry_flag = 1u;                    // every failure mode ends in the exact fallback
   unsigned char* base = fsm + (size_t)warp * ((size_t)p.cap_keys * 8 + (size_t)p.cap_band * 8 + FW_SOFF * 4 + 512);
   unsigned int* keys = reinterpret_cast<unsigned int*>(base);                           // [cap_keys] screening keys
   unsigned int* sidx = keys + p.cap_keys;                                                // [cap_keys] local indices
@@ -561,7 +584,7 @@ tc_finalize_kernel(const FinParams p) {
   }
   if (lane == 0) soff[0] = 0;
   if (__any_sync(0xffffffffu, bad)) {  // a segment overflowed in the filter pass: records are missing -> exact fallback
-    if (lane == 0) p.overflow[row] = 2;
+    if (lane == 0) p.overflow[row] = 1;
     return;
   }
   for (int t = lane; t < p.d; t += 32) qs[t] = p.q[row * p.d + t];
@@ -640,14 +663,22 @@ tc_finalize_kernel(const FinParams p) {
     n += __shfl_sync(0xffffffffu, incl, 31);
   }
   if (n > p.cap_keys) { if (lane == 0) p.overflow[row] = retry_flag; return; }
-  if (n < p.k) { if (lane == 0) p.overflow[row] = 2; return; }
+  if (n < p.k) { if (lane == 0) p.overflow[row] = 1; return; }
   __syncwarp();
   // tau = k-th best screening score; keep the survivors inside its error band
-  const unsigned int tau_key = warp_kth_largest_smem(keys, n, p.k, lane);
+  unsigned int tau_key;
+  if (n <= 1024) {   // the usual case: this lane's <= 32 keys live in registers, no shared-memory traffic in the 32-step search
+    unsigned int kr[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { const int t = j * 32 + lane; kr[j] = t < n ? keys[t] : 0u; }
+    tau_key = warp_kth_largest_regs<32>(kr, p.k);
+  } else {
+    tau_key = warp_kth_largest_smem(keys, n, p.k, lane);
+  }
   const float lim = key2f(tau_key) - p.cut[row];
   // Self-check that makes the threshold choice a pure performance matter: the whole band [lim, inf) must
   // lie above the filter threshold, otherwise survivors could be missing -> exact fallback.
-  if (!(lim >= thr_row) || !(lim > -INFINITY)) { if (lane == 0) p.overflow[row] = 2; return; }
+  if (!(lim >= thr_row) || !(lim > -INFINITY)) { if (lane == 0) p.overflow[row] = 1; return; }
   int m = 0;
   for (int tb = 0; tb < n; tb += 32) {
     const int t = tb + lane;
@@ -659,10 +690,14 @@ tc_finalize_kernel(const FinParams p) {
   if (m > p.cap_band) { if (lane == 0) p.overflow[row] = retry_flag; return; }  // band too crowded (massive ties)
   __syncwarp();
   // exact re-scoring; band[t] becomes the composite key (score desc, index asc) == larger is better
-  for (int t = lane; t < m; t += 32) {
+  for (int t = lane; t < m; t += 64) {   // two candidates per lane in flight: twice the loads per DRAM round trip
+    const int t2 = t + 32;
     const unsigned int idx = (unsigned int)band[t];
-    const float s = exact_score(qs, p.corpus + (long long)idx * p.d, p.d);
+    const unsigned int idx2 = t2 < m ? (unsigned int)band[t2] : idx;
+    float s, s2;
+    exact_score2(qs, p.corpus + (long long)idx * p.d, p.corpus + (long long)idx2 * p.d, p.d, s, s2);
     band[t] = ((unsigned long long)f2key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+    if (t2 < m) band[t2] = ((unsigned long long)f2key(s2) << 32) | (unsigned long long)(0xFFFFFFFFu - idx2);
   }
   __syncwarp();
   // rank sort: every lane ranks up to 4 own entries per sweep over the band (broadcast reads); ranks are unique
@@ -703,7 +738,7 @@ tc_exclude_fallback_kernel(const FinParams p, const float* __restrict__ tmp_s, c
   extern __shared__ __align__(16) unsigned char fsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * FW_WARPS + warp;
-  if (row >= p.Q || was_fallback[row] != 2) return;
+  if (row >= p.Q || was_fallback[row] == 0) return;
   unsigned long long* srt = reinterpret_cast<unsigned long long*>(fsm) + (size_t)warp * 2 * p.k;
   unsigned long long* akey = srt + p.k;
   for (int t = lane; t < p.k; t += 32)
@@ -718,9 +753,9 @@ struct FallbackProvider {
   float* qs;
   __device__ void begin(int row, void* extra) {
     qs = reinterpret_cast<float*>(extra);
-    if (overflow[row] == 2) for (int t = threadIdx.x; t < d; t += blockDim.x) qs[t] = q[(long long)row * d + t];
+    if (overflow[row] != 0) for (int t = threadIdx.x; t < d; t += blockDim.x) qs[t] = q[(long long)row * d + t];
   }
-  __device__ long long count(int row) const { return overflow[row] == 2 ? N : 0; }
+  __device__ long long count(int row) const { return overflow[row] != 0 ? N : 0; }
   __device__ void get(int, long long t, float& s, long long& i) const {
     const float* c = corpus + t * d;
     float acc = 0.f;
@@ -736,7 +771,7 @@ tc_count_fallback_kernel(const float* __restrict__ q, const float* __restrict__ 
   __shared__ float qs[128];
   __shared__ int total;
   const int row = blockIdx.x;
-  if (overflow[row] != 2) return;
+  if (overflow[row] == 0) return;
   for (int t = threadIdx.x; t < d; t += 256) qs[t] = q[(long long)row * d + t];
   if (threadIdx.x == 0) total = 0;
   __syncthreads();
@@ -779,7 +814,7 @@ static void prof_mark(cudaStream_t st, int stage) {
 
 struct Plan {
   int kb, stages; long long n_tiles; int nqb; long long Qp;
-  int stride, n_sample, group, bins_per_part, n_bins, bins_ld, parts_sample, parts_full, cap_part;
+  int stride, n_sample, group, bins_per_part, n_bins, bins_ld, parts_sample, parts_full, cap_part, cap_keys, cap_band;
   size_t smem;
   // workspace offsets
   size_t o_qimg, o_margin, o_cut, o_thr, o_qexp, o_count, o_ovf, o_binmax, o_cand, o_tmp, total;
@@ -820,9 +855,17 @@ static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
     pl.bins_ld = (pl.n_bins + 31) / 32 * 32;
   }
   {
-    int cp = 2 * CAND_CAP / (pl.parts_full * 2);  // octet records: (part, column-half) segments add up to ~2x the per-query capacity
-    int p2 = 32; while (p2 * 2 <= cp && p2 < 512) p2 <<= 1;   // 32..512 records per segment
+    // octet records per (part, column-half) segment: expected lambda = k * stride / segments (the threshold sits near rank
+    // 1.2 k / sampled fraction, ~0.8 records per survivor); capacity = 2 lambda + 12 sqrt(lambda) + 8, a power of two in 32..512
+    const double lambda = (double)k * pl.stride / (pl.parts_full * 2.0);
+    const double want = 2.0 * lambda + 12.0 * sqrt(lambda) + 8.0;
+    int p2 = 32; while (p2 < want && p2 < 512) p2 <<= 1;
     pl.cap_part = p2;
+    // finalize capacities per query: ~1.3 k * stride survivors are expected (+60 %), the re-scored band holds ~k + the
+    // candidates within 2 eps of tau
+    int ck = 1024; while (ck < 1.6 * 1.3 * k * pl.stride && ck < 4096) ck <<= 1;
+    pl.cap_keys = ck;
+    pl.cap_band = k <= 128 ? 512 : 1024;
   }
   pl.smem = (size_t)(2 + pl.stages) * pl.kb * SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   size_t o = 0;
@@ -866,14 +909,9 @@ static int launch_scan_mode(const Plan& pl, const ScanParams& sp, cudaStream_t s
 template <int MODE>
 static int launch_finalize(FinParams fp, cudaStream_t st) {
   auto kern = tc_finalize_kernel<MODE>;
-  const size_t big = FW_WARPS * fin_warp_bytes(FW_KEYS_BIG, FW_BAND_BIG);
-  TFRS_DYN_SMEM(kern, (int)big);
+  TFRS_DYN_SMEM(kern, (int)(FW_WARPS * fin_warp_bytes(4096, 1024)));
   const unsigned grid = (unsigned)ceil_div(fp.Q, FW_WARPS);
-  fp.cap_keys = FW_KEYS_SMALL; fp.cap_band = FW_BAND_SMALL; fp.pass = 0;
-  kern<<<grid, FW_WARPS * 32, FW_WARPS * fin_warp_bytes(FW_KEYS_SMALL, FW_BAND_SMALL), st>>>(fp);
-  TFRS_LAUNCH_CHECK();
-  fp.cap_keys = FW_KEYS_BIG; fp.cap_band = FW_BAND_BIG; fp.pass = 1;   // rows that overflowed the first try (none, normally)
-  kern<<<grid, FW_WARPS * 32, big, st>>>(fp);
+  kern<<<grid, FW_WARPS * 32, FW_WARPS * fin_warp_bytes(fp.cap_keys, fp.cap_band), st>>>(fp);
   TFRS_LAUNCH_CHECK();
   return TFRS_OK;
 }
@@ -941,6 +979,7 @@ static int run_call(const Call& c) {
   fp.q = c.q; fp.corpus = c.corpus; fp.d = c.d; fp.k = c.k; fp.index_offset = c.index_offset; fp.N = c.N; fp.Q = c.Q;
   fp.count = count; fp.cand_s = cand_s; fp.cand_i = cand_i; fp.segs = pl.parts_full * 2; fp.cap_part = pl.cap_part;
   fp.cut = cut; fp.thr = thr; fp.overflow = ovf; fp.out_s = c.out_s; fp.out_i = c.out_i;
+  fp.cap_keys = pl.cap_keys; fp.cap_band = pl.cap_band;
   fp.identifiers = c.identifiers; fp.exclusions = c.exclusions; fp.n_excl = c.n_excl; fp.k_out = c.k_out;
   fp.pos = c.pos; fp.qexp = qexp; fp.hdr = hdr; fp.out_count = c.out_count;
   if (c.mode == FIN_TOPK) rc = launch_finalize<FIN_TOPK>(fp, st);

@@ -57,6 +57,9 @@ class _SharedMean(Mean):
       self._owner._acc[self._slot] = 0.0
       if self._slot == 0:
         self._owner._acc[-1] = 0.0
+    self._owner._acc_host = None
+    if self._slot == 0:
+      self._owner._unsorted = None
 
   reset_state = reset_states
 
