@@ -13,18 +13,21 @@ namespace tfrs {
 constexpr int AG_TILE = 8192;       // keys per CTA tile (64 KB of shared memory)
 constexpr int AG_THREADS = 1024;
 constexpr unsigned long long AG_INVALID = ~0ull;
+constexpr unsigned long long AG_BAD_ID = 0xFFFFFFFFFFull;   // out-of-range ids sort last and are skipped by ag_apply
+
+template <typename IdT>
+__device__ __forceinline__ unsigned long long ag_key(const IdT* __restrict__ ids, long long j, long long rows) {
+  const long long r = (long long)ids[j];
+  return (((r >= 0 && r < rows) ? (unsigned long long)r : AG_BAD_ID) << 24) | (unsigned long long)j;
+}
+
 
 template <typename IdT>
 __global__ void ag_build_keys(const IdT* __restrict__ ids, long long n, long long rows, long long P,
                               unsigned long long* __restrict__ keys) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
-  unsigned long long k = AG_INVALID;
-  if (i < n) {
-    long long r = (long long)ids[i];
-    if (r >= 0 && r < rows) k = ((unsigned long long)r << 24) | (unsigned long long)i;
-  }
-  keys[i] = k;
+  keys[i] = i < n ? ag_key(ids, i, rows) : AG_INVALID;   // padding (~0) and out-of-range ids (AG_BAD_ID) sort last
 }
 
 __device__ __forceinline__ void ag_cmpswap(unsigned long long& a, unsigned long long& b, bool asc) {
@@ -57,36 +60,37 @@ ag_bitonic_local(unsigned long long* __restrict__ keys, long long P, long long f
   for (int t = threadIdx.x; t < tile; t += AG_THREADS) keys[base + t] = sk[t];
 }
 
-// n <= AG_SINGLE: keys are built and fully sorted by ONE CTA in shared memory (one launch instead of build + tile sorts
-// + global merge stages); the batch sizes of the training step (cfg3: 16384 ids) take this path.
-constexpr int AG_SINGLE = 16384;   // 128 KB of 64-bit keys
+// n <= AG_RANK_MAX: all-pairs RANK sort.  Keys are unique (the position is part of the key), so the sorted slot of a
+// key is the number of keys below it: every thread owns one key and counts over a quarter of the batch staged through
+// shared memory; the partial counts meet in rank[] (integer atomics: order-independent).  n^2 = 2.7e8 comparisons at the
+// training step's batch (cfg3: 16384 ids) keep the whole chip busy for ~30 us in ONE wave, where the bitonic network
+// needs ~100 barrier-separated stages on two CTAs.
+constexpr int AG_RANK_MAX = 16384;
+constexpr int AR_THREADS = 128, AR_TILE = 1024, AR_SPLIT = 4;
 template <typename IdT>
-__global__ void __launch_bounds__(AG_THREADS)
-ag_sort_single(const IdT* __restrict__ ids, long long n, long long rows, int P, unsigned long long* __restrict__ keys) {
-  extern __shared__ unsigned long long sk[];
-  for (int i = threadIdx.x; i < P; i += AG_THREADS) {
-    unsigned long long k = AG_INVALID;
-    if (i < n) {
-      const long long r = (long long)ids[i];
-      if (r >= 0 && r < rows) k = ((unsigned long long)r << 24) | (unsigned long long)i;
-    }
-    sk[i] = k;
+__global__ void __launch_bounds__(AR_THREADS)
+ag_rank_count(const IdT* __restrict__ ids, long long n, long long rows, unsigned int* __restrict__ rank) {
+  __shared__ unsigned long long tile[AR_TILE];
+  const long long i = (long long)blockIdx.x * AR_THREADS + threadIdx.x;
+  const unsigned long long mine = i < n ? ag_key(ids, i, rows) : ~0ull;
+  const long long per = (n + AR_SPLIT - 1) / AR_SPLIT;
+  const long long j_lo = (long long)blockIdx.y * per, j_hi = min(n, j_lo + per);
+  unsigned int r = 0;
+  for (long long j0 = j_lo; j0 < j_hi; j0 += AR_TILE) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < AR_TILE; t += AR_THREADS) tile[t] = (j0 + t < j_hi) ? ag_key(ids, j0 + t, rows) : ~0ull;
+    __syncthreads();
+#pragma unroll 16
+    for (int t = 0; t < AR_TILE; ++t) r += (tile[t] < mine) ? 1u : 0u;   // padding (~0) is never below a key
   }
-  __syncthreads();
-  for (int size = 2; size <= P; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = threadIdx.x; t < (P >> 1); t += AG_THREADS) {
-        const int lo = 2 * t - (t & (stride - 1));
-        const int hi = lo + stride;
-        const bool asc = ((lo & size) == 0);
-        unsigned long long a = sk[lo], b = sk[hi];
-        ag_cmpswap(a, b, asc);
-        sk[lo] = a; sk[hi] = b;
-      }
-      __syncthreads();
-    }
-  }
-  for (int i = threadIdx.x; i < P; i += AG_THREADS) keys[i] = sk[i];
+  if (i < n && r) atomicAdd(&rank[i], r);
+}
+
+template <typename IdT>
+__global__ void ag_rank_scatter(const IdT* __restrict__ ids, long long n, long long rows, const unsigned int* __restrict__ rank,
+                                unsigned long long* __restrict__ keys) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[rank[i]] = ag_key(ids, i, rows);
 }
 
 __global__ void ag_bitonic_global(unsigned long long* __restrict__ keys, long long P, long long size, long long stride) {
@@ -100,27 +104,109 @@ __global__ void ag_bitonic_global(unsigned long long* __restrict__ keys, long lo
   keys[lo] = a; keys[hi] = b;
 }
 
+// One warp per run of equal ids (the warp of the run's first slot; the others exit).  Duplicates are summed in order of
+// occurrence -- the keys are sorted by (id, position) -- with the gradient rows of 8 members in flight per step, so a hot
+// id's chain costs one DRAM round trip per 8 members instead of two per member.  Runs longer than AG_LONG members are left
+// to ag_apply_long (a whole CTA stages their rows through shared memory).
+constexpr int AG_LONG = 64;
+__device__ __forceinline__ void ag_update(float* __restrict__ trow, float* __restrict__ arow, int c, float g, float lr, float eps, int eps_inside) {
+  const float a = __fadd_rn(arow[c], __fmul_rn(g, g));
+  arow[c] = a;
+  const float den = eps_inside ? __fsqrt_rn(__fadd_rn(a, eps)) : __fadd_rn(__fsqrt_rn(a), eps);
+  trow[c] = __fsub_rn(trow[c], __fdiv_rn(__fmul_rn(lr, g), den));
+}
+
 __global__ void __launch_bounds__(256)
 ag_apply(const unsigned long long* __restrict__ keys, long long n, const float* __restrict__ grad, int d,
-         float* __restrict__ table, float* __restrict__ accum, float lr, float eps, int eps_inside) {
+         float* __restrict__ table, float* __restrict__ accum, float lr, float eps, int eps_inside,
+         unsigned int* __restrict__ long_count, unsigned int* __restrict__ long_list) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per sorted slot
   const int lane = threadIdx.x & 31;
   if (i >= n) return;
   const unsigned long long key = keys[i];
-  if (key == AG_INVALID) return;
   const unsigned long long id = key >> 24;
+  if (id == AG_BAD_ID) return;
   if (i > 0 && (keys[i - 1] >> 24) == id) return;  // not the head of its run
+  // run length: ballots over 32-slot windows
   long long end = i + 1;
-  while (end < n && (keys[end] >> 24) == id) ++end;
+  for (;;) {
+    const long long j = end + lane;
+    const bool same = j < n && (keys[j] >> 24) == id;
+    const unsigned int vote = __ballot_sync(0xffffffffu, same);
+    const int run = __ffs(~vote) - 1;          // leading members of this window (32 when all match: ~vote == 0 -> ffs 0 -> -1)
+    if (vote == 0xffffffffu) { end += 32; if (end - i > AG_LONG) break; continue; }
+    end += run;
+    break;
+  }
+  if (end - i > AG_LONG) {   // hot id: hand the run to the CTA-wide kernel
+    if (lane == 0) long_list[atomicAdd(long_count, 1u)] = (unsigned int)i;
+    return;
+  }
   float* trow = table + (long long)id * d;
   float* arow = accum + (long long)id * d;
+  const int L = (int)(end - i);
   for (int c = lane; c < d; c += 32) {
-    float g = grad[(long long)(key & 0xFFFFFFull) * d + c];
-    for (long long j = i + 1; j < end; ++j) g = __fadd_rn(g, grad[(long long)(keys[j] & 0xFFFFFFull) * d + c]);
-    float a = __fadd_rn(arow[c], __fmul_rn(g, g));
-    arow[c] = a;
-    float den = eps_inside ? __fsqrt_rn(__fadd_rn(a, eps)) : __fadd_rn(__fsqrt_rn(a), eps);
-    trow[c] = __fsub_rn(trow[c], __fdiv_rn(__fmul_rn(lr, g), den));
+    float g = 0.f;
+    for (int m0 = 0; m0 < L; m0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v[u] = (m0 + u < L) ? __ldg(grad + (long long)(keys[i + m0 + u] & 0xFFFFFFull) * d + c) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (m0 + u < L) g = (m0 + u == 0) ? v[u] : __fadd_rn(g, v[u]);
+    }
+    ag_update(trow, arow, c, g, lr, eps, eps_inside);
+  }
+}
+
+// Hot ids (Zipf batches: one id can own a tenth of the batch): one CTA per long run.  All 256 threads stream the run's
+// gradient rows into a shared-memory tile (AL_ROWS rows in flight per step), then one thread per column adds the tile's
+// rows IN ORDER -- the chain is fp32 adds on shared memory, not DRAM round trips.
+constexpr int AL_THREADS = 256, AL_ROWS = 64;   // rows per tile: min(AL_ROWS, 64 KB / row bytes)
+__global__ void __launch_bounds__(AL_THREADS)
+ag_apply_long(const unsigned long long* __restrict__ keys, long long n, const float* __restrict__ grad, int d,
+              float* __restrict__ table, float* __restrict__ accum, float lr, float eps, int eps_inside,
+              const unsigned int* __restrict__ long_count, const unsigned int* __restrict__ long_list, int tile_rows) {
+  extern __shared__ float al_tile[];   // [tile_rows][d]
+  __shared__ long long run_end;
+  for (unsigned int w = blockIdx.x; w < *long_count; w += gridDim.x) {
+    const long long i = long_list[w];
+    const unsigned long long id = keys[i] >> 24;
+    if (threadIdx.x == 0) {
+      long long e = i + 1;
+      while (e < n && (keys[e] >> 24) == id) ++e;   // sorted keys, sequential reads: cheap next to the row traffic
+      run_end = e;
+    }
+    __syncthreads();
+    const long long end = run_end;
+    float acc_g[4];   // a thread owns columns threadIdx.x + 256*u (d <= 1024)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc_g[u] = 0.f;
+    for (long long m0 = i; m0 < end; m0 += tile_rows) {
+      const int rows_here = (int)min((long long)tile_rows, end - m0);
+      for (int e = threadIdx.x; e < rows_here * d; e += AL_THREADS) {
+        const int r = e / d, c = e - r * d;
+        al_tile[e] = __ldg(grad + (long long)(keys[m0 + r] & 0xFFFFFFull) * d + c);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = threadIdx.x + AL_THREADS * u;
+        if (c < d) {
+          float g = acc_g[u];
+          for (int r = 0; r < rows_here; ++r) g = (m0 == i && r == 0) ? al_tile[c] : __fadd_rn(g, al_tile[r * d + c]);
+          acc_g[u] = g;
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = threadIdx.x + AL_THREADS * u;
+      if (c < d) ag_update(table + (long long)id * d, accum + (long long)id * d, c, acc_g[u], lr, eps, eps_inside);
+    }
+    __syncthreads();
   }
 }
 
@@ -131,7 +217,8 @@ using namespace tfrs;
 
 extern "C" size_t tfrs_sparse_adagrad_workspace_bytes(int64_t n, int d) {
   (void)d;
-  return (size_t)ag_pow2(n > 2 ? n : 2) * 8 + 256;
+  const size_t P = (size_t)ag_pow2(n > 2 ? n : 2);
+  return P * 8 /*keys*/ + P * 4 /*ranks*/ + (P / AG_LONG + 2) * 4 /*long-run list*/ + 1024;
 }
 
 extern "C" int tfrs_sparse_adagrad_f32(float* table, float* accum, int64_t rows, int d, const void* ids,
@@ -143,22 +230,37 @@ extern "C" int tfrs_sparse_adagrad_f32(float* table, float* accum, int64_t rows,
   TFRS_CHECK_ARG(rows < (1ll << 40), "sparse_adagrad: rows must be < 2^40");
   if (n == 0) return TFRS_OK;
   TFRS_CHECK_ARG(ids && grad_rows, "sparse_adagrad: NULL ids/grad");
+  TFRS_CHECK_ARG(d <= 1024, "sparse_adagrad: d=%d > 1024", d);
   const long long P = ag_pow2(n > 2 ? n : 2);
-  if (!ws || ws_bytes < (size_t)P * 8) { set_error("sparse_adagrad: workspace too small"); return TFRS_ERR_WORKSPACE_TOO_SMALL; }
+  if (!ws || ws_bytes < tfrs_sparse_adagrad_workspace_bytes(n, d)) { set_error("sparse_adagrad: workspace too small"); return TFRS_ERR_WORKSPACE_TOO_SMALL; }
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* keys = (unsigned long long*)ws;
-  if (P <= AG_SINGLE) {
-    if (ids_dtype == TFRS_I32) {
-      TFRS_DYN_SMEM(ag_sort_single<int32_t>, AG_SINGLE * 8);
-      ag_sort_single<int32_t><<<1, AG_THREADS, (size_t)P * 8, st>>>((const int32_t*)ids, n, rows, (int)P, keys);
-    } else {
-      TFRS_DYN_SMEM(ag_sort_single<int64_t>, AG_SINGLE * 8);
-      ag_sort_single<int64_t><<<1, AG_THREADS, (size_t)P * 8, st>>>((const int64_t*)ids, n, rows, (int)P, keys);
-    }
+  unsigned int* rank = (unsigned int*)(keys + P);
+  unsigned int* long_count = rank + P;
+  unsigned int* long_list = long_count + 1;
+  auto apply = [&]() -> int {
+    TFRS_CUDA(cudaMemsetAsync(long_count, 0, 4, st));
+    ag_apply<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(keys, n, grad_rows, d, table, accum, lr, eps, eps_inside_sqrt, long_count, long_list);
     TFRS_LAUNCH_CHECK();
-    ag_apply<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(keys, n, grad_rows, d, table, accum, lr, eps, eps_inside_sqrt);
+    int tile_rows = (64 * 1024) / (d * 4); if (tile_rows > AL_ROWS) tile_rows = AL_ROWS; if (tile_rows < 1) tile_rows = 1;
+    TFRS_DYN_SMEM(ag_apply_long, 64 * 1024);
+    ag_apply_long<<<(unsigned)sm_count(), AL_THREADS, (size_t)tile_rows * d * 4, st>>>(keys, n, grad_rows, d, table, accum, lr, eps, eps_inside_sqrt,
+                                                                                       long_count, long_list, tile_rows);
     TFRS_LAUNCH_CHECK();
     return TFRS_OK;
+  };
+  if (n <= AG_RANK_MAX) {
+    TFRS_CUDA(cudaMemsetAsync(rank, 0, (size_t)n * 4, st));
+    const dim3 grid((unsigned)ceil_div(n, AR_THREADS), AR_SPLIT);
+    if (ids_dtype == TFRS_I32) {
+      ag_rank_count<int32_t><<<grid, AR_THREADS, 0, st>>>((const int32_t*)ids, n, rows, rank);
+      ag_rank_scatter<int32_t><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((const int32_t*)ids, n, rows, rank, keys);
+    } else {
+      ag_rank_count<int64_t><<<grid, AR_THREADS, 0, st>>>((const int64_t*)ids, n, rows, rank);
+      ag_rank_scatter<int64_t><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((const int64_t*)ids, n, rows, rank, keys);
+    }
+    TFRS_LAUNCH_CHECK(); count_launch(1);
+    return apply();
   }
   unsigned kb = (unsigned)ceil_div(P, 256);
   if (ids_dtype == TFRS_I32) ag_build_keys<int32_t><<<kb, 256, 0, st>>>((const int32_t*)ids, n, rows, P, keys);
@@ -177,7 +279,5 @@ extern "C" int tfrs_sparse_adagrad_f32(float* table, float* accum, int64_t rows,
     ag_bitonic_local<<<tiles, AG_THREADS, AG_TILE * 8, st>>>(keys, P, size, size);
     TFRS_LAUNCH_CHECK();
   }
-  ag_apply<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(keys, n, grad_rows, d, table, accum, lr, eps, eps_inside_sqrt);
-  TFRS_LAUNCH_CHECK();
-  return TFRS_OK;
+  return apply();
 }

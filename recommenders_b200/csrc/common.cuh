@@ -63,6 +63,10 @@ struct DeviceOnce {
     static ::tfrs::DeviceOnce once__;                                                                             \
     if (once__.need()) {                                                                                          \
       TFRS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));         \
+      /* without the carve-out hint the driver sizes the L1/shared split for ONE block of this kernel, which caps   \
+         multi-block-per-SM kernels (the warp-per-query finalize) at one resident block */                          \
+      TFRS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,                        \
+                                     (int)cudaSharedmemCarveoutMaxShared));                                         \
       once__.done();                                                                                              \
     }                                                                                                             \
   } while (0)

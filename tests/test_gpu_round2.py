@@ -286,3 +286,30 @@ def test_compile_then_fit_trains_lazily_built_cross():
   assert not torch.equal(model.cross.kernel.detach(), k0), "Cross.kernel was never updated"
   assert not torch.equal(model.mlcn.u_kernels[0].detach(), u0) and not torch.equal(model.emb.weight, e0)
   assert float(out["loss"]) < l0
+
+
+# ------------------------------------------------------------------------------------------------
+# sparse Adagrad: rank sort + long runs (hot ids of a Zipf batch) stay bit-exact
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,rows,d,kind", [(16384, 5, 64, "uniform"), (16384, 1_000_000, 64, "zipf"), (9000, 50000, 32, "zipf"),
+                                           (16384, 10_000_000, 64, "uniform"), (40000, 1000, 16, "zipf"), (3000, 7, 200, "uniform")])
+def test_sparse_adagrad_hot_ids_bit_exact(ops, n, rows, d, kind):
+  rng = np.random.RandomState(n + d)
+  if kind == "zipf":
+    ids = np.minimum(rng.zipf(1.05, size=n) - 1, rows - 1).astype(np.int64)
+  else:
+    ids = rng.randint(0, rows, size=n).astype(np.int64)
+  ids[::97] = -1 if n > 5000 else ids[::97]            # out-of-range ids are skipped
+  used = np.unique(ids[ids >= 0])
+  table_rows = int(min(rows, 200_000))                   # keep the host copy small: remap ids into a compact table
+  remap = {int(v): j for j, v in enumerate(used)} if rows > table_rows else None
+  if remap is not None:
+    ids = np.array([remap[int(v)] if v >= 0 else -1 for v in ids], np.int64)
+  table = rng.uniform(-0.05, 0.05, size=(table_rows, d)).astype(np.float32)
+  acc = np.full((table_rows, d), 0.1, np.float32)
+  g = (rng.normal(size=(n, d)) * 0.01).astype(np.float32)
+  et, ea = orc.sparse_adagrad(table, acc, ids, g, 0.5)
+  tt = torch.from_numpy(table).cuda(); ta = torch.from_numpy(acc).cuda()
+  ops.sparse_adagrad_(tt, ta, torch.from_numpy(ids).cuda(), torch.from_numpy(g).cuda(), 0.5)
+  np.testing.assert_array_equal(tt.cpu().numpy().view(np.uint32), et.view(np.uint32))
+  np.testing.assert_array_equal(ta.cpu().numpy().view(np.uint32), ea.view(np.uint32))

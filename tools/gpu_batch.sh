@@ -24,6 +24,8 @@ for what in "$@"; do
     softmax)  step softmax_launches 150 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file "$out/launches_softmax.csv" python tools/softmax_probe.py 16384 64 2 ;;
     cross)    step cross_probe 200 python tools/cross_probe.py; step cross_launches 150 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file "$out/launches_cross.csv" python tools/cross_step_probe.py 2 ;;
     ncu)      step ncu_launches 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$out/launches_bench.csv" python bench.py --steps 3 --warmup 3 --no-secondary --no-cpu-baseline ;;
+    ncufin)   step ncu_fin 300 ncu --set full --clock-control none --import-source on -k regex:tc_finalize -s 3 -c 1 -f -o "$out/prof_finalize" python bench.py --steps 2 --warmup 3 --no-secondary --no-cpu-baseline ;;
+    ncuscan)  step ncu_scan 300 ncu --set full --clock-control none --import-source on -k regex:tc_scan -s 6 -c 2 -f -o "$out/prof_scan" python bench.py --steps 2 --warmup 3 --no-secondary --no-cpu-baseline ;;
     *) echo "unknown step $what" ;;
   esac
 done
