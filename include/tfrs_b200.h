@@ -181,6 +181,15 @@ typedef struct tfrs_comm* tfrs_comm_t;
 int tfrs_comm_unique_id(void* out128);
 int tfrs_comm_create(tfrs_comm_t* comm, int rank, int world, const void* unique_id128);
 int tfrs_comm_destroy(tfrs_comm_t comm);
+/* Optional: map every rank's exchange buffer into every peer (cudaIpc over NVLink / NVSwitch), sized for calls up to
+ * (max_Q, max_k).  Collective; synchronises the device.  With it tfrs_topk_sharded_f32 replaces the NCCL all-gather +
+ * replicated merge by its own kernels: every rank STORES the slice of its lists owned by rank o straight into o's buffer
+ * (owner = contiguous block of ceil(Q / world) queries), owners merge only their block and store the result into every
+ * rank's result area, epoch flags order the steps -- 1/world of the all-gather's NVLink traffic and of the merge work.
+ * Returns TFRS_ERR_UNSUPPORTED on EVERY rank when any peer mapping fails (the NCCL path stays in use).
+ * tfrs_comm_p2p_capacity: 1 when the mapped buffers hold a (Q, k) call. */
+int tfrs_comm_enable_p2p(tfrs_comm_t comm, int64_t max_Q, int max_k);
+int tfrs_comm_p2p_capacity(tfrs_comm_t comm, int64_t Q, int k);
 int tfrs_comm_rank(tfrs_comm_t comm);
 int tfrs_comm_world(tfrs_comm_t comm);
 int tfrs_topk_allgather(tfrs_comm_t comm, const float* s, const int64_t* i, int64_t Q, int k, float* all_s,

@@ -83,10 +83,134 @@ __global__ void fill_pad_kernel(float* __restrict__ s, long long* __restrict__ i
 }  // namespace
 }  // namespace tfrs
 
+constexpr int TFRS_MAX_RANKS = 16;
 struct tfrs_comm {
   tfrs::ncclComm_t comm;
   int rank, world, device;
+  // peer-memory exchange (tfrs_comm_enable_p2p): xbuf[r] = rank r's exchange buffer as mapped into THIS process
+  // (cudaIpc over NVLink/NVSwitch; xbuf[rank] is the local allocation)
+  unsigned char* xbuf[TFRS_MAX_RANKS];
+  size_t xbytes;
+  unsigned int epoch;
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// Peer-memory exchange: the collective of the sharded scan as our own kernels over NVLink P2P stores.
+//
+// NCCL's all-gather moves every rank's whole [Q,k] list to every rank (world x 4.9 MB received at cfg2) and every rank
+// then merges all Q queries.  Here query q has an OWNER rank (contiguous blocks of Qo = ceil(Q / world) queries):
+//   A. every rank stores the slice of its local lists that belongs to owner o straight into o's exchange buffer
+//      (st.global on the IPC-mapped peer pointer) and raises flagA[src] there            -> (world-1)/world of ONE list leaves a rank
+//   B. the owner merges the world sorted lists of its Qo queries (tfrs_topk_merge_sorted_strided on local memory)
+//   C. the owner stores its final [Qo,k] block into every rank's result area and raises flagB[owner] there
+//   D. every rank waits for the world flagB's and copies the result area to the caller's buffers
+// 8x less NVLink traffic and 8x less merge work per rank than all-gather + replicated merge.  Flags are call epochs
+// (monotone, never reset); data -> __threadfence_system() -> flag on the writer, flag -> fence -> data on the reader.
+// A buffer is only overwritten by call e+1 after its readers of call e have finished: writers of step A(e+1) have passed
+// their own D(e), which needs the owner's C(e), which follows the owner's B(e) reads; writers of C(e+1) have passed
+// B(e+1)'s wait on every rank's A(e+1), which follows that rank's D(e) reads.
+// ---------------------------------------------------------------------------------------------------------------
+namespace tfrs {
+namespace {
+constexpr size_t XFLAGS = 8192;                 // flagA[r] at 128*r, flagB[r] at 4096 + 128*r, block counters at the end
+struct XLayout { long long Qo; size_t a_s, a_i, b_s, b_i, total; };
+XLayout x_layout(int world, long long Q, int k) {
+  XLayout L;
+  L.Qo = (Q + world - 1) / world;
+  size_t o = XFLAGS;
+  auto take = [&](size_t b) { size_t r = o; o += align_up(b, 256); return r; };
+  L.a_s = take((size_t)world * L.Qo * k * 4);
+  L.a_i = take((size_t)world * L.Qo * k * 8);
+  L.b_s = take((size_t)world * L.Qo * k * 4);   // result area, padded to world * Qo rows
+  L.b_i = take((size_t)world * L.Qo * k * 8);
+  L.total = o;
+  return L;
+}
+
+struct PeerPtrs { unsigned char* p[TFRS_MAX_RANKS]; };
+
+__device__ __forceinline__ void spin_until(const volatile unsigned int* flag, unsigned int epoch) {
+  const long long t0 = clock64();
+  while ((int)(*flag - epoch) < 0) {            // wrap-safe "flag < epoch"
+    if (clock64() - t0 > 20000000000ll) __trap();   // ~10 s: a peer died -- fail loudly instead of hanging the GPU
+    __nanosleep(64);
+  }
+}
+
+// the last CTA of a grid to get here raises this rank's flag in every peer's buffer
+__device__ __forceinline__ void signal_when_grid_done(PeerPtrs peers, int world, size_t flag_off, int rank, unsigned int epoch,
+                                                      unsigned int* counter) {
+  __threadfence_system();            // this CTA's peer stores are ordered before its arrival
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(counter, 1u);
+    last = (prev == gridDim.x - 1);
+    if (last) *counter = 0;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    if ((int)threadIdx.x < world)
+      *reinterpret_cast<volatile unsigned int*>(peers.p[threadIdx.x] + flag_off + 128 * rank) = epoch;
+  }
+}
+
+// A: owner o gets rows [o*Qo, (o+1)*Qo) of this rank's local lists, at list slot `rank` of its area A
+__global__ void __launch_bounds__(256)
+x_scatter_kernel(PeerPtrs peers, int world, int rank, const float* __restrict__ loc_s, const long long* __restrict__ loc_i,
+                 long long Q, int k, XLayout L, unsigned int epoch) {
+  const long long per_owner16 = L.Qo * k * 12 / 4;   // in 4-byte words: scores (1 word) + indices (2 words) per entry
+  (void)per_owner16;
+  for (int o = 0; o < world; ++o) {
+    const long long q0 = (long long)o * L.Qo, q1 = min(Q, q0 + L.Qo);
+    if (q1 <= q0) continue;
+    const long long n = (q1 - q0) * k;
+    float* ds = reinterpret_cast<float*>(peers.p[o] + L.a_s) + (long long)rank * L.Qo * k;
+    long long* di = reinterpret_cast<long long*>(peers.p[o] + L.a_i) + (long long)rank * L.Qo * k;
+    const float* ss = loc_s + q0 * k; const long long* si = loc_i + q0 * k;
+    for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < n; t += (long long)gridDim.x * 256) { ds[t] = ss[t]; di[t] = si[t]; }
+  }
+  signal_when_grid_done(peers, world, 0, rank, epoch, reinterpret_cast<unsigned int*>(peers.p[rank] + XFLAGS - 128));
+}
+
+__global__ void x_wait_kernel(const unsigned char* local, size_t flag_off, int world, unsigned int epoch) {
+  if ((int)threadIdx.x < world) spin_until(reinterpret_cast<const volatile unsigned int*>(local + flag_off + 128 * threadIdx.x), epoch);
+  __threadfence_system();
+}
+
+// C: this owner's merged [Qo_mine, k] block (already in its own result area) -> every other rank's result area
+__global__ void __launch_bounds__(256)
+x_bcast_kernel(PeerPtrs peers, int world, int rank, long long Q, int k, XLayout L, unsigned int epoch) {
+  const long long q0 = (long long)rank * L.Qo, q1 = min(Q, q0 + L.Qo);
+  const long long n = q1 > q0 ? (q1 - q0) * k : 0;
+  const float* ss = reinterpret_cast<const float*>(peers.p[rank] + L.b_s) + q0 * k;
+  const long long* si = reinterpret_cast<const long long*>(peers.p[rank] + L.b_i) + q0 * k;
+  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < n; t += (long long)gridDim.x * 256) {
+    const float v = ss[t]; const long long ix = si[t];
+    for (int o = 0; o < world; ++o) {
+      if (o == rank) continue;
+      reinterpret_cast<float*>(peers.p[o] + L.b_s)[q0 * k + t] = v;
+      reinterpret_cast<long long*>(peers.p[o] + L.b_i)[q0 * k + t] = ix;
+    }
+  }
+  signal_when_grid_done(peers, world, 4096, rank, epoch, reinterpret_cast<unsigned int*>(peers.p[rank] + XFLAGS - 64));
+}
+
+// D: wait for every owner's block, then hand the result area to the caller's buffers
+__global__ void __launch_bounds__(256)
+x_collect_kernel(const unsigned char* local, int world, long long Q, int k, XLayout L, unsigned int epoch, float* __restrict__ out_s,
+                 long long* __restrict__ out_i) {
+  if ((int)threadIdx.x < world) spin_until(reinterpret_cast<const volatile unsigned int*>(local + 4096 + 128 * threadIdx.x), epoch);
+  __threadfence_system();
+  __syncthreads();
+  const float* ss = reinterpret_cast<const float*>(local + L.b_s);
+  const long long* si = reinterpret_cast<const long long*>(local + L.b_i);
+  const long long n = Q * k;
+  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < n; t += (long long)gridDim.x * 256) { out_s[t] = ss[t]; out_i[t] = si[t]; }
+}
+}  // namespace
+}  // namespace tfrs
 
 using namespace tfrs;
 
@@ -119,12 +243,82 @@ extern "C" int tfrs_comm_create(tfrs_comm_t* out, int rank, int world, const voi
   return TFRS_OK;
 }
 
+static void x_release(tfrs_comm* c) {
+  for (int r = 0; r < c->world && r < TFRS_MAX_RANKS; ++r) {
+    if (!c->xbuf[r]) continue;
+    if (r == c->rank) cudaFree(c->xbuf[r]); else cudaIpcCloseMemHandle(c->xbuf[r]);
+    c->xbuf[r] = nullptr;
+  }
+  c->xbytes = 0;
+}
+
 extern "C" int tfrs_comm_destroy(tfrs_comm_t c) {
   if (!c) return TFRS_OK;
+  cudaDeviceSynchronize();
+  x_release(c);
   NcclApi* a = nccl_api();
   if (a && c->comm) a->CommDestroy(c->comm);
   delete c;
   return TFRS_OK;
+}
+
+// Collective over the group: (re)allocates the exchange buffers for calls up to (max_Q, max_k) and maps every peer's
+// buffer into this process (cudaIpc; the handles travel through one NCCL all-gather).  Synchronises the device.
+extern "C" int tfrs_comm_enable_p2p(tfrs_comm_t c, int64_t max_Q, int max_k) {
+  TFRS_CHECK_ARG(c && max_Q > 0 && max_k > 0, "comm_enable_p2p: bad argument");
+  if (c->world > TFRS_MAX_RANKS) { set_error("comm_enable_p2p: world=%d > %d", c->world, TFRS_MAX_RANKS); return TFRS_ERR_UNSUPPORTED; }
+  NcclApi* a = nccl_api();
+  if (!a) { set_error("comm: NCCL is not available"); return TFRS_ERR_NCCL; }
+  TFRS_CUDA(cudaDeviceSynchronize());
+  x_release(c);
+  const XLayout L = x_layout(c->world, max_Q, max_k);
+  void* local = nullptr;
+  TFRS_CUDA(cudaMalloc(&local, L.total));
+  TFRS_CUDA(cudaMemset(local, 0, L.total));
+  cudaIpcMemHandle_t mine;
+  TFRS_CUDA(cudaIpcGetMemHandle(&mine, local));
+  cudaIpcMemHandle_t* dev = nullptr;
+  TFRS_CUDA(cudaMalloc((void**)&dev, sizeof(cudaIpcMemHandle_t) * (c->world + 1)));
+  TFRS_CUDA(cudaMemcpy(dev + c->world, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+  TFRS_NCCL(a->AllGather(dev + c->world, dev, sizeof(cudaIpcMemHandle_t), NCCL_UINT8, c->comm, (cudaStream_t)0));
+  TFRS_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t all[TFRS_MAX_RANKS];
+  TFRS_CUDA(cudaMemcpy(all, dev, sizeof(cudaIpcMemHandle_t) * c->world, cudaMemcpyDeviceToHost));
+  cudaFree(dev);
+  c->xbuf[c->rank] = (unsigned char*)local;
+  c->xbytes = L.total;
+  c->epoch = 0;
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) continue;
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      set_error("comm_enable_p2p: cudaIpcOpenMemHandle(rank %d) -> %s", r, cudaGetErrorString(e));
+      c->xbuf[r] = nullptr;
+      // every rank must agree on the outcome: the all-reduce below tells the others
+    } else {
+      c->xbuf[r] = (unsigned char*)p;
+    }
+  }
+  // agree: if ANY rank failed to map a peer, every rank falls back to the NCCL path
+  int* ok_dev = nullptr;
+  TFRS_CUDA(cudaMalloc((void**)&ok_dev, 8));
+  int ok = 1;
+  for (int r = 0; r < c->world; ++r) if (!c->xbuf[r]) ok = 0;
+  float okf = ok ? 0.f : 1.f;   // max over ranks of "failed"
+  TFRS_CUDA(cudaMemcpy(ok_dev, &okf, 4, cudaMemcpyHostToDevice));
+  if (a->AllReduce) TFRS_NCCL(a->AllReduce(ok_dev, ok_dev + 1, 1, NCCL_FLOAT32, NCCL_MAX, c->comm, (cudaStream_t)0));
+  TFRS_CUDA(cudaDeviceSynchronize());
+  float failed = 1.f;
+  TFRS_CUDA(cudaMemcpy(&failed, ok_dev + 1, 4, cudaMemcpyDeviceToHost));
+  cudaFree(ok_dev);
+  if (failed != 0.f) { x_release(c); if (ok) set_error("comm_enable_p2p: a peer could not map the exchange buffers"); return TFRS_ERR_UNSUPPORTED; }
+  return TFRS_OK;
+}
+
+extern "C" int tfrs_comm_p2p_capacity(tfrs_comm_t c, int64_t Q, int k) {
+  if (!c || !c->xbytes || Q <= 0 || k <= 0) return 0;
+  return x_layout(c->world, Q, k).total <= c->xbytes ? 1 : 0;
 }
 
 extern "C" int tfrs_comm_rank(tfrs_comm_t c) { return c ? c->rank : -1; }
@@ -205,6 +399,30 @@ extern "C" int tfrs_topk_sharded_f32(tfrs_comm_t c, const float* q, int64_t Q, c
     if (rc == TFRS_ERR_UNSUPPORTED)
       rc = tfrs_topk_scan_f32(q, Q, corpus_local, N_local, d, k, index_offset, nullptr, nullptr, 0, send_s, (int64_t*)send_i, w, L.scan, st);
     if (rc) return rc;
+  }
+  if (c->xbytes && x_layout(c->world, Q, k).total <= c->xbytes) {
+    // peer-memory exchange: scatter to the owners -> owners merge their block -> owners store the results everywhere
+    const XLayout X = x_layout(c->world, Q, k);
+    PeerPtrs peers{};
+    for (int r = 0; r < c->world; ++r) peers.p[r] = c->xbuf[r];
+    const unsigned int epoch = ++c->epoch;
+    unsigned char* local = c->xbuf[c->rank];
+    const unsigned grid = (unsigned)(sm_count() < 64 ? sm_count() : 64);
+    x_scatter_kernel<<<grid, 256, 0, st>>>(peers, c->world, c->rank, send_s, send_i, Q, k, X, epoch);
+    TFRS_LAUNCH_CHECK();
+    x_wait_kernel<<<1, 32, 0, st>>>(local, 0, c->world, epoch);
+    TFRS_LAUNCH_CHECK();
+    const long long q0 = (long long)c->rank * X.Qo, q1 = Q < q0 + X.Qo ? Q : q0 + X.Qo;
+    if (q1 > q0) {
+      int rc = tfrs_topk_merge_sorted_strided((const float*)(local + X.a_s), (const int64_t*)(local + X.a_i), X.Qo * k, X.Qo * k, c->world,
+                                              q1 - q0, k, k, (float*)(local + X.b_s) + q0 * k, (int64_t*)(local + X.b_i) + q0 * k, st);
+      if (rc) return rc;
+    }
+    x_bcast_kernel<<<grid, 256, 0, st>>>(peers, c->world, c->rank, Q, k, X, epoch);
+    TFRS_LAUNCH_CHECK();
+    x_collect_kernel<<<grid, 256, 0, st>>>(local, c->world, Q, k, X, epoch, out_scores, (long long*)out_idx);
+    TFRS_LAUNCH_CHECK();
+    return TFRS_OK;
   }
   TFRS_NCCL(a->AllGather(send, recv, L.block, NCCL_UINT8, c->comm, st));
   count_launch(1);

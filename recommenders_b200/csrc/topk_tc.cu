@@ -413,9 +413,9 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 // k-th largest of the keys a warp holds in registers (KPL per lane, unused slots = 0 = below every float key):
 // bitwise binary search for the largest v with #{key >= v} >= k, one REDUX.SUM per bit.
 template <int KPL>
-__device__ __forceinline__ unsigned int warp_kth_largest_regs(const unsigned int (&key)[KPL], int k) {
-  unsigned int prefix = 0;
-  for (int bit = 31; bit >= 0; --bit) {
+__device__ __forceinline__ unsigned int warp_kth_largest_regs(const unsigned int (&key)[KPL], int k, unsigned int prefix = 0, int top_bit = 31) {
+  // `prefix` = the bits above top_bit, known to be shared by every real key (unused slots are 0 and never reach it)
+  for (int bit = top_bit; bit >= 0; --bit) {
     const unsigned int cand = prefix | (1u << bit);
     int c = 0;
 #pragma unroll
@@ -426,12 +426,11 @@ __device__ __forceinline__ unsigned int warp_kth_largest_regs(const unsigned int
   return prefix;
 }
 // the same over n keys in shared memory
-__device__ __forceinline__ unsigned int warp_kth_largest_smem(const unsigned int* keys, int n, int k, int lane) {
-  unsigned int prefix = 0;
-  for (int bit = 31; bit >= 0; --bit) {
+__device__ __forceinline__ unsigned int warp_kth_largest_smem(const unsigned long long* ks, int n, int k, int lane, unsigned int prefix, int top_bit) {
+  for (int bit = top_bit; bit >= 0; --bit) {
     const unsigned int cand = prefix | (1u << bit);
     int c = 0;
-    for (int t = lane; t < n; t += 32) c += (keys[t] >= cand) ? 1 : 0;
+    for (int t = lane; t < n; t += 32) c += ((unsigned int)(ks[t] >> 32) >= cand) ? 1 : 0;
     c = __reduce_add_sync(0xffffffffu, c);
     if (c >= k) prefix = cand;
   }
@@ -458,16 +457,17 @@ tc_threshold_kernel(const float* __restrict__ binmax, int bins_ld, int n_bins, i
 // (3) finalize: one WARP per query, no block-wide barriers.
 enum { FIN_TOPK = 0, FIN_EXCLUDE = 1, FIN_COUNT = 2 };
 constexpr int FW_WARPS = 4;                       // queries per CTA
-constexpr int FW_SOFF = 304;                      // >= FIN_MAX_PARTS + 1 segment offsets
 // Capacities per query come from the plan (they grow with k); a row that overflows them takes the exact fallback.
 // overflow[row]: 0 = done, 1 = exact fallback
-static size_t fin_warp_bytes(int cap_keys, int cap_band) { return (size_t)cap_keys * 8 + (size_t)cap_band * 8 + FW_SOFF * 4 + 512; }
+__host__ __device__ inline size_t fin_warp_bytes_dev(int cap_keys, int segs, int d) {
+  return (size_t)cap_keys * 8 + (size_t)((segs + 1 + 3) & ~3) * 4 + (size_t)((d + 3) & ~3) * 4;
+}
 
 struct FinParams {
   const float* q; const float* corpus; int d; int k; long long index_offset; long long N; long long Q;
   const unsigned int* count; const float* cand_s; const unsigned int* cand_i; int segs; int cap_part;
   const float* cut; const float* thr; unsigned int* overflow;
-  int cap_keys, cap_band;                        // per-query capacities of the survivor / band lists (shared memory)
+  int cap_keys;                                  // survivors per query held in shared memory; the band holds cap_keys / 2
   float* out_s; long long* out_i;                // TOPK: [Q, k];  EXCLUDE: [Q, k_out]
   // EXCLUDE (k = k_out + n_excl candidates are fetched, then re-ranked)
   const long long* identifiers; const long long* exclusions; int n_excl; int k_out;
@@ -553,6 +553,8 @@ __device__ __forceinline__ void exclude_rerank(const unsigned long long* srt, in
   }
 }
 
+// Shared memory per warp: ks[cap_keys] (screening key << 32 | local index; the band is compacted IN PLACE at its
+// front, EXCLUDE parks the k best in its upper half) | soff[segs + 1] | qs[d].  cap_band = cap_keys / 2.
 template <int MODE>
 __global__ void __launch_bounds__(FW_WARPS * 32)
 tc_finalize_kernel(const FinParams p) {
@@ -560,14 +562,13 @@ tc_finalize_kernel(const FinParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * FW_WARPS + warp;
   if (row >= p.Q) return;
-  const unsigned int retry_flag = 1u;                    // every failure mode ends in the exact fallback
-  unsigned char* base = fsm + (size_t)warp * ((size_t)p.cap_keys * 8 + (size_t)p.cap_band * 8 + FW_SOFF * 4 + 512);
-  unsigned int* keys = reinterpret_cast<unsigned int*>(base);                           // [cap_keys] screening keys
-  unsigned int* sidx = keys + p.cap_keys;                                                // [cap_keys] local indices
-  unsigned long long* band = reinterpret_cast<unsigned long long*>(sidx + p.cap_keys);   // [cap_band]
-  int* soff = reinterpret_cast<int*>(band + p.cap_band);                                 // [segs + 1]
-  float* qs = reinterpret_cast<float*>(soff + FW_SOFF);                                  // [d]
+  unsigned char* base = fsm + (size_t)warp * fin_warp_bytes_dev(p.cap_keys, p.segs, p.d);
+  unsigned long long* ks = reinterpret_cast<unsigned long long*>(base);                  // [cap_keys]
+  int* soff = reinterpret_cast<int*>(ks + p.cap_keys);                                    // [segs + 1]
+  float* qs = reinterpret_cast<float*>(soff + ((p.segs + 1 + 3) & ~3));                   // [d]
+  unsigned long long* band = ks;
   const unsigned int lt_mask = (1u << lane) - 1u;
+  const unsigned int n32 = (unsigned int)p.N;   // N < 2^31
 
   // segment counts -> exclusive prefix
   int carry = 0; bool bad = false;
@@ -599,13 +600,14 @@ tc_finalize_kernel(const FinParams p) {
     const float eps = 0.5f * p.cut[row];
     const float pos = p.pos[row];
     const float pos_s = ldexpf(pos, p.hdr->st.exp + p.qexp[row]);
+    const float hi = pos_s + eps, lo_b = pos_s - eps;
     int definite = 0, m = 0;
     for (int rb = 0; rb < total_rec; rb += 32) {
       const int rec = rb + lane;
       unsigned int ix0 = 0, amb = 0; int cnt = 0;
       if (rec < total_rec) {
-        int lo = 0, hi = p.segs;
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (soff[mid] <= rec) lo = mid; else hi = mid; }
+        int lo = 0, hi_s = p.segs;
+        while (hi_s - lo > 1) { const int mid = (lo + hi_s) >> 1; if (soff[mid] <= rec) lo = mid; else hi_s = mid; }
         const long long at = (row * p.segs + lo) * p.cap_part + (rec - soff[lo]);
         ix0 = __ldg(p.cand_i + at);
         const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.cand_s + at * 8));
@@ -613,22 +615,25 @@ tc_finalize_kernel(const FinParams p) {
         const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          if ((unsigned long long)(ix0 + j) < (unsigned long long)p.N) {
-            if (sc[j] > pos_s + eps) ++definite;
-            else if (sc[j] > pos_s - eps) { amb |= 1u << j; ++cnt; }
-          }
+          const bool real = ix0 + j < n32;
+          definite += (real && sc[j] > hi) ? 1 : 0;
+          const bool a = real && sc[j] > lo_b && !(sc[j] > hi);
+          amb |= a ? (1u << j) : 0u; cnt += a ? 1 : 0;
         }
       }
       const int incl = warp_incl_scan(cnt, lane);
-      int at_pos = m + incl - cnt;
+      const int tot = __shfl_sync(0xffffffffu, incl, 31);
+      if (m + tot <= p.cap_keys) {
+        int at_pos = m + incl - cnt;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (amb & (1u << j)) { if (at_pos < p.cap_band) band[at_pos] = (unsigned long long)(ix0 + j); ++at_pos; }
-      m += __shfl_sync(0xffffffffu, incl, 31);
+        for (int j = 0; j < 8; ++j)
+          if (amb & (1u << j)) { band[at_pos] = (unsigned long long)(ix0 + j); ++at_pos; }
+      }
+      m += tot;
     }
     definite = __reduce_add_sync(0xffffffffu, definite);
     if (definite >= p.k) { if (lane == 0) { p.out_count[row] = p.k; p.overflow[row] = 0; } return; }
-    if (m > p.cap_band) { if (lane == 0) p.overflow[row] = retry_flag; return; }
+    if (m > p.cap_keys) { if (lane == 0) p.overflow[row] = 1; return; }
     __syncwarp();
     int greater = 0;
     for (int t = lane; t < m; t += 32)
@@ -638,8 +643,9 @@ tc_finalize_kernel(const FinParams p) {
     return;
   }
 
-  // ---- TOPK / EXCLUDE: survivors (score >= filter threshold, real row) -> keys/sidx
+  // ---- TOPK / EXCLUDE: survivors (score >= filter threshold, real row) -> ks
   int n = 0;
+  unsigned int kmax = 0u, kmin = 0xFFFFFFFFu;
   for (int rb = 0; rb < total_rec; rb += 32) {
     const int rec = rb + lane;
     float sc[8]; unsigned int ix0 = 0, keep = 0; int cnt = 0;
@@ -652,42 +658,68 @@ tc_finalize_kernel(const FinParams p) {
       const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.cand_s + at * 8) + 1);
       sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (sc[j] >= thr_row && (unsigned long long)(ix0 + j) < (unsigned long long)p.N) { keep |= 1u << j; ++cnt; }
+      for (int j = 0; j < 8; ++j) {
+        const bool kp = sc[j] >= thr_row && ix0 + j < n32;
+        keep |= kp ? (1u << j) : 0u; cnt += kp ? 1 : 0;
+      }
     }
     const int incl = warp_incl_scan(cnt, lane);
-    int at_pos = n + incl - cnt;
+    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+    if (n + tot <= p.cap_keys) {   // warp-uniform: the stores below need no per-entry bound check
+      int at_pos = n + incl - cnt;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (keep & (1u << j)) { if (at_pos < p.cap_keys) { keys[at_pos] = f2key(sc[j]); sidx[at_pos] = ix0 + j; } ++at_pos; }
-    n += __shfl_sync(0xffffffffu, incl, 31);
+      for (int j = 0; j < 8; ++j) {
+        if (keep & (1u << j)) {
+          const unsigned int key = f2key(sc[j] + 0.0f);   // -0 -> +0: key order == float order
+          kmax = max(kmax, key); kmin = min(kmin, key);
+          ks[at_pos] = ((unsigned long long)key << 32) | (unsigned long long)(ix0 + j);
+          ++at_pos;
+        }
+      }
+    }
+    n += tot;
   }
-  if (n > p.cap_keys) { if (lane == 0) p.overflow[row] = retry_flag; return; }
-  if (n < p.k) { if (lane == 0) p.overflow[row] = 1; return; }
+  if (n > p.cap_keys || n < p.k) { if (lane == 0) p.overflow[row] = 1; return; }
   __syncwarp();
-  // tau = k-th best screening score; keep the survivors inside its error band
+  // tau = k-th best screening score: bitwise search below the bits the largest and the smallest key share
+  kmax = __reduce_max_sync(0xffffffffu, kmax); kmin = __reduce_min_sync(0xffffffffu, kmin);
   unsigned int tau_key;
-  if (n <= 1024) {   // the usual case: this lane's <= 32 keys live in registers, no shared-memory traffic in the 32-step search
-    unsigned int kr[32];
+  {
+    const unsigned int diff = kmax ^ kmin;
+    const int top = diff ? (31 - __clz(diff)) : -1;           // highest bit in which the survivors differ
+    const unsigned int prefix0 = top >= 31 ? 0u : (top < 0 ? kmax : (kmax & ~((2u << top) - 1u)));   // top == -1: all keys equal
+    if (n <= 512) {
+      unsigned int kr[16];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { const int t = j * 32 + lane; kr[j] = t < n ? keys[t] : 0u; }
-    tau_key = warp_kth_largest_regs<32>(kr, p.k);
-  } else {
-    tau_key = warp_kth_largest_smem(keys, n, p.k, lane);
+      for (int j = 0; j < 16; ++j) { const int t = j * 32 + lane; kr[j] = t < n ? (unsigned int)(ks[t] >> 32) : 0u; }
+      tau_key = warp_kth_largest_regs<16>(kr, p.k, prefix0, top);
+    } else if (n <= 1024) {
+      unsigned int kr[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { const int t = j * 32 + lane; kr[j] = t < n ? (unsigned int)(ks[t] >> 32) : 0u; }
+      tau_key = warp_kth_largest_regs<32>(kr, p.k, prefix0, top);
+    } else {
+      tau_key = warp_kth_largest_smem(ks, n, p.k, lane, prefix0, top);
+    }
   }
   const float lim = key2f(tau_key) - p.cut[row];
   // Self-check that makes the threshold choice a pure performance matter: the whole band [lim, inf) must
   // lie above the filter threshold, otherwise survivors could be missing -> exact fallback.
   if (!(lim >= thr_row) || !(lim > -INFINITY)) { if (lane == 0) p.overflow[row] = 1; return; }
+  // band = survivors with screening score >= lim, compacted in place (write position <= read position)
+  const unsigned int lim_key = f2key(lim + 0.0f);
   int m = 0;
   for (int tb = 0; tb < n; tb += 32) {
     const int t = tb + lane;
-    const bool keep = t < n && key2f(keys[t]) >= lim;
+    const unsigned long long e = t < n ? ks[t] : 0ull;
+    const bool keep = t < n && (unsigned int)(e >> 32) >= lim_key;
     const unsigned int vote = __ballot_sync(0xffffffffu, keep);
-    if (keep) { const int at_pos = m + __popc(vote & lt_mask); if (at_pos < p.cap_band) band[at_pos] = (unsigned long long)sidx[t]; }
+    __syncwarp();                     // every lane has read its entry of this chunk before any lane overwrites the chunk
+    if (keep) band[m + __popc(vote & lt_mask)] = e;
     m += __popc(vote);
   }
-  if (m > p.cap_band) { if (lane == 0) p.overflow[row] = retry_flag; return; }  // band too crowded (massive ties)
+  const int cap_band = p.cap_keys >> 1;
+  if (m > cap_band) { if (lane == 0) p.overflow[row] = 1; return; }  // band too crowded (massive ties)
   __syncwarp();
   // exact re-scoring; band[t] becomes the composite key (score desc, index asc) == larger is better
   for (int t = lane; t < m; t += 64) {   // two candidates per lane in flight: twice the loads per DRAM round trip
@@ -701,7 +733,7 @@ tc_finalize_kernel(const FinParams p) {
   }
   __syncwarp();
   // rank sort: every lane ranks up to 4 own entries per sweep over the band (broadcast reads); ranks are unique
-  unsigned long long* srt = reinterpret_cast<unsigned long long*>(keys);  // EXCLUDE: the k best in order (keys/sidx are dead)
+  unsigned long long* srt = ks + cap_band;  // EXCLUDE: the k best in order (upper half: never touched by the band)
   for (int t0 = 0; t0 < m; t0 += 128) {
     unsigned long long mine[4]; int rank[4];
 #pragma unroll
@@ -726,7 +758,7 @@ tc_finalize_kernel(const FinParams p) {
   }
   if (MODE == FIN_EXCLUDE) {
     __syncwarp();
-    exclude_rerank(srt, p.k, band, row, p, lane);   // band (>= k words) is dead after the ranking
+    exclude_rerank(srt, p.k, band, row, p, lane);   // the band (>= k words) is dead after the ranking
   }
   if (lane == 0) p.overflow[row] = 0;
 }
@@ -864,8 +896,8 @@ static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
     // finalize capacities per query: ~1.3 k * stride survivors are expected (+60 %), the re-scored band holds ~k + the
     // candidates within 2 eps of tau
     int ck = 1024; while (ck < 1.6 * 1.3 * k * pl.stride && ck < 4096) ck <<= 1;
-    pl.cap_keys = ck;
-    pl.cap_band = k <= 128 ? 512 : 1024;
+    pl.cap_keys = ck;                 // the re-scored band holds cap_keys / 2 >= 512 entries (~k + the candidates within 2 eps of tau)
+    pl.cap_band = ck / 2;
   }
   pl.smem = (size_t)(2 + pl.stages) * pl.kb * SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   size_t o = 0;
@@ -909,9 +941,9 @@ static int launch_scan_mode(const Plan& pl, const ScanParams& sp, cudaStream_t s
 template <int MODE>
 static int launch_finalize(FinParams fp, cudaStream_t st) {
   auto kern = tc_finalize_kernel<MODE>;
-  TFRS_DYN_SMEM(kern, (int)(FW_WARPS * fin_warp_bytes(4096, 1024)));
+  TFRS_DYN_SMEM(kern, (int)(FW_WARPS * fin_warp_bytes_dev(4096, FIN_MAX_PARTS, 128)));
   const unsigned grid = (unsigned)ceil_div(fp.Q, FW_WARPS);
-  kern<<<grid, FW_WARPS * 32, FW_WARPS * fin_warp_bytes(fp.cap_keys, fp.cap_band), st>>>(fp);
+  kern<<<grid, FW_WARPS * 32, FW_WARPS * fin_warp_bytes_dev(fp.cap_keys, fp.segs, fp.d), st>>>(fp);
   TFRS_LAUNCH_CHECK();
   return TFRS_OK;
 }
@@ -979,7 +1011,7 @@ static int run_call(const Call& c) {
   fp.q = c.q; fp.corpus = c.corpus; fp.d = c.d; fp.k = c.k; fp.index_offset = c.index_offset; fp.N = c.N; fp.Q = c.Q;
   fp.count = count; fp.cand_s = cand_s; fp.cand_i = cand_i; fp.segs = pl.parts_full * 2; fp.cap_part = pl.cap_part;
   fp.cut = cut; fp.thr = thr; fp.overflow = ovf; fp.out_s = c.out_s; fp.out_i = c.out_i;
-  fp.cap_keys = pl.cap_keys; fp.cap_band = pl.cap_band;
+  fp.cap_keys = pl.cap_keys;
   fp.identifiers = c.identifiers; fp.exclusions = c.exclusions; fp.n_excl = c.n_excl; fp.k_out = c.k_out;
   fp.pos = c.pos; fp.qexp = qexp; fp.hdr = hdr; fp.out_count = c.out_count;
   if (c.mode == FIN_TOPK) rc = launch_finalize<FIN_TOPK>(fp, st);

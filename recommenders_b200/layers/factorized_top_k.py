@@ -116,6 +116,22 @@ class ShardComm:
     self._handle = ctypes.c_void_p()
     raw = (ctypes.c_char * 128).from_buffer_copy(box[0])
     _ffi.check(_ffi.lib().tfrs_comm_create(ctypes.byref(self._handle), self.rank, self.world, raw), "comm_create")
+    self.p2p = self.world > 1   # peer-memory exchange (NVLink stores + epoch flags) instead of the NCCL all-gather
+
+  def ensure_p2p(self, Q: int, k: int) -> bool:
+    """Maps the exchange buffers for (Q, k) calls if they are not big enough yet (collective: all ranks see the same
+    Q, k and therefore take the same decision).  False -> the NCCL all-gather path is used."""
+    from .. import _ffi
+    if not self.p2p:
+      return False
+    if _ffi.lib().tfrs_comm_p2p_capacity(self._handle, Q, k):
+      return True
+    rc = _ffi.lib().tfrs_comm_enable_p2p(self._handle, max(Q, 1024), max(k, 16))
+    if rc == -2:          # some peer cannot be mapped: every rank got the same answer
+      self.p2p = False
+      return False
+    _ffi.check(rc, "comm_enable_p2p")
+    return True
 
   @property
   def handle(self):

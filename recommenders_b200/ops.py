@@ -234,6 +234,7 @@ def topk_sharded(comm, q: torch.Tensor, corpus_local: torch.Tensor, index_buf: O
   Q, d = q.shape; N = corpus_local.shape[0]
   out_s = torch.empty((Q, k), dtype=torch.float32, device=q.device)
   out_i = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+  comm.ensure_p2p(Q, k)
   wsb = lib().tfrs_topk_sharded_workspace_bytes(comm.world, Q, N, d, k)
   ws = workspace(wsb + 1024, q.device, "sharded")
   check(lib().tfrs_topk_sharded_f32(comm.handle, ptr(q), Q, ptr(corpus_local), ptr(index_buf), N, d, k, index_offset,
