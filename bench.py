@@ -360,7 +360,10 @@ def main():
                    "l2": "inputs (fp16 image 128 MB + fp32 corpus 256 MB per 1M rows) exceed the 126 MB L2 between steps; "
                          f"{NQ} query batches rotate",
                    "parallelism": f"corpus-shard x{world}",
-                   "collective": "tfrs_topk_sharded_f32: one ncclAllGather issued by libtfrs_b200.so" if world > 1 else None},
+                   "collective": (None if world == 1 else
+                                  ("tfrs_topk_sharded_f32: peer-memory exchange (NVLink P2P stores to the owner rank, owner merges 1/N of the "
+                                   "queries, stores the result to every rank; epoch flags)" if getattr(layer._shard[1], "p2p", False) else
+                                   "tfrs_topk_sharded_f32: one ncclAllGather issued by libtfrs_b200.so + replicated merge"))},
         "clocks": sampler.summary() if sampler is not None else None,
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": Q * d * 4, "d2h_bytes_per_step": Q * k * 8,
                 "ms_per_step": float(ms2) / args.steps},

@@ -8,6 +8,7 @@ exact rescoring).  Results follow tf.math.top_k's contract: scores descending, t
 from __future__ import annotations
 
 import abc
+import os
 from typing import Dict, Optional, Text, Tuple, Union
 
 import numpy as np
@@ -116,7 +117,8 @@ class ShardComm:
     self._handle = ctypes.c_void_p()
     raw = (ctypes.c_char * 128).from_buffer_copy(box[0])
     _ffi.check(_ffi.lib().tfrs_comm_create(ctypes.byref(self._handle), self.rank, self.world, raw), "comm_create")
-    self.p2p = self.world > 1   # peer-memory exchange (NVLink stores + epoch flags) instead of the NCCL all-gather
+    # peer-memory exchange (NVLink stores + epoch flags) instead of the NCCL all-gather; TFRS_SHARD_EXCHANGE=nccl keeps NCCL
+    self.p2p = self.world > 1 and os.environ.get("TFRS_SHARD_EXCHANGE", "p2p").lower() != "nccl"
 
   def ensure_p2p(self, Q: int, k: int) -> bool:
     """Maps the exchange buffers for (Q, k) calls if they are not big enough yet (collective: all ranks see the same

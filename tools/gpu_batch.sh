@@ -26,6 +26,10 @@ for what in "$@"; do
     ncu)      step ncu_launches 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$out/launches_bench.csv" python bench.py --steps 3 --warmup 3 --no-secondary --no-cpu-baseline ;;
     ncufin)   step ncu_fin 300 ncu --set full --clock-control none --import-source on -k regex:tc_finalize -s 3 -c 1 -f -o "$out/prof_finalize" python bench.py --steps 2 --warmup 3 --no-secondary --no-cpu-baseline ;;
     ncuscan)  step ncu_scan 300 ncu --set full --clock-control none --import-source on -k regex:tc_scan -s 6 -c 2 -f -o "$out/prof_scan" python bench.py --steps 2 --warmup 3 --no-secondary --no-cpu-baseline ;;
+    adagrad)  step adagrad_launches 120 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file "$out/launches_adagrad.csv" python tools/adagrad_probe.py 2; step adagrad_probe 60 python tools/adagrad_probe.py 20 ;;
+    benchn)   step bench_multi 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus ${NGPU:-2} --steps 30 --warmup 5 ;;
+    benchnccl) TFRS_SHARD_EXCHANGE=nccl step bench_multi_nccl 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus ${NGPU:-2} --steps 30 --warmup 5 ;;
+    benchn4)  step bench_multi_cfg4 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus ${NGPU:-2} --steps 10 --warmup 3 --workload cfg4 ;;
     *) echo "unknown step $what" ;;
   esac
 done
