@@ -168,26 +168,49 @@ __global__ void __launch_bounds__(AL_THREADS)
 ag_apply_long(const unsigned long long* __restrict__ keys, long long n, const float* __restrict__ grad, int d,
               float* __restrict__ table, float* __restrict__ accum, float lr, float eps, int eps_inside,
               const unsigned int* __restrict__ long_count, const unsigned int* __restrict__ long_list, int tile_rows) {
-  extern __shared__ float al_tile[];   // [tile_rows][d]
-  __shared__ long long run_end;
+  extern __shared__ __align__(16) float al_tile[];   // [tile_rows][d]
+  __shared__ unsigned int pos_sh[AL_ROWS];
   for (unsigned int w = blockIdx.x; w < *long_count; w += gridDim.x) {
     const long long i = long_list[w];
     const unsigned long long id = keys[i] >> 24;
-    if (threadIdx.x == 0) {
-      long long e = i + 1;
-      while (e < n && (keys[e] >> 24) == id) ++e;   // sorted keys, sequential reads: cheap next to the row traffic
-      run_end = e;
+    // run end: 256 sorted keys per step (the members form a contiguous prefix of every window)
+    long long end = i + 1;
+    for (;;) {
+      const long long j = end + threadIdx.x;
+      const int same = (j < n && (keys[j] >> 24) == id) ? 1 : 0;
+      const int cnt = __syncthreads_count(same);
+      end += cnt;
+      if (cnt < AL_THREADS) break;
     }
-    __syncthreads();
-    const long long end = run_end;
     float acc_g[4];   // a thread owns columns threadIdx.x + 256*u (d <= 1024)
 #pragma unroll
     for (int u = 0; u < 4; ++u) acc_g[u] = 0.f;
     for (long long m0 = i; m0 < end; m0 += tile_rows) {
       const int rows_here = (int)min((long long)tile_rows, end - m0);
-      for (int e = threadIdx.x; e < rows_here * d; e += AL_THREADS) {
-        const int r = e / d, c = e - r * d;
-        al_tile[e] = __ldg(grad + (long long)(keys[m0 + r] & 0xFFFFFFull) * d + c);
+      // the tile's gradient-row numbers first (one coalesced read), then every thread has 4 independent 16-byte row
+      // loads in flight: one DRAM round trip per tile instead of one per element
+      if ((int)threadIdx.x < rows_here) pos_sh[threadIdx.x] = (unsigned int)(keys[m0 + threadIdx.x] & 0xFFFFFFull);
+      __syncthreads();
+      if ((d & 3) == 0) {
+        const unsigned int d4 = (unsigned int)d >> 2, total4 = (unsigned int)rows_here * d4;
+        for (unsigned int e0 = threadIdx.x; e0 < total4; e0 += AL_THREADS * 4) {
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const unsigned int e = e0 + u * AL_THREADS;
+            if (e < total4) { const unsigned int r = e / d4, c4 = e - r * d4; v[u] = __ldg(reinterpret_cast<const float4*>(grad + (long long)pos_sh[r] * d) + c4); }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const unsigned int e = e0 + u * AL_THREADS;
+            if (e < total4) reinterpret_cast<float4*>(al_tile)[e] = v[u];
+          }
+        }
+      } else {
+        for (int e = threadIdx.x; e < rows_here * d; e += AL_THREADS) {
+          const int r = e / d, c = e - r * d;
+          al_tile[e] = __ldg(grad + (long long)pos_sh[r] * d + c);
+        }
       }
       __syncthreads();
 #pragma unroll

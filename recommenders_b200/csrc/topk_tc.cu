@@ -52,6 +52,7 @@ constexpr int HEADER_BYTES = 1024;
 constexpr int THREADS = 640;      // 4 control warps + 16 epilogue warps (4 per SM sub-partition)
 constexpr int EPI_WARPS = 16;
 constexpr int EPI_WARP0 = 4;
+constexpr int CAND_CAP = 2048;       // octet records kept per query across all segments (sizing of cap_part)
 constexpr int MAX_SAMPLE_STRIDE = 4;
 constexpr int FIN_MAX_PARTS = 2 * 148;  // survivor-list segments per query: (corpus part, column half)
 constexpr int MAX_BINS = 1024;       // bin maxima per query (32 per lane of the threshold warp)
@@ -206,11 +207,12 @@ struct ScanParams {
   // FILTER
   const float* thr;               // [Qp]
   unsigned int* count;            // [Qp, parts, 2]   records written by each (query, corpus part, half)
-  // Survivor ENTRIES (screening score, local index), 8 bytes each.  One private segment per (query row, corpus part,
-  // column half): a single writer thread, no atomics.  The hit path is rare and warp-uniform down to the octet; inside
-  // an octet that holds a survivor the lane appends exactly the columns that pass.
-  float2* cand;                   // [Qp, parts, 2, cap_part]  (score, __int_as_float(local index))
-  int cap_part;                   // entries per segment
+  // Survivor RECORDS: when any of 8 consecutive columns of a row passes the threshold, the whole octet is
+  // appended (two 16-byte stores + the index of its first column); finalize drops the non-survivors.
+  // One private segment per (query row, corpus part, column half): a single writer thread, no atomics.
+  float* cand_s;                  // [Qp, parts, 2, cap_part, 8] screening scores of the octet
+  unsigned int* cand_i;           // [Qp, parts, 2, cap_part]    local index of the octet's first column
+  int cap_part;                   // records per segment
   uint32_t idesc;
 };
 
@@ -302,10 +304,13 @@ tc_scan_kernel(const ScanParams p) {
     const bool row_ok = row < p.Q;
     float thr = INFINITY;
     if (MODE == MODE_FILTER && row_ok) thr = p.thr[row];
-    float2* my_e = nullptr;
+    float* my_s = nullptr; unsigned int* my_i = nullptr;
     unsigned int my_cnt = 0, my_ovf = 0;
     const unsigned int cap = (unsigned int)p.cap_part;
-    if (MODE == MODE_FILTER) my_e = p.cand + (((long long)row * p.parts + part) * 2 + half) * p.cap_part;
+    if (MODE == MODE_FILTER) {
+      const long long seg = (((long long)row * p.parts + part) * 2 + half) * p.cap_part;
+      my_s = p.cand_s + seg * 8; my_i = p.cand_i + seg;
+    }
     float binm = -INFINITY;
     int in_group = 0, bin_out = 0;
     float* my_bins = nullptr;
@@ -350,20 +355,18 @@ tc_scan_kernel(const ScanParams p) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) qmask |= (qmx[i] >= thr) ? (1u << i) : 0u;
               const unsigned int umask = __reduce_or_sync(0xffffffffu, qmask);
-              const bool room = my_cnt + 32u <= cap;   // worst case of this visit (all 32 columns) fits
+              const bool room = my_cnt + 4u <= cap;    // worst case of this visit (4 octets) fits
               my_ovf |= (!room && m >= thr) ? 1u : 0u;
               const unsigned int idx0 = (unsigned int)(col0 + h * 64 + c2 * 32);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 if (umask & (1u << i)) {             // uniform: some lane's octet i has a survivor
-                  if (room && qmx[i] >= thr) {       // per lane: append the columns of my octet that pass (predicated, no loop)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                      if (v[8 * i + j] >= thr) {
-                        my_e[my_cnt] = make_float2(v[8 * i + j], __uint_as_float(idx0 + 8 * i + j));
-                        ++my_cnt;
-                      }
-                    }
+                  if (room && qmx[i] >= thr) {       // per lane: append my whole octet (predicated, no loop)
+                    float4* dst = reinterpret_cast<float4*>(my_s + (size_t)my_cnt * 8);
+                    dst[0] = make_float4(v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3]);
+                    dst[1] = make_float4(v[8 * i + 4], v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
+                    my_i[my_cnt] = idx0 + 8 * i;
+                    ++my_cnt;
                   }
                 }
               }
@@ -462,7 +465,7 @@ __host__ __device__ inline size_t fin_warp_bytes_dev(int cap_keys, int segs, int
 
 struct FinParams {
   const float* q; const float* corpus; int d; int k; long long index_offset; long long N; long long Q;
-  const unsigned int* count; const float2* cand; int segs; int cap_part;
+  const unsigned int* count; const float* cand_s; const unsigned int* cand_i; int segs; int cap_part;
   const float* cut; const float* thr; unsigned int* overflow;
   int cap_keys;                                  // survivors per query held in shared memory; the band holds cap_keys / 2
   float* out_s; long long* out_i;                // TOPK: [Q, k];  EXCLUDE: [Q, k_out]
@@ -587,7 +590,7 @@ tc_finalize_kernel(const FinParams p) {
   }
   for (int t = lane; t < p.d; t += 32) qs[t] = p.q[row * p.d + t];
   __syncwarp();
-  const int total_rec = soff[p.segs];   // survivor entries of this query (every one scored >= the filter threshold)
+  const int total_rec = soff[p.segs];
   const float thr_row = p.thr[row];
 
   if (MODE == FIN_COUNT) {
@@ -599,21 +602,34 @@ tc_finalize_kernel(const FinParams p) {
     const float pos_s = ldexpf(pos, p.hdr->st.exp + p.qexp[row]);
     const float hi = pos_s + eps, lo_b = pos_s - eps;
     int definite = 0, m = 0;
-    for (int eb = 0; eb < total_rec; eb += 32) {
-      const int e = eb + lane;
-      bool amb = false; unsigned int ix = 0;
-      if (e < total_rec) {
+    for (int rb = 0; rb < total_rec; rb += 32) {
+      const int rec = rb + lane;
+      unsigned int ix0 = 0, amb = 0; int cnt = 0;
+      if (rec < total_rec) {
         int lo = 0, hi_s = p.segs;
-        while (hi_s - lo > 1) { const int mid = (lo + hi_s) >> 1; if (soff[mid] <= e) lo = mid; else hi_s = mid; }
-        const float2 v = __ldg(p.cand + (row * p.segs + lo) * p.cap_part + (e - soff[lo]));
-        ix = __float_as_uint(v.y);
-        const bool real = ix < n32;
-        definite += (real && v.x > hi) ? 1 : 0;
-        amb = real && v.x > lo_b && !(v.x > hi);
+        while (hi_s - lo > 1) { const int mid = (lo + hi_s) >> 1; if (soff[mid] <= rec) lo = mid; else hi_s = mid; }
+        const long long at = (row * p.segs + lo) * p.cap_part + (rec - soff[lo]);
+        ix0 = __ldg(p.cand_i + at);
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.cand_s + at * 8));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.cand_s + at * 8) + 1);
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool real = ix0 + j < n32;
+          definite += (real && sc[j] > hi) ? 1 : 0;
+          const bool a = real && sc[j] > lo_b && !(sc[j] > hi);
+          amb |= a ? (1u << j) : 0u; cnt += a ? 1 : 0;
+        }
       }
-      const unsigned int vote = __ballot_sync(0xffffffffu, amb);
-      if (amb && m + __popc(vote) <= p.cap_keys) band[m + __popc(vote & lt_mask)] = (unsigned long long)ix;
-      m += __popc(vote);
+      const int incl = warp_incl_scan(cnt, lane);
+      const int tot = __shfl_sync(0xffffffffu, incl, 31);
+      if (m + tot <= p.cap_keys) {
+        int at_pos = m + incl - cnt;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (amb & (1u << j)) { band[at_pos] = (unsigned long long)(ix0 + j); ++at_pos; }
+      }
+      m += tot;
     }
     definite = __reduce_add_sync(0xffffffffu, definite);
     if (definite >= p.k) { if (lane == 0) { p.out_count[row] = p.k; p.overflow[row] = 0; } return; }
@@ -630,22 +646,38 @@ tc_finalize_kernel(const FinParams p) {
   // ---- TOPK / EXCLUDE: survivors (score >= filter threshold, real row) -> ks
   int n = 0;
   unsigned int kmax = 0u, kmin = 0xFFFFFFFFu;
-  for (int eb = 0; eb < total_rec; eb += 32) {
-    const int e = eb + lane;
-    bool kp = false; unsigned long long entry = 0ull;
-    if (e < total_rec) {
-      int lo = 0, hi = p.segs;  // largest segment with soff[seg] <= e
-      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (soff[mid] <= e) lo = mid; else hi = mid; }
-      const float2 v = __ldg(p.cand + (row * p.segs + lo) * p.cap_part + (e - soff[lo]));
-      const unsigned int ix = __float_as_uint(v.y);
-      kp = ix < n32;                                   // zero-padded rows of the last corpus tile are not candidates
-      const unsigned int key = f2key(v.x + 0.0f);      // -0 -> +0: key order == float order
-      if (kp) { kmax = max(kmax, key); kmin = min(kmin, key); }
-      entry = ((unsigned long long)key << 32) | (unsigned long long)ix;
+  for (int rb = 0; rb < total_rec; rb += 32) {
+    const int rec = rb + lane;
+    float sc[8]; unsigned int ix0 = 0, keep = 0; int cnt = 0;
+    if (rec < total_rec) {
+      int lo = 0, hi = p.segs;  // largest segment with soff[seg] <= rec
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (soff[mid] <= rec) lo = mid; else hi = mid; }
+      const long long at = (row * p.segs + lo) * p.cap_part + (rec - soff[lo]);
+      ix0 = __ldg(p.cand_i + at);
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.cand_s + at * 8));
+      const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.cand_s + at * 8) + 1);
+      sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool kp = sc[j] >= thr_row && ix0 + j < n32;
+        keep |= kp ? (1u << j) : 0u; cnt += kp ? 1 : 0;
+      }
     }
-    const unsigned int vote = __ballot_sync(0xffffffffu, kp);
-    if (kp && n + __popc(vote) <= p.cap_keys) ks[n + __popc(vote & lt_mask)] = entry;
-    n += __popc(vote);
+    const int incl = warp_incl_scan(cnt, lane);
+    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+    if (n + tot <= p.cap_keys) {   // warp-uniform: the stores below need no per-entry bound check
+      int at_pos = n + incl - cnt;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (keep & (1u << j)) {
+          const unsigned int key = f2key(sc[j] + 0.0f);   // -0 -> +0: key order == float order
+          kmax = max(kmax, key); kmin = min(kmin, key);
+          ks[at_pos] = ((unsigned long long)key << 32) | (unsigned long long)(ix0 + j);
+          ++at_pos;
+        }
+      }
+    }
+    n += tot;
   }
   if (n > p.cap_keys || n < p.k) { if (lane == 0) p.overflow[row] = 1; return; }
   __syncwarp();
@@ -855,11 +887,11 @@ static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
     pl.bins_ld = (pl.n_bins + 31) / 32 * 32;
   }
   {
-    // survivor entries per (part, column-half) segment: expected lambda = 1.3 k * stride / segments (the threshold sits
-    // near rank 1.2 k / sampled fraction); capacity = 2 lambda + 12 sqrt(lambda) + 32, a power of two in 64..1024
-    const double lambda = 1.3 * (double)k * pl.stride / (pl.parts_full * 2.0);
-    const double want = 2.0 * lambda + 12.0 * sqrt(lambda) + 32.0;
-    int p2 = 64; while (p2 < want && p2 < 1024) p2 <<= 1;
+    // octet records per (part, column-half) segment: expected lambda = k * stride / segments (the threshold sits near rank
+    // 1.2 k / sampled fraction, ~0.8 records per survivor); capacity = 2 lambda + 12 sqrt(lambda) + 8, a power of two in 32..512
+    const double lambda = (double)k * pl.stride / (pl.parts_full * 2.0);
+    const double want = 2.0 * lambda + 12.0 * sqrt(lambda) + 8.0;
+    int p2 = 32; while (p2 < want && p2 < 512) p2 <<= 1;
     pl.cap_part = p2;
     // finalize capacities per query: ~1.3 k * stride survivors are expected (+60 %), the re-scored band holds ~k + the
     // candidates within 2 eps of tau
@@ -878,7 +910,7 @@ static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
   pl.o_count = take((size_t)pl.Qp * pl.parts_full * 2 * 4);
   pl.o_ovf = take((size_t)pl.Qp * 4);
   pl.o_binmax = take((size_t)pl.Qp * pl.bins_ld * 4);
-  pl.o_cand = take((size_t)pl.Qp * pl.parts_full * 2 * pl.cap_part * 8);
+  pl.o_cand = take((size_t)pl.Qp * pl.parts_full * 2 * pl.cap_part * (8 * 4 + 4));
   pl.o_tmp = take((size_t)Q * k * 12);   // EXCLUDE: the exact fallback's [Q, k] lists before the re-ranking
   pl.total = o;
   return true;
@@ -944,7 +976,8 @@ static int run_call(const Call& c) {
   unsigned int* count = (unsigned int*)(w + pl.o_count);
   unsigned int* ovf = (unsigned int*)(w + pl.o_ovf);
   float* binmax = (float*)(w + pl.o_binmax);
-  float2* cand = (float2*)(w + pl.o_cand);
+  float* cand_s = (float*)(w + pl.o_cand);
+  unsigned int* cand_i = (unsigned int*)(w + pl.o_cand + (size_t)pl.Qp * pl.parts_full * 2 * pl.cap_part * 32);
   float* tmp_s = (float*)(w + pl.o_tmp);
   long long* tmp_i = (long long*)(w + pl.o_tmp + align_up((size_t)c.Q * c.k * 4, 8));
   const IndexHeader* hdr = (const IndexHeader*)c.index_buf;
@@ -957,7 +990,7 @@ static int run_call(const Call& c) {
   ScanParams sp{};
   sp.qimg = qimg; sp.cimg = cimg; sp.Q = c.Q; sp.N = c.N; sp.nqb = pl.nqb; sp.n_tiles = pl.n_tiles;
   sp.binmax = binmax; sp.bins_ld = pl.bins_ld; sp.group = pl.group; sp.bins_per_part = pl.bins_per_part;
-  sp.thr = thr; sp.count = count; sp.cand = cand; sp.cap_part = pl.cap_part;
+  sp.thr = thr; sp.count = count; sp.cand_s = cand_s; sp.cand_i = cand_i; sp.cap_part = pl.cap_part;
   sp.idesc = IDESC_F16_M128_N128;
   prof_mark(st, 1);
   // (1) sampled pass -> bin maxima -> k-th largest -> threshold
@@ -976,7 +1009,7 @@ static int run_call(const Call& c) {
   // (3) exact re-scoring + final order (a warp per query); (4) exact fallback for the rows that asked for it
   FinParams fp{};
   fp.q = c.q; fp.corpus = c.corpus; fp.d = c.d; fp.k = c.k; fp.index_offset = c.index_offset; fp.N = c.N; fp.Q = c.Q;
-  fp.count = count; fp.cand = cand; fp.segs = pl.parts_full * 2; fp.cap_part = pl.cap_part;
+  fp.count = count; fp.cand_s = cand_s; fp.cand_i = cand_i; fp.segs = pl.parts_full * 2; fp.cap_part = pl.cap_part;
   fp.cut = cut; fp.thr = thr; fp.overflow = ovf; fp.out_s = c.out_s; fp.out_i = c.out_i;
   fp.cap_keys = pl.cap_keys;
   fp.identifiers = c.identifiers; fp.exclusions = c.exclusions; fp.n_excl = c.n_excl; fp.k_out = c.k_out;
