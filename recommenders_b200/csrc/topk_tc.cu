@@ -426,11 +426,11 @@ __device__ __forceinline__ unsigned int warp_kth_largest_regs(const unsigned int
   return prefix;
 }
 // the same over n keys in shared memory
-__device__ __forceinline__ unsigned int warp_kth_largest_smem(const unsigned long long* ks, int n, int k, int lane, unsigned int prefix, int top_bit) {
+__device__ __forceinline__ unsigned int warp_kth_largest_smem(const unsigned int* keys, int n, int k, int lane, unsigned int prefix, int top_bit) {
   for (int bit = top_bit; bit >= 0; --bit) {
     const unsigned int cand = prefix | (1u << bit);
     int c = 0;
-    for (int t = lane; t < n; t += 32) c += ((unsigned int)(ks[t] >> 32) >= cand) ? 1 : 0;
+    for (int t = lane; t < n; t += 32) c += (keys[t] >= cand) ? 1 : 0;
     c = __reduce_add_sync(0xffffffffu, c);
     if (c >= k) prefix = cand;
   }
@@ -456,18 +456,16 @@ tc_threshold_kernel(const float* __restrict__ binmax, int bins_ld, int n_bins, i
 
 // (3) finalize: one WARP per query, no block-wide barriers.
 enum { FIN_TOPK = 0, FIN_EXCLUDE = 1, FIN_COUNT = 2 };
-constexpr int FW_WARPS = 4;                       // queries per CTA
+constexpr int FW_WARPS = 4;                       // queries per CTA of the fallback re-rank kernel
 // Capacities per query come from the plan (they grow with k); a row that overflows them takes the exact fallback.
 // overflow[row]: 0 = done, 1 = exact fallback
-__host__ __device__ inline size_t fin_warp_bytes_dev(int cap_keys, int segs, int d) {
-  return (size_t)cap_keys * 8 + (size_t)((segs + 1 + 3) & ~3) * 4 + (size_t)((d + 3) & ~3) * 4;
-}
 
 struct FinParams {
   const float* q; const float* corpus; int d; int k; long long index_offset; long long N; long long Q;
   const unsigned int* count; const float* cand_s; const unsigned int* cand_i; int segs; int cap_part;
   const float* cut; const float* thr; unsigned int* overflow;
-  int cap_keys;                                  // survivors per query held in shared memory; the band holds cap_keys / 2
+  int cap_keys, cap_band;                        // survivors per query (keys in shared memory) / band entries re-scored exactly
+  unsigned int* band_idx; int* band_n;           // [Qp, cap_band] local indices of the band, [Qp] their number
   float* out_s; long long* out_i;                // TOPK: [Q, k];  EXCLUDE: [Q, k_out]
   // EXCLUDE (k = k_out + n_excl candidates are fetched, then re-ranked)
   const long long* identifiers; const long long* exclusions; int n_excl; int k_out;
@@ -553,22 +551,43 @@ __device__ __forceinline__ void exclude_rerank(const unsigned long long* srt, in
   }
 }
 
-// Shared memory per warp: ks[cap_keys] (screening key << 32 | local index; the band is compacted IN PLACE at its
-// front, EXCLUDE parks the k best in its upper half) | soff[segs + 1] | qs[d].  cap_band = cap_keys / 2.
+// (3a) SELECT, one warp per query, no block-wide barriers, 4 KB of shared memory per query so that ~50 queries are
+// in flight per SM (the work is a chain of dependent L2 round trips: occupancy is what hides it):
+//   pass 1  survivors of the octet records -> their screening keys in shared memory;  tau = k-th largest (bitwise
+//           search on register-resident keys);  lim = tau - 2 eps
+//   pass 2  the records again: indices of the survivors with key >= lim  -> band_idx[row, :], band_n[row]
+// COUNT mode needs one pass: #{screen > pos + eps} is counted, the indices with |screen - pos| <= eps form the band.
+__host__ __device__ inline size_t sel_warp_bytes(int cap_keys, int segs) {
+  return (size_t)cap_keys * 4 + (size_t)((segs + 1 + 3) & ~3) * 4;
+}
+constexpr int SEL_WARPS = 8;
+
+// one 32-record window of a query's octet records: lane -> (first index, 8 scores); returns false past the end
+__device__ __forceinline__ bool load_record(const FinParams& p, long long row, const int* soff, int rec, int total_rec,
+                                            unsigned int& ix0, float (&sc)[8]) {
+  if (rec >= total_rec) return false;
+  int lo = 0, hi = p.segs;  // largest segment with soff[seg] <= rec
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (soff[mid] <= rec) lo = mid; else hi = mid; }
+  const long long at = (row * p.segs + lo) * p.cap_part + (rec - soff[lo]);
+  ix0 = __ldg(p.cand_i + at);
+  const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.cand_s + at * 8));
+  const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.cand_s + at * 8) + 1);
+  sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+  return true;
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(FW_WARPS * 32)
-tc_finalize_kernel(const FinParams p) {
+__global__ void __launch_bounds__(SEL_WARPS * 32)
+tc_select_kernel(const FinParams p) {
   extern __shared__ __align__(16) unsigned char fsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * FW_WARPS + warp;
+  const long long row = (long long)blockIdx.x * SEL_WARPS + warp;
   if (row >= p.Q) return;
-  unsigned char* base = fsm + (size_t)warp * fin_warp_bytes_dev(p.cap_keys, p.segs, p.d);
-  unsigned long long* ks = reinterpret_cast<unsigned long long*>(base);                  // [cap_keys]
-  int* soff = reinterpret_cast<int*>(ks + p.cap_keys);                                    // [segs + 1]
-  float* qs = reinterpret_cast<float*>(soff + ((p.segs + 1 + 3) & ~3));                   // [d]
-  unsigned long long* band = ks;
-  const unsigned int lt_mask = (1u << lane) - 1u;
+  unsigned char* base = fsm + (size_t)warp * sel_warp_bytes(p.cap_keys, p.segs);
+  unsigned int* keys = reinterpret_cast<unsigned int*>(base);                 // [cap_keys]
+  int* soff = reinterpret_cast<int*>(keys + p.cap_keys);                       // [segs + 1]
   const unsigned int n32 = (unsigned int)p.N;   // N < 2^31
+  unsigned int* band = p.band_idx + row * p.cap_band;
 
   // segment counts -> exclusive prefix
   int carry = 0; bool bad = false;
@@ -585,34 +604,25 @@ tc_finalize_kernel(const FinParams p) {
   }
   if (lane == 0) soff[0] = 0;
   if (__any_sync(0xffffffffu, bad)) {  // a segment overflowed in the filter pass: records are missing -> exact fallback
-    if (lane == 0) p.overflow[row] = 1;
+    if (lane == 0) { p.overflow[row] = 1; p.band_n[row] = 0; }
     return;
   }
-  for (int t = lane; t < p.d; t += 32) qs[t] = p.q[row * p.d + t];
   __syncwarp();
   const int total_rec = soff[p.segs];
   const float thr_row = p.thr[row];
 
   if (MODE == FIN_COUNT) {
     // metrics/factorized_top_k.py:181-192: in_top_k(target = the positive, k) <=> #{candidates scoring > positive} < k.
-    // screen > pos + eps => exact > pos (counted as is); |screen - pos| <= eps => re-scored exactly.  When the positive
-    // lies below the listed range, at least K listed candidates are definite (L_q > pos + eps), so min(k, count) is exact.
+    // screen > pos + eps => exact > pos (counted as is); |screen - pos| <= eps => re-scored exactly (3b).  When the
+    // positive lies below the listed range, at least K listed candidates are definite (L_q > pos + eps), so
+    // min(k, count) is exact.
     const float eps = 0.5f * p.cut[row];
-    const float pos = p.pos[row];
-    const float pos_s = ldexpf(pos, p.hdr->st.exp + p.qexp[row]);
+    const float pos_s = ldexpf(p.pos[row], p.hdr->st.exp + p.qexp[row]);
     const float hi = pos_s + eps, lo_b = pos_s - eps;
     int definite = 0, m = 0;
     for (int rb = 0; rb < total_rec; rb += 32) {
-      const int rec = rb + lane;
-      unsigned int ix0 = 0, amb = 0; int cnt = 0;
-      if (rec < total_rec) {
-        int lo = 0, hi_s = p.segs;
-        while (hi_s - lo > 1) { const int mid = (lo + hi_s) >> 1; if (soff[mid] <= rec) lo = mid; else hi_s = mid; }
-        const long long at = (row * p.segs + lo) * p.cap_part + (rec - soff[lo]);
-        ix0 = __ldg(p.cand_i + at);
-        const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.cand_s + at * 8));
-        const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.cand_s + at * 8) + 1);
-        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      unsigned int ix0 = 0, amb = 0; int cnt = 0; float sc[8];
+      if (load_record(p, row, soff, rb + lane, total_rec, ix0, sc)) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const bool real = ix0 + j < n32;
@@ -623,40 +633,29 @@ tc_finalize_kernel(const FinParams p) {
       }
       const int incl = warp_incl_scan(cnt, lane);
       const int tot = __shfl_sync(0xffffffffu, incl, 31);
-      if (m + tot <= p.cap_keys) {
+      if (m + tot <= p.cap_band) {
         int at_pos = m + incl - cnt;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (amb & (1u << j)) { band[at_pos] = (unsigned long long)(ix0 + j); ++at_pos; }
+          if (amb & (1u << j)) { band[at_pos] = ix0 + j; ++at_pos; }
       }
       m += tot;
     }
     definite = __reduce_add_sync(0xffffffffu, definite);
-    if (definite >= p.k) { if (lane == 0) { p.out_count[row] = p.k; p.overflow[row] = 0; } return; }
-    if (m > p.cap_keys) { if (lane == 0) p.overflow[row] = 1; return; }
-    __syncwarp();
-    int greater = 0;
-    for (int t = lane; t < m; t += 32)
-      greater += (exact_score(qs, p.corpus + (long long)(unsigned int)band[t] * p.d, p.d) > pos) ? 1 : 0;
-    greater = __reduce_add_sync(0xffffffffu, greater);
-    if (lane == 0) { const int c = definite + greater; p.out_count[row] = c < p.k ? c : p.k; p.overflow[row] = 0; }
+    if (lane == 0) {
+      if (definite >= p.k) { p.out_count[row] = p.k; p.band_n[row] = 0; p.overflow[row] = 0; }
+      else if (m > p.cap_band) { p.overflow[row] = 1; p.band_n[row] = 0; }
+      else { p.out_count[row] = definite; p.band_n[row] = m; p.overflow[row] = 0; }   // 3b adds the re-scored ones
+    }
     return;
   }
 
-  // ---- TOPK / EXCLUDE: survivors (score >= filter threshold, real row) -> ks
+  // ---- TOPK / EXCLUDE, pass 1: screening keys of the survivors (score >= filter threshold, real row)
   int n = 0;
   unsigned int kmax = 0u, kmin = 0xFFFFFFFFu;
   for (int rb = 0; rb < total_rec; rb += 32) {
-    const int rec = rb + lane;
     float sc[8]; unsigned int ix0 = 0, keep = 0; int cnt = 0;
-    if (rec < total_rec) {
-      int lo = 0, hi = p.segs;  // largest segment with soff[seg] <= rec
-      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (soff[mid] <= rec) lo = mid; else hi = mid; }
-      const long long at = (row * p.segs + lo) * p.cap_part + (rec - soff[lo]);
-      ix0 = __ldg(p.cand_i + at);
-      const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.cand_s + at * 8));
-      const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.cand_s + at * 8) + 1);
-      sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+    if (load_record(p, row, soff, rb + lane, total_rec, ix0, sc)) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const bool kp = sc[j] >= thr_row && ix0 + j < n32;
@@ -672,14 +671,14 @@ tc_finalize_kernel(const FinParams p) {
         if (keep & (1u << j)) {
           const unsigned int key = f2key(sc[j] + 0.0f);   // -0 -> +0: key order == float order
           kmax = max(kmax, key); kmin = min(kmin, key);
-          ks[at_pos] = ((unsigned long long)key << 32) | (unsigned long long)(ix0 + j);
+          keys[at_pos] = key;
           ++at_pos;
         }
       }
     }
     n += tot;
   }
-  if (n > p.cap_keys || n < p.k) { if (lane == 0) p.overflow[row] = 1; return; }
+  if (n > p.cap_keys || n < p.k) { if (lane == 0) { p.overflow[row] = 1; p.band_n[row] = 0; } return; }
   __syncwarp();
   // tau = k-th best screening score: bitwise search below the bits the largest and the smallest key share
   kmax = __reduce_max_sync(0xffffffffu, kmax); kmin = __reduce_min_sync(0xffffffffu, kmin);
@@ -691,76 +690,105 @@ tc_finalize_kernel(const FinParams p) {
     if (n <= 512) {
       unsigned int kr[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) { const int t = j * 32 + lane; kr[j] = t < n ? (unsigned int)(ks[t] >> 32) : 0u; }
+      for (int j = 0; j < 16; ++j) { const int t = j * 32 + lane; kr[j] = t < n ? keys[t] : 0u; }
       tau_key = warp_kth_largest_regs<16>(kr, p.k, prefix0, top);
     } else if (n <= 1024) {
       unsigned int kr[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { const int t = j * 32 + lane; kr[j] = t < n ? (unsigned int)(ks[t] >> 32) : 0u; }
+      for (int j = 0; j < 32; ++j) { const int t = j * 32 + lane; kr[j] = t < n ? keys[t] : 0u; }
       tau_key = warp_kth_largest_regs<32>(kr, p.k, prefix0, top);
     } else {
-      tau_key = warp_kth_largest_smem(ks, n, p.k, lane, prefix0, top);
+      tau_key = warp_kth_largest_smem(keys, n, p.k, lane, prefix0, top);
     }
   }
   const float lim = key2f(tau_key) - p.cut[row];
   // Self-check that makes the threshold choice a pure performance matter: the whole band [lim, inf) must
   // lie above the filter threshold, otherwise survivors could be missing -> exact fallback.
-  if (!(lim >= thr_row) || !(lim > -INFINITY)) { if (lane == 0) p.overflow[row] = 1; return; }
-  // band = survivors with screening score >= lim, compacted in place (write position <= read position)
-  const unsigned int lim_key = f2key(lim + 0.0f);
+  if (!(lim >= thr_row) || !(lim > -INFINITY)) { if (lane == 0) { p.overflow[row] = 1; p.band_n[row] = 0; } return; }
+  // pass 2: the indices of the survivors inside the band (screening score >= lim)
+  const float limc = lim + 0.0f;
   int m = 0;
-  for (int tb = 0; tb < n; tb += 32) {
-    const int t = tb + lane;
-    const unsigned long long e = t < n ? ks[t] : 0ull;
-    const bool keep = t < n && (unsigned int)(e >> 32) >= lim_key;
-    const unsigned int vote = __ballot_sync(0xffffffffu, keep);
-    __syncwarp();                     // every lane has read its entry of this chunk before any lane overwrites the chunk
-    if (keep) band[m + __popc(vote & lt_mask)] = e;
-    m += __popc(vote);
-  }
-  const int cap_band = p.cap_keys >> 1;
-  if (m > cap_band) { if (lane == 0) p.overflow[row] = 1; return; }  // band too crowded (massive ties)
-  __syncwarp();
-  // exact re-scoring; band[t] becomes the composite key (score desc, index asc) == larger is better
-  for (int t = lane; t < m; t += 64) {   // two candidates per lane in flight: twice the loads per DRAM round trip
-    const int t2 = t + 32;
-    const unsigned int idx = (unsigned int)band[t];
-    const unsigned int idx2 = t2 < m ? (unsigned int)band[t2] : idx;
-    float s, s2;
-    exact_score2(qs, p.corpus + (long long)idx * p.d, p.corpus + (long long)idx2 * p.d, p.d, s, s2);
-    band[t] = ((unsigned long long)f2key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
-    if (t2 < m) band[t2] = ((unsigned long long)f2key(s2) << 32) | (unsigned long long)(0xFFFFFFFFu - idx2);
-  }
-  __syncwarp();
-  // rank sort: every lane ranks up to 4 own entries per sweep over the band (broadcast reads); ranks are unique
-  unsigned long long* srt = ks + cap_band;  // EXCLUDE: the k best in order (upper half: never touched by the band)
-  for (int t0 = 0; t0 < m; t0 += 128) {
-    unsigned long long mine[4]; int rank[4];
+  for (int rb = 0; rb < total_rec; rb += 32) {
+    float sc[8]; unsigned int ix0 = 0, keep = 0; int cnt = 0;
+    if (load_record(p, row, soff, rb + lane, total_rec, ix0, sc)) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { const int t = t0 + u * 32 + lane; mine[u] = t < m ? band[t] : ~0ull; rank[u] = 0; }
-    for (int j = 0; j < m; ++j) {
-      const unsigned long long o = band[j];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) rank[u] += (o > mine[u]) ? 1 : 0;
+      for (int j = 0; j < 8; ++j) {
+        const bool kp = sc[j] >= limc && ix0 + j < n32;
+        keep |= kp ? (1u << j) : 0u; cnt += kp ? 1 : 0;
+      }
     }
+    const int incl = warp_incl_scan(cnt, lane);
+    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+    if (tot && m + tot <= p.cap_band) {
+      int at_pos = m + incl - cnt;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int t = t0 + u * 32 + lane;
-      if (t < m && rank[u] < p.k) {
-        if (MODE == FIN_TOPK) {
-          p.out_s[row * p.k + rank[u]] = key2f((unsigned int)(mine[u] >> 32));
-          p.out_i[row * p.k + rank[u]] = (long long)(0xFFFFFFFFu - (unsigned int)mine[u]) + p.index_offset;
-        } else {
-          srt[rank[u]] = mine[u];
-        }
+      for (int j = 0; j < 8; ++j)
+        if (keep & (1u << j)) { band[at_pos] = ix0 + j; ++at_pos; }
+    }
+    m += tot;
+  }
+  if (lane == 0) {
+    if (m > p.cap_band) { p.overflow[row] = 1; p.band_n[row] = 0; }   // band too crowded (massive ties)
+    else { p.overflow[row] = 0; p.band_n[row] = m; }
+  }
+}
+
+// (3b) RE-SCORE + RANK, one 128-thread block per query: every band candidate's fp32 corpus row is fetched at once (one
+// DRAM round trip per query; ~115 MB of random 256-byte rows per cfg2 batch, the HBM-bound part of the finalize step),
+// the canonical fmaf chain gives the exact score, and each thread ranks its entry against the band in shared memory
+// (ranks are unique: (score desc, index asc) is a total order).  EXCLUDE re-ranks the k best, COUNT adds #{exact > pos}.
+constexpr int RS_BLOCK = 128;
+template <int MODE>
+__global__ void __launch_bounds__(RS_BLOCK)
+tc_rescore_kernel(const FinParams p) {
+  extern __shared__ __align__(16) unsigned char rsm[];
+  unsigned long long* sk = reinterpret_cast<unsigned long long*>(rsm);                  // [cap_band] composite keys
+  float* qs = reinterpret_cast<float*>(sk + p.cap_band);                                  // [d]
+  unsigned long long* srt = reinterpret_cast<unsigned long long*>(qs + ((p.d + 3) & ~3)); // EXCLUDE: [2 * k]
+  __shared__ int greater_sh;
+  const long long row = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (p.overflow[row] != 0) return;
+  const int m = p.band_n[row];
+  if (MODE == FIN_COUNT && m == 0) return;    // the select kernel already wrote the count
+  for (int t = tid; t < p.d; t += RS_BLOCK) qs[t] = p.q[row * p.d + t];
+  if (tid == 0) greater_sh = 0;
+  __syncthreads();
+  const unsigned int* band = p.band_idx + row * p.cap_band;
+  if (MODE == FIN_COUNT) {
+    const float pos = p.pos[row];
+    int g = 0;
+    for (int t = tid; t < m; t += RS_BLOCK) g += (exact_score(qs, p.corpus + (long long)band[t] * p.d, p.d) > pos) ? 1 : 0;
+    g = __reduce_add_sync(0xffffffffu, g);
+    if ((tid & 31) == 0 && g) atomicAdd(&greater_sh, g);
+    __syncthreads();
+    if (tid == 0) { const int c = p.out_count[row] + greater_sh; p.out_count[row] = c < p.k ? c : p.k; }
+    return;
+  }
+  for (int t = tid; t < m; t += RS_BLOCK) {
+    const unsigned int idx = band[t];
+    const float s = exact_score(qs, p.corpus + (long long)idx * p.d, p.d);
+    sk[t] = ((unsigned long long)f2key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+  }
+  __syncthreads();
+  for (int t = tid; t < m; t += RS_BLOCK) {
+    const unsigned long long mine = sk[t];
+    int rank = 0;
+#pragma unroll 4
+    for (int j = 0; j < m; ++j) rank += (sk[j] > mine) ? 1 : 0;
+    if (rank < p.k) {
+      if (MODE == FIN_TOPK) {
+        p.out_s[row * p.k + rank] = key2f((unsigned int)(mine >> 32));
+        p.out_i[row * p.k + rank] = (long long)(0xFFFFFFFFu - (unsigned int)mine) + p.index_offset;
+      } else {
+        srt[rank] = mine;
       }
     }
   }
   if (MODE == FIN_EXCLUDE) {
-    __syncwarp();
-    exclude_rerank(srt, p.k, band, row, p, lane);   // the band (>= k words) is dead after the ranking
+    __syncthreads();
+    if (tid < 32) exclude_rerank(srt, p.k, srt + p.k, row, p, tid);
   }
-  if (lane == 0) p.overflow[row] = 0;
 }
 
 // EXCLUDE for the rows the exact fallback produced: tmp_[s,i] [Q, k] sorted lists -> the same re-ranking
@@ -849,7 +877,7 @@ struct Plan {
   int stride, n_sample, group, bins_per_part, n_bins, bins_ld, parts_sample, parts_full, cap_part, cap_keys, cap_band;
   size_t smem;
   // workspace offsets
-  size_t o_qimg, o_margin, o_cut, o_thr, o_qexp, o_count, o_ovf, o_binmax, o_cand, o_tmp, total;
+  size_t o_qimg, o_margin, o_cut, o_thr, o_qexp, o_count, o_ovf, o_binmax, o_cand, o_tmp, o_band, o_bandn, total;
 };
 
 static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
@@ -912,6 +940,8 @@ static bool make_plan(long long Q, long long N, int d, int k, Plan& pl) {
   pl.o_binmax = take((size_t)pl.Qp * pl.bins_ld * 4);
   pl.o_cand = take((size_t)pl.Qp * pl.parts_full * 2 * pl.cap_part * (8 * 4 + 4));
   pl.o_tmp = take((size_t)Q * k * 12);   // EXCLUDE: the exact fallback's [Q, k] lists before the re-ranking
+  pl.o_band = take((size_t)pl.Qp * pl.cap_band * 4);
+  pl.o_bandn = take((size_t)pl.Qp * 4);
   pl.total = o;
   return true;
 }
@@ -940,10 +970,14 @@ static int launch_scan_mode(const Plan& pl, const ScanParams& sp, cudaStream_t s
 
 template <int MODE>
 static int launch_finalize(FinParams fp, cudaStream_t st) {
-  auto kern = tc_finalize_kernel<MODE>;
-  TFRS_DYN_SMEM(kern, (int)(FW_WARPS * fin_warp_bytes_dev(4096, FIN_MAX_PARTS, 128)));
-  const unsigned grid = (unsigned)ceil_div(fp.Q, FW_WARPS);
-  kern<<<grid, FW_WARPS * 32, FW_WARPS * fin_warp_bytes_dev(fp.cap_keys, fp.segs, fp.d), st>>>(fp);
+  auto ksel = tc_select_kernel<MODE>;
+  auto krs = tc_rescore_kernel<MODE>;
+  TFRS_DYN_SMEM(ksel, (int)(SEL_WARPS * sel_warp_bytes(4096, FIN_MAX_PARTS)));
+  ksel<<<(unsigned)ceil_div(fp.Q, SEL_WARPS), SEL_WARPS * 32, SEL_WARPS * sel_warp_bytes(fp.cap_keys, fp.segs), st>>>(fp);
+  TFRS_LAUNCH_CHECK();
+  const size_t rs_smem = (size_t)fp.cap_band * 8 + (size_t)((fp.d + 3) & ~3) * 4 + (MODE == FIN_EXCLUDE ? (size_t)fp.k * 16 : 0);
+  TFRS_DYN_SMEM(krs, 64 * 1024);
+  krs<<<(unsigned)fp.Q, RS_BLOCK, rs_smem, st>>>(fp);
   TFRS_LAUNCH_CHECK();
   return TFRS_OK;
 }
@@ -1011,7 +1045,8 @@ static int run_call(const Call& c) {
   fp.q = c.q; fp.corpus = c.corpus; fp.d = c.d; fp.k = c.k; fp.index_offset = c.index_offset; fp.N = c.N; fp.Q = c.Q;
   fp.count = count; fp.cand_s = cand_s; fp.cand_i = cand_i; fp.segs = pl.parts_full * 2; fp.cap_part = pl.cap_part;
   fp.cut = cut; fp.thr = thr; fp.overflow = ovf; fp.out_s = c.out_s; fp.out_i = c.out_i;
-  fp.cap_keys = pl.cap_keys;
+  fp.cap_keys = pl.cap_keys; fp.cap_band = pl.cap_band;
+  fp.band_idx = (unsigned int*)(w + pl.o_band); fp.band_n = (int*)(w + pl.o_bandn);
   fp.identifiers = c.identifiers; fp.exclusions = c.exclusions; fp.n_excl = c.n_excl; fp.k_out = c.k_out;
   fp.pos = c.pos; fp.qexp = qexp; fp.hdr = hdr; fp.out_count = c.out_count;
   if (c.mode == FIN_TOPK) rc = launch_finalize<FIN_TOPK>(fp, st);
