@@ -256,11 +256,15 @@ tc_scan_kernel(const ScanParams p) {
       mbar_expect_tx(a_full, 2 * KB * SLAB_BYTES);
       bulk_g2s(sA, p.qimg + (long long)qb * 2 * KB * SLAB_BYTES, 2 * KB * SLAB_BYTES, a_full);
       int stage = 0; uint32_t phase = 0;
+      const uint64_t pol = l2_policy_evict_first();
       for (int it = 0; it < n_iter; ++it) {
         const long long tile = (long long)(u_begin + it) * p.stride;
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], KB * SLAB_BYTES);
-        bulk_g2s(sB + stage * KB * SLAB_BYTES, p.cimg + tile * ((long long)KB * SLAB_BYTES), KB * SLAB_BYTES, &full[stage]);
+        if (MODE == MODE_FILTER)   // streamed once per pass: evict-first, so the survivor records stay in L2 for the select kernel
+          bulk_g2s_hint(sB + stage * KB * SLAB_BYTES, p.cimg + tile * ((long long)KB * SLAB_BYTES), KB * SLAB_BYTES, &full[stage], pol);
+        else
+          bulk_g2s(sB + stage * KB * SLAB_BYTES, p.cimg + tile * ((long long)KB * SLAB_BYTES), KB * SLAB_BYTES, &full[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -558,7 +562,7 @@ __device__ __forceinline__ void exclude_rerank(const unsigned long long* srt, in
 //   pass 2  the records again: indices of the survivors with key >= lim  -> band_idx[row, :], band_n[row]
 // COUNT mode needs one pass: #{screen > pos + eps} is counted, the indices with |screen - pos| <= eps form the band.
 __host__ __device__ inline size_t sel_warp_bytes(int cap_keys, int segs) {
-  return (size_t)cap_keys * 4 + (size_t)((segs + 1 + 3) & ~3) * 4;
+  return (size_t)cap_keys * 4 + (size_t)cap_keys * 2 + (size_t)((segs + 1 + 3) & ~3) * 4;
 }
 constexpr int SEL_WARPS = 8;
 
@@ -584,8 +588,9 @@ tc_select_kernel(const FinParams p) {
   const long long row = (long long)blockIdx.x * SEL_WARPS + warp;
   if (row >= p.Q) return;
   unsigned char* base = fsm + (size_t)warp * sel_warp_bytes(p.cap_keys, p.segs);
-  unsigned int* keys = reinterpret_cast<unsigned int*>(base);                 // [cap_keys]
-  int* soff = reinterpret_cast<int*>(keys + p.cap_keys);                       // [segs + 1]
+  unsigned int* keys = reinterpret_cast<unsigned int*>(base);                 // [cap_keys] screening keys
+  unsigned short* loc = reinterpret_cast<unsigned short*>(keys + p.cap_keys);  // [cap_keys] (flat record index << 3 | column): total records < 8192
+  int* soff = reinterpret_cast<int*>(loc + p.cap_keys);                        // [segs + 1]
   const unsigned int n32 = (unsigned int)p.N;   // N < 2^31
   unsigned int* band = p.band_idx + row * p.cap_band;
 
@@ -610,6 +615,10 @@ tc_select_kernel(const FinParams p) {
   __syncwarp();
   const int total_rec = soff[p.segs];
   const float thr_row = p.thr[row];
+  if (MODE != FIN_COUNT && total_rec >= 8192) {   // the 16-bit record locator holds 13 bits of record index
+    if (lane == 0) { p.overflow[row] = 1; p.band_n[row] = 0; }
+    return;
+  }
 
   if (MODE == FIN_COUNT) {
     // metrics/factorized_top_k.py:181-192: in_top_k(target = the positive, k) <=> #{candidates scoring > positive} < k.
@@ -672,6 +681,7 @@ tc_select_kernel(const FinParams p) {
           const unsigned int key = f2key(sc[j] + 0.0f);   // -0 -> +0: key order == float order
           kmax = max(kmax, key); kmin = min(kmin, key);
           keys[at_pos] = key;
+          loc[at_pos] = (unsigned short)(((rb + lane) << 3) | j);
           ++at_pos;
         }
       }
@@ -705,27 +715,25 @@ tc_select_kernel(const FinParams p) {
   // Self-check that makes the threshold choice a pure performance matter: the whole band [lim, inf) must
   // lie above the filter threshold, otherwise survivors could be missing -> exact fallback.
   if (!(lim >= thr_row) || !(lim > -INFINITY)) { if (lane == 0) { p.overflow[row] = 1; p.band_n[row] = 0; } return; }
-  // pass 2: the indices of the survivors inside the band (screening score >= lim)
-  const float limc = lim + 0.0f;
+  // pass 2: only the band members (key >= key(lim)) go back to their record for the corpus index
+  const unsigned int lim_key = f2key(lim + 0.0f);
+  const unsigned int lt_mask = (1u << lane) - 1u;
   int m = 0;
-  for (int rb = 0; rb < total_rec; rb += 32) {
-    float sc[8]; unsigned int ix0 = 0, keep = 0; int cnt = 0;
-    if (load_record(p, row, soff, rb + lane, total_rec, ix0, sc)) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const bool kp = sc[j] >= limc && ix0 + j < n32;
-        keep |= kp ? (1u << j) : 0u; cnt += kp ? 1 : 0;
+  for (int tb = 0; tb < n; tb += 32) {
+    const int t = tb + lane;
+    const bool kp = t < n && keys[t] >= lim_key;
+    const unsigned int vote = __ballot_sync(0xffffffffu, kp);
+    if (kp) {
+      const int at_pos = m + __popc(vote & lt_mask);
+      if (at_pos < p.cap_band) {
+        const unsigned int l = loc[t];
+        const int rec = (int)(l >> 3);
+        int lo = 0, hi = p.segs;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (soff[mid] <= rec) lo = mid; else hi = mid; }
+        band[at_pos] = __ldg(p.cand_i + (row * p.segs + lo) * p.cap_part + (rec - soff[lo])) + (l & 7u);
       }
     }
-    const int incl = warp_incl_scan(cnt, lane);
-    const int tot = __shfl_sync(0xffffffffu, incl, 31);
-    if (tot && m + tot <= p.cap_band) {
-      int at_pos = m + incl - cnt;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (keep & (1u << j)) { band[at_pos] = ix0 + j; ++at_pos; }
-    }
-    m += tot;
+    m += __popc(vote);
   }
   if (lane == 0) {
     if (m > p.cap_band) { p.overflow[row] = 1; p.band_n[row] = 0; }   // band too crowded (massive ties)
