@@ -190,6 +190,10 @@ int tfrs_comm_destroy(tfrs_comm_t comm);
  * tfrs_comm_p2p_capacity: 1 when the mapped buffers hold a (Q, k) call. */
 int tfrs_comm_enable_p2p(tfrs_comm_t comm, int64_t max_Q, int max_k);
 int tfrs_comm_p2p_capacity(tfrs_comm_t comm, int64_t Q, int k);
+/* option 0: exchange a GLOBAL lower bound of the k-th best score between the threshold kernel and the filter pass of the
+ * peer-memory path (default 1): each shard then keeps ~1/world of the survivors, so the per-rank select / re-score work
+ * shrinks with the shard.  Must be set identically on every rank. */
+int tfrs_comm_set_option(tfrs_comm_t comm, int option, int value);
 int tfrs_comm_rank(tfrs_comm_t comm);
 int tfrs_comm_world(tfrs_comm_t comm);
 int tfrs_topk_allgather(tfrs_comm_t comm, const float* s, const int64_t* i, int64_t Q, int k, float* all_s,

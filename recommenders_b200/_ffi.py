@@ -53,6 +53,7 @@ _SIGNATURES = {
     "tfrs_comm_destroy": (c_i, [c_p]),
     "tfrs_comm_enable_p2p": (c_i, [c_p, c_l, c_i]),
     "tfrs_comm_p2p_capacity": (c_i, [c_p, c_l, c_i]),
+    "tfrs_comm_set_option": (c_i, [c_p, c_i, c_i]),
     "tfrs_comm_rank": (c_i, [c_p]),
     "tfrs_comm_world": (c_i, [c_p]),
     "tfrs_topk_allgather": (c_i, [c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p]),

@@ -92,6 +92,7 @@ struct tfrs_comm {
   unsigned char* xbuf[TFRS_MAX_RANKS];
   size_t xbytes;
   unsigned int epoch;
+  int thr_exchange;   // exchange a global score bound before the filter pass (tfrs_comm_set_option)
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -112,8 +113,8 @@ struct tfrs_comm {
 // ---------------------------------------------------------------------------------------------------------------
 namespace tfrs {
 namespace {
-constexpr size_t XFLAGS = 8192;                 // flagA[r] at 128*r, flagB[r] at 4096 + 128*r, block counters at the end
-struct XLayout { long long Qo; size_t a_s, a_i, b_s, b_i, total; };
+constexpr size_t XFLAGS = 8192;                 // flagA[r] at 128*r, flagT[r] at 2048 + 128*r, flagB[r] at 4096 + 128*r, block counters at the end
+struct XLayout { long long Qo; size_t a_s, a_i, b_s, b_i, t, total; };
 XLayout x_layout(int world, long long Q, int k) {
   XLayout L;
   L.Qo = (Q + world - 1) / world;
@@ -123,6 +124,7 @@ XLayout x_layout(int world, long long Q, int k) {
   L.a_i = take((size_t)world * L.Qo * k * 8);
   L.b_s = take((size_t)world * L.Qo * k * 4);   // result area, padded to world * Qo rows
   L.b_i = take((size_t)world * L.Qo * k * 8);
+  L.t = take((size_t)world * world * L.Qo * 4);     // threshold exchange: [src rank][query] lower bounds of the k-th best score
   L.total = o;
   return L;
 }
@@ -153,6 +155,42 @@ __device__ __forceinline__ void signal_when_grid_done(PeerPtrs peers, int world,
     __threadfence_system();
     if ((int)threadIdx.x < world)
       *reinterpret_cast<volatile unsigned int*>(peers.p[threadIdx.x] + flag_off + 128 * rank) = epoch;
+  }
+}
+
+// T (before the filter pass): a GLOBAL lower bound of the k-th best exact score.  Shard r knows K candidates with screening
+// score >= L_r, i.e. exact score >= B_r = (L_r - eps_r) / 2^se_r; max_r B_r bounds the global k-th best from below, so shard s
+// may filter at  B * 2^se_s - eps_s - slack_s : every member of the GLOBAL top-k still passes on its shard, while the
+// survivors per shard drop from ~4.5 k to ~4.5 k / world -- the select / re-score work of the finalize step shrinks with
+// the shard instead of staying constant.  16 KB per peer; same flag protocol as the list exchange.
+__global__ void __launch_bounds__(256)
+x_thr_send_kernel(PeerPtrs peers, int world, int rank, const float* __restrict__ thr, const float* __restrict__ margin,
+                  const float* __restrict__ cut, const int* __restrict__ qexp, const int* __restrict__ exp_corpus, long long Q,
+                  size_t t_off, long long q_cap, unsigned int epoch) {
+  const int ec = *exp_corpus;
+  for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < Q; q += (long long)gridDim.x * 256) {
+    const float L = thr[q] + margin[q];
+    const float B = ldexpf(L - 0.5f * cut[q], -(ec + qexp[q]));
+    for (int o = 0; o < world; ++o) reinterpret_cast<float*>(peers.p[o] + t_off)[(long long)rank * q_cap + q] = B;
+  }
+  signal_when_grid_done(peers, world, 2048, rank, epoch, reinterpret_cast<unsigned int*>(peers.p[rank] + XFLAGS - 192));
+}
+
+__global__ void __launch_bounds__(256)
+x_thr_combine_kernel(const unsigned char* local, int world, float* __restrict__ thr, const float* __restrict__ margin,
+                     const float* __restrict__ cut, const int* __restrict__ qexp, const int* __restrict__ exp_corpus, long long Q,
+                     size_t t_off, long long q_cap, unsigned int epoch) {
+  if ((int)threadIdx.x < world) spin_until(reinterpret_cast<const volatile unsigned int*>(local + 2048 + 128 * threadIdx.x), epoch);
+  __threadfence_system();
+  __syncthreads();
+  const int ec = *exp_corpus;
+  const float* T = reinterpret_cast<const float*>(local + t_off);
+  for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < Q; q += (long long)gridDim.x * 256) {
+    float B = -INFINITY;
+    for (int r = 0; r < world; ++r) B = fmaxf(B, __ldcv(T + (long long)r * q_cap + q));
+    const float eps = 0.5f * cut[q];
+    const float t_new = ldexpf(B, ec + qexp[q]) - eps - (margin[q] - cut[q]);
+    thr[q] = fmaxf(thr[q], t_new);   // never below the shard's own rule (equal to it on the shard that set the maximum)
   }
 }
 
@@ -231,7 +269,7 @@ extern "C" int tfrs_comm_create(tfrs_comm_t* out, int rank, int world, const voi
   ncclUniqueId id;
   memcpy(&id, unique_id128, sizeof(id));
   tfrs_comm* c = new tfrs_comm{};
-  c->rank = rank; c->world = world;
+  c->rank = rank; c->world = world; c->thr_exchange = 1;
   if (cudaGetDevice(&c->device) != cudaSuccess) c->device = 0;
   ncclResult_t r = a->CommInitRank(&c->comm, world, id, rank);   // collective: every rank of the group calls it
   if (r != 0) {
@@ -316,6 +354,13 @@ extern "C" int tfrs_comm_enable_p2p(tfrs_comm_t c, int64_t max_Q, int max_k) {
   return TFRS_OK;
 }
 
+// option 0 = threshold exchange of the peer-memory path (default on).  Must be set identically on every rank.
+extern "C" int tfrs_comm_set_option(tfrs_comm_t c, int option, int value) {
+  TFRS_CHECK_ARG(c && option == 0, "comm_set_option: unknown option %d", option);
+  c->thr_exchange = value != 0;
+  return TFRS_OK;
+}
+
 extern "C" int tfrs_comm_p2p_capacity(tfrs_comm_t c, int64_t Q, int k) {
   if (!c || !c->xbytes || Q <= 0 || k <= 0) return 0;
   return x_layout(c->world, Q, k).total <= c->xbytes ? 1 : 0;
@@ -358,6 +403,37 @@ ShardLayout shard_layout(int world, int64_t Q, int64_t N_local, int d, int k) {
 }
 }  // namespace
 
+namespace tfrs {
+namespace {
+struct ThrCtx { tfrs_comm* c; unsigned int epoch; XLayout X; };
+int thr_hook(void* vctx, float* thr, const float* margin, const float* cut, const int* qexp, const int* exp_corpus, long long Q,
+             cudaStream_t st) {
+  ThrCtx* t = (ThrCtx*)vctx;
+  tfrs_comm* c = t->c;
+  PeerPtrs peers{};
+  for (int r = 0; r < c->world; ++r) peers.p[r] = c->xbuf[r];
+  const long long q_cap = (long long)c->world * t->X.Qo;
+  const unsigned grid = (unsigned)ceil_div(Q, 256) < 32u ? (unsigned)ceil_div(Q, 256) : 32u;
+  x_thr_send_kernel<<<grid, 256, 0, st>>>(peers, c->world, c->rank, thr, margin, cut, qexp, exp_corpus, Q, t->X.t, q_cap, t->epoch);
+  TFRS_LAUNCH_CHECK();
+  x_thr_combine_kernel<<<grid, 256, 0, st>>>(c->xbuf[c->rank], c->world, thr, margin, cut, qexp, exp_corpus, Q, t->X.t, q_cap, t->epoch);
+  TFRS_LAUNCH_CHECK();
+  return TFRS_OK;
+}
+__global__ void fill_neutral_kernel(float* thr, float* margin, float* cut, int* qexp, int* ec, long long Q) {
+  for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < Q; q += (long long)gridDim.x * 256) { thr[q] = -INFINITY; margin[q] = 0.f; cut[q] = 0.f; qexp[q] = 0; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *ec = 0;
+}
+int thr_hook_neutral(ThrCtx* t, long long Q, unsigned char* scratch, cudaStream_t st) {
+  // scratch: the local-scan workspace (free at this point): 4 arrays of Q floats + 1 int
+  float* thr = (float*)scratch; float* margin = thr + Q; float* cut = margin + Q; int* qexp = (int*)(cut + Q); int* ec = qexp + Q;
+  fill_neutral_kernel<<<32, 256, 0, st>>>(thr, margin, cut, qexp, ec, Q);
+  TFRS_LAUNCH_CHECK();
+  return thr_hook(t, thr, margin, cut, qexp, ec, Q, st);
+}
+}  // namespace
+}  // namespace tfrs
+
 extern "C" size_t tfrs_topk_sharded_workspace_bytes(int world, int64_t Q, int64_t N_local, int d, int k) {
   if (world <= 0 || Q <= 0 || N_local < 0 || d <= 0 || k <= 0) return 0;
   return shard_layout(world, Q, N_local, d, k).total;
@@ -387,25 +463,40 @@ extern "C" int tfrs_topk_sharded_f32(tfrs_comm_t c, const float* q, int64_t Q, c
   float* send_s = (float*)send; long long* send_i = (long long*)(send + L.idx_off);
   // local scan, written straight into the send block; shards shorter than k are padded with (-inf, INT64_MAX) so that
   // EVERY rank issues the identical collective whatever path its own shard takes
+  const bool p2p = c->xbytes && x_layout(c->world, Q, k).total <= c->xbytes;
+  const unsigned int epoch = p2p ? ++c->epoch : 0u;
   const int k_local = (int)(N_local < k ? N_local : k);
+  // the threshold exchange is itself a collective step: every rank takes the same decision (it depends only on what all
+  // ranks share: Q, k, world, the option); a shard that cannot use it (no tensor-core index) takes part with "no bound"
+  const bool thr_x = p2p && c->thr_exchange;
   if (k_local < k) {
     fill_pad_kernel<<<(unsigned)ceil_div(Q * (k - k_local), 256), 256, 0, st>>>(send_s, send_i, Q, k, k_local);
     TFRS_LAUNCH_CHECK();
   }
+  ThrCtx tctx{c, epoch, x_layout(c->world, Q, k)};
+  bool hook_ran = false;
   if (k_local > 0) {
     int rc = TFRS_ERR_UNSUPPORTED;
-    if (index_buf && k_local == k && tfrs_topk_tc_workspace_bytes(Q, N_local, d, k) > 0)
-      rc = tfrs_topk_tc_f32(q, Q, corpus_local, index_buf, N_local, d, k, index_offset, send_s, (int64_t*)send_i, w, L.scan, st);
+    if (index_buf && k_local == k && tfrs_topk_tc_workspace_bytes(Q, N_local, d, k) > 0) {
+      rc = tc_topk_sharded_local(q, Q, corpus_local, index_buf, N_local, d, k, index_offset, send_s, (int64_t*)send_i, w, L.scan, st,
+                                 thr_x ? thr_hook : nullptr, thr_x ? &tctx : nullptr);
+      hook_ran = thr_x && rc == TFRS_OK;
+    }
     if (rc == TFRS_ERR_UNSUPPORTED)
       rc = tfrs_topk_scan_f32(q, Q, corpus_local, N_local, d, k, index_offset, nullptr, nullptr, 0, send_s, (int64_t*)send_i, w, L.scan, st);
     if (rc) return rc;
   }
-  if (c->xbytes && x_layout(c->world, Q, k).total <= c->xbytes) {
+  if (thr_x && !hook_ran) {
+    // this shard took the exact path (tiny shard): it still has to take part in the threshold exchange -- it contributes
+    // "no bound" (-inf) and ignores the result
+    int rc = thr_hook_neutral(&tctx, Q, w, st);
+    if (rc) return rc;
+  }
+  if (p2p) {
     // peer-memory exchange: scatter to the owners -> owners merge their block -> owners store the results everywhere
     const XLayout X = x_layout(c->world, Q, k);
     PeerPtrs peers{};
     for (int r = 0; r < c->world; ++r) peers.p[r] = c->xbuf[r];
-    const unsigned int epoch = ++c->epoch;
     unsigned char* local = c->xbuf[c->rank];
     const unsigned grid = (unsigned)(sm_count() < 64 ? sm_count() : 64);
     x_scatter_kernel<<<grid, 256, 0, st>>>(peers, c->world, c->rank, send_s, send_i, Q, k, X, epoch);

@@ -50,6 +50,14 @@ __host__ __device__ __forceinline__ bool better(float sa, long long ia, float sb
 
 int sm_count();  // SMs of the CURRENT device (cached per device)
 
+// Hook of the sharded scan (topk_tc.cu <-> comm.cu): all device pointers; thr[q] = L_q - margin_q in the shard's screening
+// units (scores scaled by 2^(*exp_corpus + qexp[q])), cut[q] = 2 eps_q.  The hook may raise thr[].
+typedef int (*ThrHook)(void* ctx, float* thr, const float* margin, const float* cut, const int* qexp, const int* exp_corpus,
+                       long long Q, cudaStream_t st);
+int tc_topk_sharded_local(const float* q, int64_t Q, const float* corpus, const void* index_buf, int64_t N, int d, int k,
+                          int64_t index_offset, float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes, void* stream,
+                          ThrHook hook, void* hook_ctx);
+
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (call site, device): function attributes belong to
 // a device/context, so a process-wide "done" flag would leave the second GPU of a process at the 48 KB default.
 struct DeviceOnce {

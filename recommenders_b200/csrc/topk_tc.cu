@@ -470,6 +470,7 @@ struct FinParams {
   const float* cut; const float* thr; unsigned int* overflow;
   int cap_keys, cap_band;                        // survivors per query (keys in shared memory) / band entries re-scored exactly
   unsigned int* band_idx; int* band_n;           // [Qp, cap_band] local indices of the band, [Qp] their number
+  int allow_short;                               // sharded scan with a GLOBAL threshold: a shard may hold fewer than k survivors
   float* out_s; long long* out_i;                // TOPK: [Q, k];  EXCLUDE: [Q, k_out]
   // EXCLUDE (k = k_out + n_excl candidates are fetched, then re-ranked)
   const long long* identifiers; const long long* exclusions; int n_excl; int k_out;
@@ -688,8 +689,22 @@ tc_select_kernel(const FinParams p) {
     }
     n += tot;
   }
-  if (n > p.cap_keys || n < p.k) { if (lane == 0) { p.overflow[row] = 1; p.band_n[row] = 0; } return; }
+  if (n > p.cap_keys || (n < p.k && !p.allow_short)) { if (lane == 0) { p.overflow[row] = 1; p.band_n[row] = 0; } return; }
   __syncwarp();
+  if (n < p.k) {
+    // Sharded scan, threshold agreed across the shards (see comm.cu): this shard holds fewer than k candidates above it.
+    // Every one of them is re-scored and emitted -- members of the global top-k are survivors on their shard by construction.
+    const bool fits = n <= p.cap_band;
+    for (int t = lane; t < n && fits; t += 32) {
+      const unsigned int l = loc[t];
+      const int rec = (int)(l >> 3);
+      int lo = 0, hi = p.segs;
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (soff[mid] <= rec) lo = mid; else hi = mid; }
+      band[t] = __ldg(p.cand_i + (row * p.segs + lo) * p.cap_part + (rec - soff[lo])) + (l & 7u);
+    }
+    if (lane == 0) { p.overflow[row] = fits ? 0u : 1u; p.band_n[row] = fits ? n : 0; }
+    return;
+  }
   // tau = k-th best screening score: bitwise search below the bits the largest and the smallest key share
   kmax = __reduce_max_sync(0xffffffffu, kmax); kmin = __reduce_min_sync(0xffffffffu, kmin);
   unsigned int tau_key;
@@ -714,7 +729,9 @@ tc_select_kernel(const FinParams p) {
   const float lim = key2f(tau_key) - p.cut[row];
   // Self-check that makes the threshold choice a pure performance matter: the whole band [lim, inf) must
   // lie above the filter threshold, otherwise survivors could be missing -> exact fallback.
-  if (!(lim >= thr_row) || !(lim > -INFINITY)) { if (lane == 0) { p.overflow[row] = 1; p.band_n[row] = 0; } return; }
+  // (with a threshold agreed across shards the local band may reach below it: what is missing there cannot be in the
+  //  GLOBAL top-k, and the local list is only an input of the cross-shard merge)
+  if (!p.allow_short && (!(lim >= thr_row) || !(lim > -INFINITY))) { if (lane == 0) { p.overflow[row] = 1; p.band_n[row] = 0; } return; }
   // pass 2: only the band members (key >= key(lim)) go back to their record for the corpus index
   const unsigned int lim_key = f2key(lim + 0.0f);
   const unsigned int lt_mask = (1u << lane) - 1u;
@@ -773,12 +790,54 @@ tc_rescore_kernel(const FinParams p) {
     if (tid == 0) { const int c = p.out_count[row] + greater_sh; p.out_count[row] = c < p.k ? c : p.k; }
     return;
   }
-  for (int t = tid; t < m; t += RS_BLOCK) {
-    const unsigned int idx = band[t];
-    const float s = exact_score(qs, p.corpus + (long long)idx * p.d, p.d);
-    sk[t] = ((unsigned long long)f2key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+  if (p.d == 64) {
+    // d = 64 (the headline shape): EIGHT lanes fetch one 256-byte corpus row (32 bytes each, one coalesced request per row;
+    // every row of the band is in flight before the first FMA), then the canonical chain k = 0..63 walks through the eight
+    // lanes with the accumulator handed on by shuffle -- same arithmetic, same order, same bits as exact_score().
+    constexpr int RPB = RS_BLOCK / 8;          // rows per block round
+    constexpr int MAXR = 8;                    // rounds held in registers (m <= 128); larger bands loop
+    const int sub = tid & 7, grp = tid >> 3;
+    for (int t0 = 0; t0 < m; t0 += RPB * MAXR) {
+      float4 a[MAXR], b[MAXR];
+#pragma unroll
+      for (int r = 0; r < MAXR; ++r) {
+        const int t = t0 + r * RPB + grp;
+        if (t < m) {
+          const float4* src = reinterpret_cast<const float4*>(p.corpus + (long long)band[t] * 64) + sub * 2;
+          a[r] = __ldg(src); b[r] = __ldg(src + 1);
+        }
+      }
+      const float q0 = qs[sub * 8], q1 = qs[sub * 8 + 1], q2 = qs[sub * 8 + 2], q3 = qs[sub * 8 + 3];
+      const float q4 = qs[sub * 8 + 4], q5 = qs[sub * 8 + 5], q6 = qs[sub * 8 + 6], q7 = qs[sub * 8 + 7];
+#pragma unroll
+      for (int r = 0; r < MAXR; ++r) {
+        const int t = t0 + r * RPB + grp;
+        const bool live = t < m;                    // uniform per 8-lane group; the shuffles below are executed by all lanes
+        float acc = 0.f;
+#pragma unroll
+        for (int step = 0; step < 8; ++step) {
+          if (sub == step && live) {
+            acc = fmaf(q0, a[r].x, acc); acc = fmaf(q1, a[r].y, acc); acc = fmaf(q2, a[r].z, acc); acc = fmaf(q3, a[r].w, acc);
+            acc = fmaf(q4, b[r].x, acc); acc = fmaf(q5, b[r].y, acc); acc = fmaf(q6, b[r].z, acc); acc = fmaf(q7, b[r].w, acc);
+          }
+          acc = __shfl_sync(0xffffffffu, acc, (threadIdx.x & 24) | step);   // hand the accumulator to the next lane of the group
+        }
+        if (live && sub == 0) {
+          const unsigned int idx = band[t];
+          sk[t] = ((unsigned long long)f2key(acc + 0.0f) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+        }
+      }
+    }
+  } else {
+    for (int t = tid; t < m; t += RS_BLOCK) {
+      const unsigned int idx = band[t];
+      const float s = exact_score(qs, p.corpus + (long long)idx * p.d, p.d);
+      sk[t] = ((unsigned long long)f2key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+    }
   }
   __syncthreads();
+  if (MODE == FIN_TOPK && m < p.k)   // short shard list: pad with (-inf, INT64_MAX), the merge's "no entry"
+    for (int t = m + tid; t < p.k; t += RS_BLOCK) { p.out_s[row * p.k + t] = -INFINITY; p.out_i[row * p.k + t] = LLONG_MAX; }
   for (int t = tid; t < m; t += RS_BLOCK) {
     const unsigned long long mine = sk[t];
     int rank = 0;
@@ -998,6 +1057,9 @@ struct Call {
   float* out_s; long long* out_i;                                                       // TOPK / EXCLUDE
   const long long* identifiers; const long long* exclusions; int n_excl; int k_out;     // EXCLUDE
   const float* pos; int* out_count;                                                     // COUNT
+  // sharded scan: called between the threshold kernel and the filter pass with the device arrays that define the filter
+  // thresholds; may raise thr[] (comm.cu exchanges a global lower bound of the k-th best score across the shards)
+  ThrHook hook; void* hook_ctx; int allow_short;
 };
 
 static int run_call(const Call& c) {
@@ -1043,6 +1105,10 @@ static int run_call(const Call& c) {
   else
     tc_threshold_kernel<32><<<(unsigned)ceil_div(c.Q * 32, 256), 256, 0, st>>>(binmax, pl.bins_ld, pl.n_bins, c.k, margin, thr, ovf, c.Q);
   TFRS_LAUNCH_CHECK();
+  if (c.hook) {
+    rc = c.hook(c.hook_ctx, thr, margin, cut, qexp, &hdr->st.exp, c.Q, st);
+    if (rc) return rc;
+  }
   prof_mark(st, 2);
   // (2) full pass with the fused threshold filter
   rc = launch_scan_mode(pl, sp, st, MODE_FILTER);
@@ -1053,7 +1119,7 @@ static int run_call(const Call& c) {
   fp.q = c.q; fp.corpus = c.corpus; fp.d = c.d; fp.k = c.k; fp.index_offset = c.index_offset; fp.N = c.N; fp.Q = c.Q;
   fp.count = count; fp.cand_s = cand_s; fp.cand_i = cand_i; fp.segs = pl.parts_full * 2; fp.cap_part = pl.cap_part;
   fp.cut = cut; fp.thr = thr; fp.overflow = ovf; fp.out_s = c.out_s; fp.out_i = c.out_i;
-  fp.cap_keys = pl.cap_keys; fp.cap_band = pl.cap_band;
+  fp.cap_keys = pl.cap_keys; fp.cap_band = pl.cap_band; fp.allow_short = c.allow_short;
   fp.band_idx = (unsigned int*)(w + pl.o_band); fp.band_n = (int*)(w + pl.o_bandn);
   fp.identifiers = c.identifiers; fp.exclusions = c.exclusions; fp.n_excl = c.n_excl; fp.k_out = c.k_out;
   fp.pos = c.pos; fp.qexp = qexp; fp.hdr = hdr; fp.out_count = c.out_count;
@@ -1135,6 +1201,18 @@ extern "C" int tfrs_topk_tc_f32(const float* q, int64_t Q, const float* corpus, 
   c.mode = FIN_TOPK; c.q = q; c.Q = Q; c.corpus = corpus; c.index_buf = index_buf; c.N = N; c.d = d; c.k = k;
   c.index_offset = index_offset; c.ws = ws; c.ws_bytes = ws_bytes; c.st = (cudaStream_t)stream;
   c.out_s = out_scores; c.out_i = (long long*)out_idx;
+  return run_call(c);
+}
+
+// internal (comm.cu): the local scan of the sharded call, with the threshold hook and short lists allowed
+int tfrs::tc_topk_sharded_local(const float* q, int64_t Q, const float* corpus, const void* index_buf, int64_t N, int d, int k,
+                                int64_t index_offset, float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes, void* stream,
+                                tfrs::ThrHook hook, void* hook_ctx) {
+  Call c{};
+  c.mode = FIN_TOPK; c.q = q; c.Q = Q; c.corpus = corpus; c.index_buf = index_buf; c.N = N; c.d = d; c.k = k;
+  c.index_offset = index_offset; c.ws = ws; c.ws_bytes = ws_bytes; c.st = (cudaStream_t)stream;
+  c.out_s = out_scores; c.out_i = (long long*)out_idx;
+  c.hook = hook; c.hook_ctx = hook_ctx; c.allow_short = hook ? 1 : 0;
   return run_call(c);
 }
 

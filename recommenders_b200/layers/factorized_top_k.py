@@ -119,6 +119,8 @@ class ShardComm:
     _ffi.check(_ffi.lib().tfrs_comm_create(ctypes.byref(self._handle), self.rank, self.world, raw), "comm_create")
     # peer-memory exchange (NVLink stores + epoch flags) instead of the NCCL all-gather; TFRS_SHARD_EXCHANGE=nccl keeps NCCL
     self.p2p = self.world > 1 and os.environ.get("TFRS_SHARD_EXCHANGE", "p2p").lower() != "nccl"
+    if os.environ.get("TFRS_SHARD_THRESHOLD_EXCHANGE", "1") == "0":   # A/B switch; must be the same on every rank
+      _ffi.check(_ffi.lib().tfrs_comm_set_option(self._handle, 0, 0), "comm_set_option")
 
   def ensure_p2p(self, Q: int, k: int) -> bool:
     """Maps the exchange buffers for (Q, k) calls if they are not big enough yet (collective: all ranks see the same
