@@ -256,6 +256,37 @@ int tfrs_inbatch_softmax_tc_bwd(const float* q, const float* c, int64_t B, int64
                                 const float* lse, const float* grad_loss, float* dq, float* dc, void* ws,
                                 size_t ws_bytes, void* stream);
 
+/* The remaining tfrs.tasks.Retrieval loss options inside the tensor-core loss, forward and backward:
+ *   candidate_ids  (nullable, int64 [C])     remove_accidental_hits: every candidate j != i whose id equals the id of query
+ *                                            i's positive (candidate i) gets logit MIN_FLOAT (tasks/retrieval.py:194-200,
+ *                                            layers/loss.py:114-147; `logits + dup * MIN_FLOAT` rounds to MIN_FLOAT in fp32)
+ *   score_mask     (nullable, uint8 [B, C])  where(mask, s, MIN_FLOAT) (retrieval.py:202-203); row-major, nonzero = keep
+ * applied after the temperature and the bias, in the reference's order.  The ids / keep-bits are tested against the fp32
+ * accumulators in registers: no [B,C] logits, labels or masks are materialised (the byte mask is packed to bits once).
+ * Masked entries get zero gradient.  Same shape limits as the plain entry points; *_ex_workspace_bytes sizes `ws`. */
+size_t tfrs_inbatch_softmax_tc_ex_workspace_bytes(int64_t B, int64_t C, int d, int has_ids, int has_mask);
+int tfrs_inbatch_softmax_tc_fwd_ex(const float* q, const float* c, int64_t B, int64_t C, int d, float inv_temperature,
+                                   const float* sample_weight, const float* candidate_bias, const int64_t* candidate_ids,
+                                   const uint8_t* score_mask, float* loss, float* lse, void* ws, size_t ws_bytes,
+                                   void* stream);
+size_t tfrs_inbatch_softmax_tc_bwd_ex_workspace_bytes(int64_t B, int64_t C, int d, int has_ids, int has_mask);
+int tfrs_inbatch_softmax_tc_bwd_ex(const float* q, const float* c, int64_t B, int64_t C, int d, float inv_temperature,
+                                   const float* sample_weight, const float* candidate_bias, const int64_t* candidate_ids,
+                                   const uint8_t* score_mask, const float* lse, const float* grad_loss, float* dq, float* dc,
+                                   void* ws, size_t ws_bytes, void* stream);
+
+/* Hard-negative mining inside the loss (tasks/retrieval.py:205-210, layers/loss.py:61-111) without the [B,C] logits: the
+ * n + 1 best candidates of every query come from the top-K scan above (k1 = min(n + 1, C) entries per query, exact fp32
+ * scores, sorted); tfrs_hardneg_loss_fwd keeps the positive (candidate i of query i, score `positive_scores[i]`) plus the
+ * n best other candidates and computes  loss = sum_i w_i (logsumexp(kept logits / T) - positive / T)  and the gradient
+ * coefficients `coef` [B, k1 + 2] (entry t of the list, then the positive, then the row loss; w_i / T folded in).
+ * tfrs_hardneg_loss_bwd:  dq_i = g sum_t coef_it c_{j_t}  (fixed order),  dc_j += g coef_it q_i  (float atomics: the only
+ * non-bit-reproducible kernel of the library; dc is zeroed by the call). */
+int tfrs_hardneg_loss_fwd(const float* top_scores, const int64_t* top_idx, int64_t B, int k1, const float* positive_scores,
+                          float inv_temperature, const float* sample_weight, float* loss, float* coef, void* stream);
+int tfrs_hardneg_loss_bwd(const float* q, const float* c, int64_t B, int64_t C, int d, const int64_t* top_idx, int k1,
+                          const float* coef, const float* grad_loss, float* dq, float* dc, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K4  sparse Adagrad on the rows touched by a batch (optimizer.apply_gradients with IndexedSlices,
  * models/base.py:77-78; Adagrad chosen by the user, README.md:84).  Duplicate ids are summed in
@@ -302,6 +333,31 @@ size_t tfrs_cross_tc_bwd_workspace_bytes(int64_t B, int D);
 int tfrs_cross_tc_bwd_f32(const float* x0, const float* x, const float* W, const float* prod, const float* dout,
                           int64_t B, int D, int64_t ld, float diag_scale, float* dx0, float* dx, float* dW,
                           float* dbias, void* ws, size_t ws_bytes, void* stream);
+
+/* General fp32-parity GEMM on the tensor cores (the same exact-rescale + fp16 hi/lo split scheme, ~2^-21 relative error):
+ *   C[M,N] = opA(A) . opB(B),  opA(m,k) = transA ? A[k*lda+m] : A[m*lda+k],  opB(k,n) = transB ? B[n*ldb+k] : B[k*ldb+n].
+ * Reductions longer than 1024 are accumulated in chunks of 1024 with a fixed-order sum of the partials (deterministic).
+ * Serves the projections of the low-rank Cross below and large `_compute_score`-style products. */
+size_t tfrs_gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int tfrs_gemm_tc_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                     int64_t ldb, float* C, int64_t ldc, void* ws, size_t ws_bytes, void* stream);
+
+/* Low-rank DCN-v2 cross layer on the tensor cores (layers/feature_interaction/dcn.py:131-148,178-179 `projection_dim`;
+ * the layer of MultiLayerDCN, multi_layer_dcn.py:146-148):
+ *   t = x . U  [B,p] ;  out = x0 * (t . V + bias + diag_scale * x) + x       U [D,p], V [p,D] in Keras [in,out] layout
+ * Two tcgen05 GEMMs; the cross formula is the epilogue of the second one (no [B,D] product round trip).  `t` (required)
+ * and `prod` (nullable) are kept for the backward pass:
+ *   gp = g*x0 ; dx0 = g*prod ; dt = gp.V^T ; dV = t^T.gp ; dU = x^T.dt ; dx = dt.U^T + diag_scale*gp + g ; dbias = colsum(gp)
+ * -- four tensor-core GEMMs, deterministic.  D, p <= 1024.  dx0 / dx / dU / dV / dbias are nullable. */
+size_t tfrs_cross_lowrank_tc_workspace_bytes(int64_t B, int D, int p);
+int tfrs_cross_lowrank_tc_fwd_f32(const float* x0, const float* x, const float* U, const float* V, const float* bias, int64_t B,
+                                  int D, int p, int64_t ld, float diag_scale, float* out, float* prod, float* t, void* ws,
+                                  size_t ws_bytes, void* stream);
+size_t tfrs_cross_lowrank_tc_bwd_workspace_bytes(int64_t B, int D, int p);
+int tfrs_cross_lowrank_tc_bwd_f32(const float* x0, const float* x, const float* U, const float* V, const float* t,
+                                  const float* prod, const float* dout, int64_t B, int D, int p, int64_t ld, float diag_scale,
+                                  float* dx0, float* dx, float* dU, float* dV, float* dbias, void* ws, size_t ws_bytes,
+                                  void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * DLRM DotInteraction (layers/feature_interaction/dot_interaction.py:53-104): feats [B,F,d] ->

@@ -277,6 +277,46 @@ def retrieval_loss_grads(q, c, sample_weight=None, temperature=None):
   return g @ c64, g.T @ q64
 
 
+def retrieval_loss_and_grads_general(q, c, sample_weight=None, temperature=None, candidate_sampling_probability=None,
+                                     candidate_ids=None, remove_accidental_hits_=False, score_mask=None,
+                                     num_hard_negatives=None):
+  """float64 loss, d loss/d q, d loss/d c of Retrieval.call with every option (tasks/retrieval.py:178-210, layers/loss.py),
+  2-D queries.  Gradient rules follow the TF ops: `logits + dup * MIN_FLOAT` passes the gradient (the probability of such
+  an entry is 0), `tf.where(mask, s, MIN_FLOAT)` blocks it, hard-negative mining gathers: only the selected columns count."""
+  q64 = np.asarray(q, np.float64); c64 = np.asarray(c, np.float64)
+  B, C = q64.shape[0], c64.shape[0]
+  t = 1.0 if temperature is None else float(temperature)
+  s = (q64 @ c64.T) / t
+  eye = np.eye(B, C)
+  if candidate_sampling_probability is not None:
+    s = s - np.log(np.clip(np.asarray(candidate_sampling_probability, np.float64), 1e-6, 1.0))[None, :]
+  blocked = np.zeros((B, C), bool)
+  if remove_accidental_hits_:
+    ids = np.asarray(candidate_ids)
+    dup = (ids[:B][:, None] == ids[None, :]) & (eye == 0)
+    s = s + dup * float(MIN_FLOAT)
+  if score_mask is not None:
+    keep = np.asarray(score_mask, bool)
+    s = np.where(keep, s, float(MIN_FLOAT))
+    blocked |= ~keep
+  active = np.ones((B, C), bool)
+  if num_hard_negatives is not None:
+    n = min(num_hard_negatives + 1, C)
+    key = s + eye * float(MAX_FLOAT)
+    order = np.lexsort((np.broadcast_to(np.arange(C), (B, C)), -key), axis=1)[:, :n]   # value desc, index asc
+    active = np.zeros((B, C), bool)
+    np.put_along_axis(active, order, True, 1)
+  sm = np.where(active, s, -np.inf)
+  m = sm.max(1, keepdims=True)
+  e = np.exp(sm - m)
+  z = e.sum(1, keepdims=True)
+  w = np.ones(B) if sample_weight is None else np.asarray(sample_weight, np.float64).reshape(-1)
+  loss = float((w * ((m[:, 0] - (eye * s).sum(1)) + np.log(z[:, 0]))).sum())   # max-subtracted, as TF's fused op
+  g = (e / z - eye) * active
+  g = np.where(blocked, 0.0, g) * (w[:, None] / t)
+  return loss, g @ c64, g.T @ q64
+
+
 # ----------------------------------------------------------------------------------------------
 # Cross layer   (layers/feature_interaction/dcn.py:151-186)
 # ----------------------------------------------------------------------------------------------

@@ -69,6 +69,12 @@ _SIGNATURES = {
     "tfrs_inbatch_softmax_tc_fwd": (c_i, [c_p, c_p, c_l, c_l, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "tfrs_inbatch_softmax_tc_bwd_workspace_bytes": (c_sz, [c_l, c_l, c_i]),
     "tfrs_inbatch_softmax_tc_bwd": (c_i, [c_p, c_p, c_l, c_l, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "tfrs_inbatch_softmax_tc_ex_workspace_bytes": (c_sz, [c_l, c_l, c_i, c_i, c_i]),
+    "tfrs_inbatch_softmax_tc_fwd_ex": (c_i, [c_p, c_p, c_l, c_l, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "tfrs_inbatch_softmax_tc_bwd_ex_workspace_bytes": (c_sz, [c_l, c_l, c_i, c_i, c_i]),
+    "tfrs_inbatch_softmax_tc_bwd_ex": (c_i, [c_p, c_p, c_l, c_l, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "tfrs_hardneg_loss_fwd": (c_i, [c_p, c_p, c_l, c_i, c_p, c_f, c_p, c_p, c_p, c_p]),
+    "tfrs_hardneg_loss_bwd": (c_i, [c_p, c_p, c_l, c_l, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
     "tfrs_sparse_adagrad_workspace_bytes": (c_sz, [c_l, c_i]),
     "tfrs_sparse_adagrad_f32": (c_i, [c_p, c_p, c_l, c_i, c_p, c_i, c_l, c_p, c_f, c_f, c_i, c_p, c_sz, c_p]),
     "tfrs_cross_fwd_f32": (c_i, [c_p, c_p, c_p, c_p, c_l, c_i, c_l, c_f, c_p, c_p, c_p]),
@@ -80,6 +86,13 @@ _SIGNATURES = {
     "tfrs_cross_bwd_f32": (c_i, [c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_l, c_f, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "tfrs_cross_tc_bwd_workspace_bytes": (c_sz, [c_l, c_i]),
     "tfrs_cross_tc_bwd_f32": (c_i, [c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_l, c_f, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "tfrs_gemm_tc_workspace_bytes": (c_sz, [c_l, c_l, c_l]),
+    "tfrs_gemm_tc_f32": (c_i, [c_i, c_i, c_l, c_l, c_l, c_p, c_l, c_p, c_l, c_p, c_l, c_p, c_sz, c_p]),
+    "tfrs_cross_lowrank_tc_workspace_bytes": (c_sz, [c_l, c_i, c_i]),
+    "tfrs_cross_lowrank_tc_fwd_f32": (c_i, [c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_l, c_f, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "tfrs_cross_lowrank_tc_bwd_workspace_bytes": (c_sz, [c_l, c_i, c_i]),
+    "tfrs_cross_lowrank_tc_bwd_f32": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_l, c_f, c_p, c_p, c_p, c_p, c_p,
+                                           c_p, c_sz, c_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

@@ -199,3 +199,111 @@ extern "C" int tfrs_cross_tc_bwd_f32(const float* x0, const float* x, const floa
   }
   return TFRS_OK;
 }
+
+// ---- general tensor-core GEMM (the low-rank Cross projections; ops.matmul on large shapes) --------------------------------
+//   C[M,N] = opA(A) . opB(B),  opA(m,k) = transA ? A[k*lda + m] : A[m*lda + k],  opB(k,n) = transB ? B[n*ldb + k] : B[k*ldb + n]
+extern "C" size_t tfrs_gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t K) { return tc::gemm_tc_workspace(M, N, K); }
+
+extern "C" int tfrs_gemm_tc_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                                int64_t ldb, float* C, int64_t ldc, void* ws, size_t ws_bytes, void* stream) {
+  TFRS_CHECK_ARG(A && B && C, "gemm_tc: NULL pointer");
+  TFRS_CHECK_ARG(M > 0 && N > 0 && K > 0 && ldc >= N, "gemm_tc: bad shape");
+  const tc::GemmOperand a{A, lda, transA != 0};
+  const tc::GemmOperand b{B, ldb, transB == 0};   // image rows = n, reduction index k: B[k*ldb + n] is the "transposed" read
+  const tc::GemmEpilogue ep{tc::GEMM_EPI_PLAIN, nullptr, 0, nullptr, 0, nullptr, 0.f, nullptr};
+  return tc::gemm_tc(a, b, M, N, K, ep, C, ldc, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// ---- low-rank Cross on the tensor cores (dcn.py:131-148,178-179; multi_layer_dcn.py:146-148) -------------------------------
+//   t = x . U   [B,p]        (U [D,p]: Dense(projection_dim, use_bias=False))
+//   out = x0 * (t . V + bias + diag * x) + x      (V [p,D]: Dense(D)) -- the cross formula is the second GEMM's epilogue
+namespace tfrs {
+static size_t lr_gemm_ws(long long B, int D, int p) {
+  size_t a = tc::gemm_tc_workspace(B, p, D), b = tc::gemm_tc_workspace(B, D, p);
+  size_t c = tc::gemm_tc_workspace(p, D, B), d = tc::gemm_tc_workspace(D, p, B);
+  size_t m = a > b ? a : b; m = m > c ? m : c; return m > d ? m : d;
+}
+}  // namespace tfrs
+
+extern "C" size_t tfrs_cross_lowrank_tc_workspace_bytes(int64_t B, int D, int p) {
+  if (B <= 0 || D <= 0 || p <= 0) return 0;
+  const size_t a = tc::gemm_tc_workspace(B, p, D), b = tc::gemm_tc_workspace(B, D, p);
+  return a > b ? a : b;
+}
+
+extern "C" int tfrs_cross_lowrank_tc_fwd_f32(const float* x0, const float* x, const float* U, const float* V, const float* bias,
+                                             int64_t B, int D, int p, int64_t ld, float diag_scale, float* out, float* prod,
+                                             float* t, void* ws, size_t ws_bytes, void* stream) {
+  TFRS_CHECK_ARG(x0 && x && U && V && out && t, "cross_lowrank_tc_fwd: NULL pointer");
+  TFRS_CHECK_ARG(B > 0 && D > 0 && p > 0 && ld >= D, "cross_lowrank_tc_fwd: bad shape");
+  TFRS_CHECK_ARG(diag_scale >= 0.f, "`diag_scale` should be non-negative. Got `diag_scale` = %g", diag_scale);
+  if (D > 1024 || p > 1024) { set_error("cross_lowrank_tc_fwd: needs D, projection_dim <= 1024"); return TFRS_ERR_UNSUPPORTED; }
+  cudaStream_t st = (cudaStream_t)stream;
+  // t = x . U : image rows of B' = the p outputs, element (n, k) = U[k*p + n]
+  int rc = tc::gemm_tc(tc::GemmOperand{x, ld, false}, tc::GemmOperand{U, p, true}, B, p, D,
+                       tc::GemmEpilogue{tc::GEMM_EPI_PLAIN, nullptr, 0, nullptr, 0, nullptr, 0.f, nullptr}, t, p, ws, ws_bytes, st);
+  if (rc) return rc;
+  // out = x0 * (t . V + bias + diag x) + x : element (n, k) = V[k*D + n]
+  return tc::gemm_tc(tc::GemmOperand{t, p, false}, tc::GemmOperand{V, D, true}, B, D, p,
+                     tc::GemmEpilogue{tc::GEMM_EPI_CROSS, x0, ld, x, ld, bias, diag_scale, prod}, out, ld, ws, ws_bytes, st);
+}
+
+// backward:  gp = g * x0 ; dx0 = g * prod ; dt = gp . V^T ; dV = t^T . gp ; dU = x^T . dt ; dx = dt . U^T + diag * gp + g ;
+//            dbias = colsum(gp).  All four GEMMs on the tensor cores (the two batch-long reductions chunked, partials summed
+//            in fixed order): deterministic.
+extern "C" size_t tfrs_cross_lowrank_tc_bwd_workspace_bytes(int64_t B, int D, int p) {
+  if (B <= 0 || D <= 0 || p <= 0) return 0;
+  return align_up((size_t)B * D * 4, 1024) + align_up((size_t)B * p * 4, 1024) + align_up((size_t)CROSS_COL_SPLITS * D * 4, 1024) +
+         lr_gemm_ws(B, D, p);
+}
+
+extern "C" int tfrs_cross_lowrank_tc_bwd_f32(const float* x0, const float* x, const float* U, const float* V, const float* t,
+                                             const float* prod, const float* dout, int64_t B, int D, int p, int64_t ld,
+                                             float diag_scale, float* dx0, float* dx, float* dU, float* dV, float* dbias, void* ws,
+                                             size_t ws_bytes, void* stream) {
+  TFRS_CHECK_ARG(x0 && x && U && V && t && dout, "cross_lowrank_tc_bwd: NULL pointer");
+  TFRS_CHECK_ARG(B > 0 && D > 0 && p > 0 && ld >= D && B < (1ll << 31), "cross_lowrank_tc_bwd: bad shape");
+  TFRS_CHECK_ARG(!dx0 || prod, "cross_lowrank_tc_bwd: dx0 needs the saved `prod`");
+  if (D > 1024 || p > 1024) { set_error("cross_lowrank_tc_bwd: needs D, projection_dim <= 1024"); return TFRS_ERR_UNSUPPORTED; }
+  if (!ws || ws_bytes < tfrs_cross_lowrank_tc_bwd_workspace_bytes(B, D, p)) { set_error("cross_lowrank_tc_bwd: workspace too small"); return TFRS_ERR_WORKSPACE_TOO_SMALL; }
+  TFRS_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "cross_lowrank_tc_bwd: workspace must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* w = (unsigned char*)ws;
+  float* gp = (float*)w; w += align_up((size_t)B * D * 4, 1024);
+  float* dt = (float*)w; w += align_up((size_t)B * p * 4, 1024);
+  float* colpart = (float*)w; w += align_up((size_t)CROSS_COL_SPLITS * D * 4, 1024);
+  const size_t gws = ws_bytes - (size_t)(w - (unsigned char*)ws);
+  const long long total = (long long)B * D;
+  const unsigned blocks = (unsigned)(ceil_div(total, 256) < 148 * 16 ? ceil_div(total, 256) : 148 * 16);
+  cross_bwd_elem<<<blocks, 256, 0, st>>>(x0, prod, dout, B, D, ld, gp, dx0, nullptr);
+  TFRS_LAUNCH_CHECK();
+  const tc::GemmEpilogue plain{tc::GEMM_EPI_PLAIN, nullptr, 0, nullptr, 0, nullptr, 0.f, nullptr};
+  int rc;
+  if (dx || dU) {   // dt[b, j] = sum_o gp[b, o] V[j, o]
+    rc = tc::gemm_tc(tc::GemmOperand{gp, D, false}, tc::GemmOperand{V, D, false}, B, p, D, plain, dt, p, w, gws, st);
+    if (rc) return rc;
+  }
+  if (dV) {         // dV[j, o] = sum_b t[b, j] gp[b, o]
+    rc = tc::gemm_tc(tc::GemmOperand{t, p, true}, tc::GemmOperand{gp, D, true}, p, D, B, plain, dV, D, w, gws, st);
+    if (rc) return rc;
+  }
+  if (dU) {         // dU[i, j] = sum_b x[b, i] dt[b, j]
+    rc = tc::gemm_tc(tc::GemmOperand{x, ld, true}, tc::GemmOperand{dt, p, true}, D, p, B, plain, dU, p, w, gws, st);
+    if (rc) return rc;
+  }
+  if (dx) {         // dx[b, i] = sum_j dt[b, j] U[i, j] + diag gp[b, i] + g[b, i]
+    rc = tc::gemm_tc(tc::GemmOperand{dt, p, false}, tc::GemmOperand{U, p, false}, B, D, p,
+                     tc::GemmEpilogue{tc::GEMM_EPI_DX, gp, D, dout, ld, nullptr, diag_scale, nullptr}, dx, ld, w, gws, st);
+    if (rc) return rc;
+  }
+  if (dbias) {
+    long long rps = ceil_div(B, CROSS_COL_SPLITS);
+    int used = (int)ceil_div(B, rps);
+    dim3 grid((unsigned)ceil_div(D, 256), (unsigned)used);
+    cross_colsum_partial<<<grid, 256, 0, st>>>(gp, B, D, rps, colpart);
+    TFRS_LAUNCH_CHECK();
+    cross_reduce_splits<<<(unsigned)ceil_div(D, 256), 256, 0, st>>>(colpart, D, used, dbias);
+    TFRS_LAUNCH_CHECK();
+  }
+  return TFRS_OK;
+}

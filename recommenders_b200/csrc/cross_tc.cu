@@ -117,6 +117,20 @@ cross_tc_kernel(const CrossParams p) {
       const uint32_t tphase = (it >> 1) & 1;
       const long long mb = t / p.n_nt; const int nt = (int)(t % p.n_nt);
       const int n0 = nt * 128 + half * 64;
+      {
+        // x / x0 of the NEXT tile are pulled into L2 now, one tile time ahead of their use: otherwise every batch of row
+        // loads below waits a full DRAM round trip and the epilogue, not the MMAs, paces the kernel
+        const long long tn = t + gridDim.x;
+        if (tn < n_tiles) {
+          const long long rn = (tn / p.n_nt) * 256 + ab * 128 + quad * 32 + lane;
+          const int cn = (int)(tn % p.n_nt) * 128 + half * 64;
+          if (rn < p.B && cn < p.D) {
+            const int c1 = min(cn + 32, p.D - 1);
+            prefetch_l2(p.x + rn * p.ld + cn); prefetch_l2(p.x + rn * p.ld + c1);
+            prefetch_l2(p.x0 + rn * p.ld + cn); prefetch_l2(p.x0 + rn * p.ld + c1);
+          }
+        }
+      }
       mbar_wait(&t_full[buf], tphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ab * 2 + buf) * 128 + half * 64);

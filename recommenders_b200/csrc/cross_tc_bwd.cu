@@ -24,17 +24,19 @@ constexpr int SG_THREADS2 = 640;
 constexpr int SG_STAGES2 = 2;
 constexpr int SG_STAGE_BYTES = 6 * 16384;  // A: 2 blocks x (hi, lo); B: (hi, lo)
 constexpr int DW_CHUNK_SLABS = 16;         // 1024 batch rows per accumulation chain
-enum { SG_DX = 1, SG_DW = 2 };
+enum { SG_DX = 1, SG_DW = 2, SG_PLAIN = 3, SG_CROSS = 4 };
 
 struct SgParams {
   const unsigned char* aimg; const unsigned char* bimg;  // [tile128][kb_total][hi|lo][16 KB]
   const CxStats* ast; const CxStats* bst;
   int kb_total, kb_chunk, n_mb, n_nt, n_kc;
   long long M, N;                     // valid rows / columns of the product
-  const float* e0; long long ld0;     // DX: gp (ld D)
-  const float* e1; long long ld1;     // DX: g = dout
+  const float* e0; long long ld0;     // DX: gp (ld D);            CROSS: x0
+  const float* e1; long long ld1;     // DX: g = dout;             CROSS: x
+  const float* bias;                  // CROSS: bias [N] (nullable)
   float diag;
-  float* out; long long ld_out;       // DX: dx;  DW: partial [n_kc][M][N]
+  float* out; long long ld_out;       // DX: dx;  DW: partial [n_kc][M][N];  PLAIN: C;  CROSS: out
+  float* prod;                        // CROSS: x.W + bias + diag*x for the backward pass (nullable, ld_out)
 };
 
 template <int MODE>
@@ -126,6 +128,20 @@ split_gemm_kernel(const SgParams p) {
       const int buf = it & 1;
       const uint32_t tphase = (it >> 1) & 1;
       const int n0 = nt * 128 + half * 64;
+      if (MODE == SG_DX || MODE == SG_CROSS) {
+        // The epilogue operands of the NEXT tile are pulled into L2 now, one tile time ahead of their use: without it
+        // every batch of row loads below waits a full DRAM round trip and the epilogue, not the MMAs, paces the kernel.
+        const long long tn = t + gridDim.x;
+        if (tn < n_items) {
+          const long long remn = tn % per_chunk;
+          const long long rn = (remn / p.n_nt) * 256 + ab * 128 + quad * 32 + lane;
+          const int cn = (int)(remn % p.n_nt) * 128 + half * 64;
+          if (rn < p.M && cn < p.N) {
+            if (MODE == SG_CROSS || p.diag != 0.f) { prefetch_l2(p.e0 + rn * p.ld0 + cn); prefetch_l2(p.e0 + rn * p.ld0 + min(cn + 32, (int)p.N - 1)); }
+            prefetch_l2(p.e1 + rn * p.ld1 + cn); prefetch_l2(p.e1 + rn * p.ld1 + min(cn + 32, (int)p.N - 1));
+          }
+        }
+      }
       mbar_wait(&t_full[buf], tphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ab * 2 + buf) * 128 + half * 64);
@@ -161,6 +177,35 @@ split_gemm_kernel(const SgParams p) {
             for (int j = 0; j < 32; ++j) {
               const long long rr = row_base + j;
               if (rr < p.M) dst[rr * p.N] = __uint_as_float(r[blk * 32 + j]) * unscale;
+            }
+          } else if (MODE == SG_PLAIN) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const long long rr = row_base + j;
+              if (rr < p.M) p.out[rr * p.ld_out + col] = __uint_as_float(r[blk * 32 + j]) * unscale;
+            }
+          } else if (MODE == SG_CROSS) {   // out = x0 * (acc + bias + diag * x) + x   (dcn.py:176-186)
+            const float bcol = p.bias ? __ldg(p.bias + col) : 0.f;
+#pragma unroll
+            for (int j0 = 0; j0 < 32; j0 += 4) {   // 8 independent loads in flight before the first store
+              float xv[4], x0v[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const long long rr = row_base + j0 + u;
+                const bool ok = rr < p.M;
+                x0v[u] = ok ? __ldg(p.e0 + rr * p.ld0 + col) : 0.f;
+                xv[u] = ok ? __ldg(p.e1 + rr * p.ld1 + col) : 0.f;
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const long long rr = row_base + j0 + u;
+                if (rr < p.M) {
+                  float pv = __uint_as_float(r[blk * 32 + j0 + u]) * unscale + bcol;
+                  if (p.diag != 0.f) pv += p.diag * xv[u];
+                  if (p.prod) p.prod[rr * p.ld_out + col] = pv;
+                  p.out[rr * p.ld_out + col] = x0v[u] * pv + xv[u];
+                }
+              }
             }
           } else {
 #pragma unroll
@@ -267,12 +312,95 @@ static int sg_launch(int mode, const SgParams& p, cudaStream_t st) {
   const size_t smem = (size_t)SG_STAGES2 * SG_STAGE_BYTES + 1024 + 256;
   TFRS_DYN_SMEM(split_gemm_kernel<SG_DX>, (int)smem);
   TFRS_DYN_SMEM(split_gemm_kernel<SG_DW>, (int)smem);
+  TFRS_DYN_SMEM(split_gemm_kernel<SG_PLAIN>, (int)smem);
+  TFRS_DYN_SMEM(split_gemm_kernel<SG_CROSS>, (int)smem);
   const long long items = (long long)p.n_mb * p.n_nt * p.n_kc;
   int grid = sm_count(); if (grid > items) grid = (int)items;
   if (mode == SG_DX) split_gemm_kernel<SG_DX><<<grid, SG_THREADS2, smem, st>>>(p);
-  else split_gemm_kernel<SG_DW><<<grid, SG_THREADS2, smem, st>>>(p);
+  else if (mode == SG_DW) split_gemm_kernel<SG_DW><<<grid, SG_THREADS2, smem, st>>>(p);
+  else if (mode == SG_PLAIN) split_gemm_kernel<SG_PLAIN><<<grid, SG_THREADS2, smem, st>>>(p);
+  else split_gemm_kernel<SG_CROSS><<<grid, SG_THREADS2, smem, st>>>(p);
   TFRS_LAUNCH_CHECK();
   return TFRS_OK;
+}
+
+// ---- general split-fp16 GEMM: C[M,N] = A'[M,K] . B'[N,K]^T with one of the epilogues above ------------------------------
+// An operand is described by where element (row r of the image, reduction index k) lives in memory.
+struct GtPlan { int n_mb, n_nt, kb, n_kc; size_t o_st, o_aimg, o_bimg, o_partial, total; };
+static void gt_plan(long long M, long long N, long long K, GtPlan& pl) {
+  pl.n_mb = (int)ceil_div(M, 256); pl.n_nt = (int)ceil_div(N, 128); pl.kb = (int)ceil_div(K, 64);
+  pl.n_kc = (int)ceil_div(pl.kb, DW_CHUNK_SLABS);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 1024); return r; };
+  pl.o_st = take(2048);
+  pl.o_aimg = take((size_t)pl.n_mb * 2 * pl.kb * 32768);
+  pl.o_bimg = take((size_t)pl.n_nt * pl.kb * 32768);
+  pl.o_partial = take(pl.n_kc > 1 ? (size_t)pl.n_kc * M * N * 4 : 0);
+  pl.total = o;
+}
+size_t gemm_tc_workspace(long long M, long long N, long long K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  GtPlan pl; gt_plan(M, N, K, pl);
+  return pl.total;
+}
+
+// out[m*ld + n] = sum_z partial[z][m][n]  (z ascending: deterministic)
+__global__ void __launch_bounds__(256)
+sg_reduce_chunks_strided_kernel(const float* __restrict__ partial, long long M, long long N, int chunks, float* __restrict__ out, long long ld) {
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (e >= M * N) return;
+  float a = partial[e];
+  for (int z = 1; z < chunks; ++z) a += partial[(long long)z * M * N + e];
+  out[(e / N) * ld + (e % N)] = a;
+}
+
+static int gt_image(const GemmOperand& op, long long rows, long long K, int kb, long long n_tiles128, CxStats* st_, unsigned char* img,
+                    cudaStream_t st) {
+  // max |element|: the operand's memory is [rows, K] (ld) or, transposed, [K, rows] (ld)
+  if (op.transposed) cx_amax_kernel<<<cx_amax_grid(K), 256, 0, st>>>(op.ptr, K, (int)rows, op.ld, st_);
+  else cx_amax_kernel<<<cx_amax_grid(rows), 256, 0, st>>>(op.ptr, rows, (int)K, op.ld, st_);
+  TFRS_LAUNCH_CHECK();
+  cx_exp_kernel<<<1, 1, 0, st>>>(st_);
+  TFRS_LAUNCH_CHECK();
+  if (op.transposed) {   // tiled shared-memory transpose: coalesced on both sides
+    cx_split_image_t_kernel<<<dim3((unsigned)kb, (unsigned)n_tiles128), 256, 0, st>>>(op.ptr, K, (int)rows, op.ld, kb, st_, img);
+  } else {
+    const long long chunks = n_tiles128 * 128 * (long long)kb * 8;
+    const unsigned g = (unsigned)(ceil_div(chunks, 256) < (1 << 20) ? ceil_div(chunks, 256) : (1 << 20));
+    cx_split_image_kernel<false><<<g, 256, 0, st>>>(op.ptr, rows, (int)K, op.ld, kb, n_tiles128, st_, img);
+  }
+  TFRS_LAUNCH_CHECK();
+  return TFRS_OK;
+}
+
+int gemm_tc(const GemmOperand& A, const GemmOperand& Bop, long long M, long long N, long long K, const GemmEpilogue& ep,
+            float* out, long long ld_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  GtPlan pl; gt_plan(M, N, K, pl);
+  if (!ws || ws_bytes < pl.total) { set_error("gemm_tc: workspace too small"); return TFRS_ERR_WORKSPACE_TOO_SMALL; }
+  TFRS_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "gemm_tc: workspace must be 16-byte aligned");
+  TFRS_CHECK_ARG(N < (1ll << 31) && M < (1ll << 31), "gemm_tc: M / N too large");
+  if (ep.mode != GEMM_EPI_PLAIN && pl.n_kc > 1) { set_error("gemm_tc: fused epilogues need K <= %d", DW_CHUNK_SLABS * 64); return TFRS_ERR_UNSUPPORTED; }
+  unsigned char* w8 = (unsigned char*)ws;
+  CxStats* ast = (CxStats*)(w8 + pl.o_st); CxStats* bst = (CxStats*)(w8 + pl.o_st + 1024);
+  TFRS_CUDA(cudaMemsetAsync(w8 + pl.o_st, 0, 2048, st));
+  int rc = gt_image(A, M, K, pl.kb, (long long)pl.n_mb * 2, ast, w8 + pl.o_aimg, st);
+  if (rc) return rc;
+  rc = gt_image(Bop, N, K, pl.kb, pl.n_nt, bst, w8 + pl.o_bimg, st);
+  if (rc) return rc;
+  SgParams p{};
+  p.aimg = w8 + pl.o_aimg; p.bimg = w8 + pl.o_bimg; p.ast = ast; p.bst = bst;
+  p.kb_total = pl.kb; p.n_mb = pl.n_mb; p.n_nt = pl.n_nt; p.M = M; p.N = N;
+  p.e0 = ep.e0; p.ld0 = ep.ld0; p.e1 = ep.e1; p.ld1 = ep.ld1; p.bias = ep.bias; p.diag = ep.diag; p.prod = ep.prod;
+  if (pl.n_kc > 1) {   // long reduction (the batch): chunked accumulation chains, fixed-order sum of the partials
+    p.kb_chunk = DW_CHUNK_SLABS; p.n_kc = pl.n_kc; p.out = (float*)(w8 + pl.o_partial); p.ld_out = N;
+    rc = sg_launch(SG_DW, p, st);
+    if (rc) return rc;
+    sg_reduce_chunks_strided_kernel<<<(unsigned)ceil_div(M * N, 256), 256, 0, st>>>(p.out, M, N, pl.n_kc, out, ld_out);
+    TFRS_LAUNCH_CHECK();
+    return TFRS_OK;
+  }
+  p.kb_chunk = pl.kb; p.n_kc = 1; p.out = out; p.ld_out = ld_out;
+  return sg_launch(ep.mode == GEMM_EPI_PLAIN ? SG_PLAIN : (ep.mode == GEMM_EPI_CROSS ? SG_CROSS : SG_DX), p, st);
 }
 
 // dx (if non-NULL) and dW (if non-NULL) from gp [B,D] (dense, ld = D), x / dout / dx with row stride ld.

@@ -69,9 +69,21 @@ gather_kernel(GatherParams p, long long n, float* __restrict__ out, long long ou
 // Variant "warp-chunk": a warp owns 32 consecutive batch rows of one table.  Lane l loads ids[i0+l] ONCE (one coalesced
 // 128-byte read per 32 rows instead of a redundant id read per 16-byte lane), row ids travel by shuffle, and the
 // warp then issues up to 8 independent 16-byte row reads per thread before the first store.
+//
+// Hot rows (skewed id distributions): a CTA covers GT_CTA_ROWS batch rows of one table.  Vocabularies are normally
+// frequency-sorted, so the hot rows are the FIRST rows of the table: when more of the CTA's ids fall into the first H rows
+// (H = GT_HOT_BYTES / row bytes) than the H rows it costs to fetch them, thread 0 stages that contiguous block in shared
+// memory with one bulk-TMA copy (cp.async.bulk + mbarrier) and every hit is served from there -- duplicates of a hot row
+// inside the chunk cost one L2 read instead of one each.  Uniform ids never trigger it (one block-wide count, no copy).
+constexpr int GT_HOT_BYTES = 16384;
+constexpr int GT_CTA_CHUNKS = 2;                          // 32-row chunks per warp
+constexpr int GT_CTA_ROWS = (GT_THREADS / 32) * 32 * GT_CTA_CHUNKS;
+
 template <typename IdT>
 __global__ void __launch_bounds__(GT_THREADS)
 gather_warpchunk_kernel(GatherParams p, long long n, float* __restrict__ out, long long out_ld) {
+  __shared__ __align__(128) float4 hot[GT_HOT_BYTES / 16];
+  __shared__ __align__(8) uint64_t hot_bar;
   const int t = blockIdx.y;
   const float4* __restrict__ table = reinterpret_cast<const float4*>(p.table[t]);
   const IdT* __restrict__ ids = reinterpret_cast<const IdT*>(p.ids[t]);
@@ -79,30 +91,68 @@ gather_warpchunk_kernel(GatherParams p, long long n, float* __restrict__ out, lo
   const int L = p.dim[t] >> 2;             // 16-byte lanes per row: power of two, <= 32 (checked by the host)
   const int lshift = 31 - __clz(L);
   const int R = 32 >> lshift;              // rows covered by one warp-wide load
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane & (L - 1), rsel = lane >> lshift;
-  const long long i0 = ((long long)blockIdx.x * (GT_THREADS / 32) + (threadIdx.x >> 5)) * 32;
-  if (i0 >= n) return;
-  long long rid = -1;
-  if (i0 + lane < n) { const long long r = (long long)ids[i0 + lane]; rid = (r >= 0 && r < rows) ? r : -1; }
-  const bool lane_valid = i0 + lane < n;
+  const long long H = min((long long)(GT_HOT_BYTES / 16) >> lshift, rows);   // rows of the table that fit the staging buffer
   float4* __restrict__ o4 = reinterpret_cast<float4*>(out + p.col_off[t]);
   const long long ld4 = out_ld >> 2;
-  const int steps = 32 / R;                // warp-wide loads to cover the 32 rows
-  for (int s0 = 0; s0 < steps; s0 += 8) {
-    float4 v[8]; bool ok[8];
+  const int steps = 32 / R;                // warp-wide loads to cover 32 rows
+
+  long long rid[GT_CTA_CHUNKS];
+  int n_hot = 0;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = (s0 + u) * R + rsel;   // row of the chunk this lane serves in step s0+u
-      const long long r = __shfl_sync(0xffffffffu, rid, j & 31);
-      const bool in = __shfl_sync(0xffffffffu, (int)lane_valid, j & 31) != 0;
-      ok[u] = (s0 + u) < steps && in;
-      v[u] = (ok[u] && r >= 0) ? __ldg(table + r * L + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int ch = 0; ch < GT_CTA_CHUNKS; ++ch) {
+    const long long i = (long long)blockIdx.x * GT_CTA_ROWS + (ch * (GT_THREADS / 32) + warp) * 32 + lane;
+    rid[ch] = -1;
+    if (i < n) { const long long r = (long long)ids[i]; rid[ch] = (r >= 0 && r < rows) ? r : -1; }
+    n_hot += (rid[ch] >= 0 && rid[ch] < H) ? 1 : 0;
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&hot_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  n_hot = __syncthreads_count(n_hot) + 0;   // >= 1 hot id per counted thread; two chunks per thread are folded below
+  // __syncthreads_count counts THREADS with a non-zero predicate: good enough for the decision (a lower bound of the hits)
+  const bool staged = (long long)n_hot > H / 2 && H > 0;
+  if (staged) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&hot_bar);
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)(H << lshift) * 16u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((uint32_t)__cvta_generic_to_shared(hot)), "l"(table), "r"(bytes), "r"(bar) : "memory");
     }
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GT_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra GT_DONE;\n"
+        "bra GT_WAIT;\n"
+        "GT_DONE:\n"
+        "}\n" ::"r"(bar) : "memory");
+  }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = (s0 + u) * R + rsel;
-      if (ok[u]) o4[(i0 + j) * ld4 + sub] = v[u];
+  for (int ch = 0; ch < GT_CTA_CHUNKS; ++ch) {
+    const long long i0 = (long long)blockIdx.x * GT_CTA_ROWS + (ch * (GT_THREADS / 32) + warp) * 32;
+    if (i0 >= n) continue;                 // warp-uniform
+    const bool lane_valid = i0 + lane < n;
+    for (int s0 = 0; s0 < steps; s0 += 8) {
+      float4 v[8]; bool ok[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = (s0 + u) * R + rsel;   // row of the chunk this lane serves in step s0+u
+        const long long r = __shfl_sync(0xffffffffu, rid[ch], j & 31);
+        const bool in = __shfl_sync(0xffffffffu, (int)lane_valid, j & 31) != 0;
+        ok[u] = (s0 + u) < steps && in;
+        if (ok[u] && r >= 0) v[u] = (staged && r < H) ? hot[(r << lshift) + sub] : __ldg(table + r * L + sub);
+        else v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = (s0 + u) * R + rsel;
+        if (ok[u]) o4[(i0 + j) * ld4 + sub] = v[u];
+      }
     }
   }
 }
@@ -146,7 +196,7 @@ extern "C" int tfrs_gather_f32(const float* const* tables, const int64_t* rows, 
       chunkable = L >= 1 && L <= 32 && (L & (L - 1)) == 0;
     }
     if (chunkable) {
-      dim3 g2((unsigned)ceil_div(n, (long long)GT_THREADS), (unsigned)nt);  // 32 rows per warp, 8 warps per CTA
+      dim3 g2((unsigned)ceil_div(n, (long long)GT_CTA_ROWS), (unsigned)nt);  // GT_CTA_CHUNKS x 32 rows per warp, 8 warps per CTA
       if (ids_dtype == TFRS_I32) gather_warpchunk_kernel<int32_t><<<g2, GT_THREADS, 0, st>>>(p, n, out, out_ld);
       else gather_warpchunk_kernel<int64_t><<<g2, GT_THREADS, 0, st>>>(p, n, out, out_ld);
       TFRS_LAUNCH_CHECK();

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "tc_split.cuh"
+#include "softmax_ext.cuh"
 
 namespace tfrs {
 namespace tc {
@@ -32,13 +33,24 @@ struct SoftmaxTcParams {
   long long n_ctiles;
   float inv_t;
   float2* partial;            // [Bp, parts, 2] (max, sum-exp) in log2 units
-  float* pos;                 // [Bp] positive logit q_i.c_i/T (+ bias_i) (natural units)
-  const float* cbias2;        // BIAS: per-candidate logit bias in log2 units, padded to n_ctiles*128 (zeros beyond C)
+  float* pos;                 // [Bp] positive logit (q_i.c_i/T + bias_i, after the masks) in log2 units
+  const float* cbias2;        // MODE >= 1: per-candidate logit bias in log2 units, padded to n_ctiles*128 (zeros beyond C)
+  // MODE 2 (the remaining Retrieval options, each nullable):
+  const int* id_lo; const int* id_hi;   // candidate ids split into 32-bit halves, padded: remove_accidental_hits
+  const uint32_t* mbits; int mwords;    // score_mask as bits [Bp][mwords = n_ctiles*4] (1 = keep)
 };
 
-template <int KB, bool BIAS>
+// MIN_FLOAT (layers/loss.py:23: float32 min / 100) in log2 units: the value a masked logit takes
+constexpr float SX_MIN2 = -3.4028235e36f * SX_LOG2E;
+
+// MODE 0: plain; 1: + per-candidate bias (sampling-probability correction); 2: + accidental-hit removal (candidate ids,
+// tasks/retrieval.py:194-200, layers/loss.py:114-147: logits + dup * MIN_FLOAT == MIN_FLOAT in fp32) and score_mask
+// (retrieval.py:202-203: where(mask, s, MIN_FLOAT)) applied to the accumulators in registers.
+template <int KB, int MODE>
 __global__ void __launch_bounds__(SX_THREADS, 1)
 softmax_tc_kernel(const SoftmaxTcParams p) {
+  constexpr bool BIAS = MODE >= 1;
+  constexpr bool EXT = MODE == 2;
   extern __shared__ __align__(1024) unsigned char sx_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sx_raw) + 1023) & ~uintptr_t(1023));
   constexpr int SX_STAGES = sx_stages(KB);
@@ -124,6 +136,8 @@ softmax_tc_kernel(const SoftmaxTcParams p) {
     // logits in log2 units: s2 = acc * 2^-(eq+ec) * invT * log2(e)
     const float scale2 = ldexpf(p.inv_t * SX_LOG2E, -(p.qst->exp + p.cst->exp));
     float m2 = -INFINITY, l = 0.f, pos2 = 0.f;
+    int rid_lo = 0, rid_hi = 0;   // id of this row's positive candidate (candidate `row`); the arrays are padded past Bp
+    if (EXT && p.id_lo) { rid_lo = p.id_lo[row]; rid_hi = p.id_hi[row]; }
     for (int it = 0; it < n_iter; ++it) {
       const int buf = it & 1;
       const uint32_t tphase = (it >> 1) & 1;
@@ -150,6 +164,31 @@ softmax_tc_kernel(const SoftmaxTcParams p) {
           r[4 * j4 + 1] = __float_as_uint(fmaf(__uint_as_float(r[4 * j4 + 1]), scale2, bb.y));
           r[4 * j4 + 2] = __float_as_uint(fmaf(__uint_as_float(r[4 * j4 + 2]), scale2, bb.z));
           r[4 * j4 + 3] = __float_as_uint(fmaf(__uint_as_float(r[4 * j4 + 3]), scale2, bb.w));
+        }
+      }
+      if (EXT) {
+        if (p.id_lo) {   // accidental hits: another candidate with the id of this row's positive -> MIN_FLOAT
+          const int4* il = reinterpret_cast<const int4*>(p.id_lo + col0);
+#pragma unroll
+          for (int j4 = 0; j4 < 16; ++j4) {
+            const int4 v = __ldg(il + j4);
+            if ((v.x == rid_lo) | (v.y == rid_lo) | (v.z == rid_lo) | (v.w == rid_lo)) {   // rare
+              const int* ih = p.id_hi + col0 + 4 * j4;
+              const long long c = col0 + 4 * j4;
+              if (v.x == rid_lo && __ldg(ih + 0) == rid_hi && c + 0 != row) r[4 * j4 + 0] = __float_as_uint(SX_MIN2);
+              if (v.y == rid_lo && __ldg(ih + 1) == rid_hi && c + 1 != row) r[4 * j4 + 1] = __float_as_uint(SX_MIN2);
+              if (v.z == rid_lo && __ldg(ih + 2) == rid_hi && c + 2 != row) r[4 * j4 + 2] = __float_as_uint(SX_MIN2);
+              if (v.w == rid_lo && __ldg(ih + 3) == rid_hi && c + 3 != row) r[4 * j4 + 3] = __float_as_uint(SX_MIN2);
+            }
+          }
+        }
+        if (p.mbits) {   // score_mask: bit = keep
+          const uint2 mw = __ldg(reinterpret_cast<const uint2*>(p.mbits + row * p.mwords + (t_begin + it) * 4 + half * 2));
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (!((mw.x >> j) & 1u)) r[j] = __float_as_uint(SX_MIN2);
+            if (!((mw.y >> j) & 1u)) r[32 + j] = __float_as_uint(SX_MIN2);
+          }
         }
       }
       const float sc = BIAS ? 1.0f : scale2;
@@ -196,7 +235,7 @@ softmax_tc_kernel(const SoftmaxTcParams p) {
       p.partial[(row * p.parts + part) * 2 + half] = make_float2(m2, l);
       // exactly one (part, half) thread of the row saw the diagonal column
       const long long dt = row / 128;
-      if (dt >= t_begin && dt < t_end && ((row % 128) / 64) == half) p.pos[row] = pos2 * (1.0f / SX_LOG2E);
+      if (dt >= t_begin && dt < t_end && ((row % 128) / 64) == half) p.pos[row] = pos2;
     }
   }
   tc_fence_before();
@@ -204,7 +243,8 @@ softmax_tc_kernel(const SoftmaxTcParams p) {
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-// lse_i = ln2 * (M + log2(sum_p l_p 2^(m_p - M)));  rowloss_i = w_i (lse_i - pos_i)
+// lse_i = ln2 * (M + log2(sum_p l_p 2^(m_p - M)));  rowloss_i = w_i (lse_i - pos_i), formed as ln2 * ((M - pos2_i) + log2 L)
+// so that a row whose logits are ALL MIN_FLOAT (fully masked) still yields log(C), as the max-subtracted reference does
 __global__ void __launch_bounds__(256)
 smtc_combine_kernel(const float2* __restrict__ partial, int n_partials, const float* __restrict__ pos,
                     const float* __restrict__ w, long long B, float* __restrict__ lse, float* __restrict__ rowloss) {
@@ -215,9 +255,9 @@ smtc_combine_kernel(const float2* __restrict__ partial, int n_partials, const fl
   for (int i = 0; i < n_partials; ++i) M = fmaxf(M, pp[i].x);
   float L = 0.f;
   for (int i = 0; i < n_partials; ++i) L += pp[i].y * exp2f(pp[i].x - M);
-  const float l = (M + log2f(L)) * 0.6931471805599453f;
-  lse[row] = l;
-  rowloss[row] = (w ? w[row] : 1.0f) * (l - pos[row]);
+  const float lg = log2f(L);
+  lse[row] = (M + lg) * 0.6931471805599453f;
+  rowloss[row] = (w ? w[row] : 1.0f) * (((M - pos[row]) + lg) * 0.6931471805599453f);
 }
 
 __global__ void __launch_bounds__(1024) smtc_reduce_loss(const float* __restrict__ rowloss, long long B, float* __restrict__ loss) {
@@ -230,9 +270,9 @@ __global__ void __launch_bounds__(1024) smtc_reduce_loss(const float* __restrict
   if (threadIdx.x == 0) loss[0] = (float)red[0];
 }
 
-struct SxPlan { int kb, nqb, parts; long long Bp, n_ctiles; size_t smem, o_qst, o_cst, o_qimg, o_cimg, o_partial, o_pos, o_rowloss, o_bias, total; };
+struct SxPlan { int kb, nqb, parts; long long Bp, n_ctiles, idpad; size_t smem, o_qst, o_cst, o_qimg, o_cimg, o_partial, o_pos, o_rowloss, o_bias, o_idlo, o_idhi, o_mbits, total; };
 
-static bool sx_plan(long long B, long long C, int d, SxPlan& pl) {
+static bool sx_plan(long long B, long long C, int d, SxPlan& pl, bool has_ids = false, bool has_mask = false) {
   if (B <= 0 || C < B || d <= 0 || d > 128) return false;
   pl.kb = (int)ceil_div(d, 64);
   pl.nqb = (int)ceil_div(B, 256);
@@ -257,6 +297,10 @@ static bool sx_plan(long long B, long long C, int d, SxPlan& pl) {
   pl.o_pos = take((size_t)pl.Bp * 4);
   pl.o_rowloss = take((size_t)pl.Bp * 4);
   pl.o_bias = take((size_t)pl.n_ctiles * 128 * 4);
+  pl.idpad = pl.Bp > pl.n_ctiles * 128 ? pl.Bp : pl.n_ctiles * 128;
+  pl.o_idlo = take(has_ids ? (size_t)pl.idpad * 4 : 0);
+  pl.o_idhi = take(has_ids ? (size_t)pl.idpad * 4 : 0);
+  pl.o_mbits = take(has_mask ? (size_t)pl.Bp * pl.n_ctiles * 4 * 4 : 0);
   pl.total = o;
   return true;
 }
@@ -271,20 +315,27 @@ extern "C" size_t tfrs_inbatch_softmax_tc_workspace_bytes(int64_t B, int64_t C, 
   return sx_plan(B, C, d, pl) ? pl.total : 0;
 }
 
-// cbias2[i] = bias[i] * log2(e) for i < C, 0 on the padding
+// cbias2[i] = bias[i] * log2(e) for i < C, 0 on the padding (and everywhere when bias == NULL)
 __global__ void __launch_bounds__(256)
 smtc_bias_kernel(const float* __restrict__ bias, long long C, long long Cpad, float* __restrict__ cbias2) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (i < Cpad) cbias2[i] = i < C ? bias[i] * SX_LOG2E : 0.f;
+  if (i < Cpad) cbias2[i] = (bias && i < C) ? bias[i] * SX_LOG2E : 0.f;
 }
 
-extern "C" int tfrs_inbatch_softmax_tc_fwd(const float* q, const float* c, int64_t B, int64_t C, int d, float inv_temperature,
-                                           const float* sample_weight, const float* candidate_bias, float* loss, float* lse,
-                                           void* ws, size_t ws_bytes, void* stream) {
+extern "C" size_t tfrs_inbatch_softmax_tc_ex_workspace_bytes(int64_t B, int64_t C, int d, int has_ids, int has_mask) {
+  SxPlan pl;
+  return sx_plan(B, C, d, pl, has_ids != 0, has_mask != 0) ? pl.total : 0;
+}
+
+extern "C" int tfrs_inbatch_softmax_tc_fwd_ex(const float* q, const float* c, int64_t B, int64_t C, int d, float inv_temperature,
+                                              const float* sample_weight, const float* candidate_bias,
+                                              const int64_t* candidate_ids, const uint8_t* score_mask, float* loss, float* lse,
+                                              void* ws, size_t ws_bytes, void* stream) {
   TFRS_CHECK_ARG(q && c && loss && lse, "inbatch_softmax_tc_fwd: NULL pointer");
   SxPlan pl;
+  const bool ext = candidate_ids || score_mask;
   if (!(inv_temperature > 0.f)) { set_error("inbatch_softmax_tc_fwd: needs a positive temperature"); return TFRS_ERR_UNSUPPORTED; }
-  if (!sx_plan(B, C, d, pl)) { set_error("inbatch_softmax_tc_fwd: shape outside the tensor-core path (need B <= C, d <= 128)"); return TFRS_ERR_UNSUPPORTED; }
+  if (!sx_plan(B, C, d, pl, candidate_ids != nullptr, score_mask != nullptr)) { set_error("inbatch_softmax_tc_fwd: shape outside the tensor-core path (need B <= C, d <= 128)"); return TFRS_ERR_UNSUPPORTED; }
   if (!ws || ws_bytes < pl.total) { set_error("inbatch_softmax_tc_fwd: workspace too small"); return TFRS_ERR_WORKSPACE_TOO_SMALL; }
   TFRS_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "inbatch_softmax_tc_fwd: workspace must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
@@ -314,21 +365,41 @@ extern "C" int tfrs_inbatch_softmax_tc_fwd(const float* q, const float* c, int64
   p.qimg = qimg; p.cimg = cimg; p.qst = qst; p.cst = cst; p.B = B; p.C = C; p.nqb = pl.nqb; p.parts = pl.parts; p.kb = pl.kb;
   p.n_ctiles = pl.n_ctiles; p.inv_t = inv_temperature; p.partial = partial; p.pos = pos;
   const int s1 = (int)((2 + sx_stages(1)) * 32768 + 1280), s2 = (int)((2 + sx_stages(2)) * 2 * 32768 + 1280);
-  TFRS_DYN_SMEM((softmax_tc_kernel<1, false>), s1);
-  TFRS_DYN_SMEM((softmax_tc_kernel<2, false>), s2);
-  TFRS_DYN_SMEM((softmax_tc_kernel<1, true>), s1);
-  TFRS_DYN_SMEM((softmax_tc_kernel<2, true>), s2);
+  TFRS_DYN_SMEM((softmax_tc_kernel<1, 0>), s1);
+  TFRS_DYN_SMEM((softmax_tc_kernel<2, 0>), s2);
+  TFRS_DYN_SMEM((softmax_tc_kernel<1, 1>), s1);
+  TFRS_DYN_SMEM((softmax_tc_kernel<2, 1>), s2);
+  TFRS_DYN_SMEM((softmax_tc_kernel<1, 2>), s1);
+  TFRS_DYN_SMEM((softmax_tc_kernel<2, 2>), s2);
   const unsigned grid = (unsigned)(pl.nqb * pl.parts);
-  if (candidate_bias) {
+  if (candidate_bias || ext) {
     float* cb2 = (float*)(w + pl.o_bias);
     smtc_bias_kernel<<<(unsigned)ceil_div(pl.n_ctiles * 128, 256), 256, 0, st>>>(candidate_bias, C, pl.n_ctiles * 128, cb2);
     TFRS_LAUNCH_CHECK();
     p.cbias2 = cb2;
-    if (pl.kb == 1) softmax_tc_kernel<1, true><<<grid, SX_THREADS, pl.smem, st>>>(p);
-    else softmax_tc_kernel<2, true><<<grid, SX_THREADS, pl.smem, st>>>(p);
+  }
+  if (candidate_ids) {
+    int* lo = (int*)(w + pl.o_idlo); int* hi = (int*)(w + pl.o_idhi);
+    sx_ids_split_kernel<<<(unsigned)ceil_div(pl.idpad, 256), 256, 0, st>>>((const long long*)candidate_ids, C, pl.idpad, lo, hi);
+    TFRS_LAUNCH_CHECK();
+    p.id_lo = lo; p.id_hi = hi;
+  }
+  if (score_mask) {
+    uint32_t* mb = (uint32_t*)(w + pl.o_mbits);
+    p.mwords = (int)(pl.n_ctiles * 4);
+    sx_mask_pack_kernel<<<(unsigned)ceil_div(pl.Bp * p.mwords, 256), 256, 0, st>>>(score_mask, B, C, pl.Bp, p.mwords, mb);
+    TFRS_LAUNCH_CHECK();
+    p.mbits = mb;
+  }
+  if (ext) {
+    if (pl.kb == 1) softmax_tc_kernel<1, 2><<<grid, SX_THREADS, pl.smem, st>>>(p);
+    else softmax_tc_kernel<2, 2><<<grid, SX_THREADS, pl.smem, st>>>(p);
+  } else if (candidate_bias) {
+    if (pl.kb == 1) softmax_tc_kernel<1, 1><<<grid, SX_THREADS, pl.smem, st>>>(p);
+    else softmax_tc_kernel<2, 1><<<grid, SX_THREADS, pl.smem, st>>>(p);
   } else {
-    if (pl.kb == 1) softmax_tc_kernel<1, false><<<grid, SX_THREADS, pl.smem, st>>>(p);
-    else softmax_tc_kernel<2, false><<<grid, SX_THREADS, pl.smem, st>>>(p);
+    if (pl.kb == 1) softmax_tc_kernel<1, 0><<<grid, SX_THREADS, pl.smem, st>>>(p);
+    else softmax_tc_kernel<2, 0><<<grid, SX_THREADS, pl.smem, st>>>(p);
   }
   TFRS_LAUNCH_CHECK();
   smtc_combine_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, st>>>(partial, pl.parts * 2, pos, sample_weight, B, lse, rowloss);
@@ -336,4 +407,11 @@ extern "C" int tfrs_inbatch_softmax_tc_fwd(const float* q, const float* c, int64
   smtc_reduce_loss<<<1, 1024, 0, st>>>(rowloss, B, loss);
   TFRS_LAUNCH_CHECK();
   return TFRS_OK;
+}
+
+extern "C" int tfrs_inbatch_softmax_tc_fwd(const float* q, const float* c, int64_t B, int64_t C, int d, float inv_temperature,
+                                           const float* sample_weight, const float* candidate_bias, float* loss, float* lse,
+                                           void* ws, size_t ws_bytes, void* stream) {
+  return tfrs_inbatch_softmax_tc_fwd_ex(q, c, B, C, d, inv_temperature, sample_weight, candidate_bias, nullptr, nullptr, loss, lse,
+                                        ws, ws_bytes, stream);
 }

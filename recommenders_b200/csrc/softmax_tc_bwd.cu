@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "tc_split.cuh"
+#include "softmax_ext.cuh"
 
 namespace tfrs {
 namespace tc {
@@ -40,6 +41,9 @@ struct SoftmaxBwdParams {
   int n_xb, parts, d;
   float inv_t;
   float* out;
+  // EXT (accidental-hit removal / score_mask, see softmax_tc.cu): masked entries get G = 0
+  const int* id_lo; const int* id_hi;   // candidate ids (32-bit halves, padded); query j's positive is candidate j
+  const uint32_t* mbits; int mwords;    // keep-bits [stationary row][streamed column]: the (B,C) matrix for dq, its transpose for dc
 };
 
 // One thread's 64 accumulator columns -> A, split into fp16 hi (written in place over r[0..31]: output slot 2*j4+e
@@ -49,10 +53,12 @@ struct SoftmaxBwdParams {
 // EDGE = the tile holds the diagonal or columns beyond the valid range (rare): masks compiled in only there.
 // BIAS: logits carry a per-candidate bias b_c: the exponent is s/T + b_c - lse_q.  Non-transposed: candidates are the
 // columns (cb4 = this thread's 64 biases, read through L2); transposed: the candidate is the row (bias_r).
-template <bool TRANSPOSED, bool EDGE, bool BIAS>
+// EXT: kill0 / kill1 = bit j set -> entry j (columns 0..31 / 32..63) is masked: A = 0 (where() blocks the gradient of a
+// masked score, and exp(MIN_FLOAT - lse) = 0 for an accidental hit).
+template <bool TRANSPOSED, bool EDGE, bool BIAS, bool EXT>
 __device__ __forceinline__ void sb_transform(uint32_t (&r)[64], uint32_t (&lo)[32], float scale, float lse_r,
                                              const float4* __restrict__ aux4, int n_valid, int jd,
-                                             const float4* __restrict__ cb4, float bias_r) {
+                                             const float4* __restrict__ cb4, float bias_r, uint32_t kill0, uint32_t kill1) {
 #pragma unroll
   for (int j4 = 0; j4 < 16; ++j4) {
     float lq[4] = {lse_r, lse_r, lse_r, lse_r}, wq[4] = {16384.f, 16384.f, 16384.f, 16384.f};
@@ -77,6 +83,7 @@ __device__ __forceinline__ void sb_transform(uint32_t (&r)[64], uint32_t (&lo)[3
         if (EDGE && j == jd) pr -= 16384.f;
       }
       a[e] = (!EDGE || j < n_valid) ? pr : 0.f;
+      if (EXT && (((j < 32 ? kill0 : kill1) >> (j & 31)) & 1u)) a[e] = 0.f;
     }
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
@@ -89,9 +96,11 @@ __device__ __forceinline__ void sb_transform(uint32_t (&r)[64], uint32_t (&lo)[3
   }
 }
 
-template <bool TRANSPOSED, bool BIAS>
+template <bool TRANSPOSED, int MODE>
 __global__ void __launch_bounds__(SB_THREADS, 1)
 softmax_tc_bwd_kernel(const SoftmaxBwdParams p) {
+  constexpr bool BIAS = MODE >= 1;
+  constexpr bool EXT = MODE == 2;
   extern __shared__ __align__(1024) unsigned char sb_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sb_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* sX = smem;                       // 32 KB
@@ -214,9 +223,13 @@ softmax_tc_bwd_kernel(const SoftmaxBwdParams p) {
     // (everything that chunk needs was issued before the MMA thread can block on dx_drained: no circular wait).
     const int c0 = grp * 32 + half * 16;
     const uint32_t dx_addr = tmem_dx + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
-    float dacc[16];
+    // running fp32 sum of the drained chunks: 16 values per thread, kept in SHARED memory ([i][epilogue thread]: conflict-free)
+    // -- in registers they pushed the transform loop (64 accumulators + 32 lo words live) past the 96-register budget
+    float* dacc = reinterpret_cast<float*>(smem + 32768 + SB_STAGES * SB_STAGE_BYTES + 1024) + (ew * 32 + lane);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) dacc[i] = 0.f;
+    for (int i = 0; i < 16; ++i) dacc[i * 512] = 0.f;
+    int rid_lo = 0, rid_hi = 0;   // id of the stationary row: the positive's id of query `row` (dq) / of candidate `row` (dc)
+    if (EXT && p.id_lo) { rid_lo = p.id_lo[row]; rid_hi = p.id_hi[row]; }
     const int n_chunks = (n_iter + SB_DRAIN - 1) / SB_DRAIN;
     int next_chunk = 0;
     auto drain_until = [&](int t_next) {  // drain every chunk whose last tile is <= t_next - 3
@@ -227,7 +240,7 @@ softmax_tc_bwd_kernel(const SoftmaxBwdParams p) {
         tmem_ld16(dx_addr, acc);
         tmem_ld_wait16(acc);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) dacc[i] += __uint_as_float(acc[i]);
+        for (int i = 0; i < 16; ++i) dacc[i * 512] += __uint_as_float(acc[i]);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dx_drained);
@@ -251,11 +264,35 @@ softmax_tc_bwd_kernel(const SoftmaxBwdParams p) {
       const bool edge = n_valid < 64 || ((long long)xb * 128 < col0 + 64 && col0 < (long long)xb * 128 + 128);
       uint32_t lo[32];
       const float4* cb4 = (BIAS && !TRANSPOSED) ? reinterpret_cast<const float4*>(p.cbias_pad + col0) : nullptr;
+      uint32_t kill0 = 0, kill1 = 0;
+      if (EXT) {
+        if (p.mbits) {
+          const uint2 mw = __ldg(reinterpret_cast<const uint2*>(p.mbits + row * p.mwords + (t_begin + it) * 4 + half * 2));
+          kill0 = ~mw.x; kill1 = ~mw.y;
+        }
+        if (p.id_lo) {
+          const int4* il = reinterpret_cast<const int4*>(p.id_lo + col0);
+#pragma unroll
+          for (int j4 = 0; j4 < 16; ++j4) {
+            const int4 v = __ldg(il + j4);
+            if ((v.x == rid_lo) | (v.y == rid_lo) | (v.z == rid_lo) | (v.w == rid_lo)) {   // rare
+              const int* ih = p.id_hi + col0 + 4 * j4;
+              const long long c = col0 + 4 * j4;
+              uint32_t hit = 0;
+              if (v.x == rid_lo && __ldg(ih + 0) == rid_hi && c + 0 != row) hit |= 1u;
+              if (v.y == rid_lo && __ldg(ih + 1) == rid_hi && c + 1 != row) hit |= 2u;
+              if (v.z == rid_lo && __ldg(ih + 2) == rid_hi && c + 2 != row) hit |= 4u;
+              if (v.w == rid_lo && __ldg(ih + 3) == rid_hi && c + 3 != row) hit |= 8u;
+              if (j4 < 8) kill0 |= hit << (4 * j4); else kill1 |= hit << (4 * (j4 - 8));
+            }
+          }
+        }
+      }
       if (edge) {
         const int jd = (row >= col0 && row < col0 + 64) ? (int)(row - col0) : -1;
-        sb_transform<TRANSPOSED, true, BIAS>(r, lo, scale, lse_r, aux4, n_valid, jd, cb4, bias_r);
+        sb_transform<TRANSPOSED, true, BIAS, EXT>(r, lo, scale, lse_r, aux4, n_valid, jd, cb4, bias_r, kill0, kill1);
       } else {
-        sb_transform<TRANSPOSED, false, BIAS>(r, lo, scale, lse_r, aux4, 64, -1, cb4, bias_r);
+        sb_transform<TRANSPOSED, false, BIAS, EXT>(r, lo, scale, lse_r, aux4, 64, -1, cb4, bias_r, kill0, kill1);
       }
       tmem_st32(taddr, r);        // hi: columns [0, 32) of this 64-column half
       tmem_st32(taddr + 32, lo);  // lo: columns [32, 64)
@@ -273,7 +310,7 @@ softmax_tc_bwd_kernel(const SoftmaxBwdParams p) {
       float* dst = p.out + (long long)part * p.part_stride + row * p.d;
 #pragma unroll
       for (int i = 0; i < 16; ++i)
-        if (c0 + i < p.d) dst[c0 + i] = dacc[i] * fs;
+        if (c0 + i < p.d) dst[c0 + i] = dacc[i * 512] * fs;
     }
   }
   tc_fence_before();
@@ -331,9 +368,9 @@ static int sb_parts(long long n_xb, long long n_ytiles) {
 
 struct SbPlan {
   long long q_tiles, c_tiles; int parts_q, parts_c;
-  size_t o_qst, o_cst, o_wst, o_qimg, o_cimg, o_lse, o_w, o_bias, o_partial, total;
+  size_t o_qst, o_cst, o_wst, o_qimg, o_cimg, o_lse, o_w, o_bias, o_partial, o_idlo, o_idhi, o_mbits, o_mbits_t, total;
 };
-static bool sb_plan(long long B, long long C, int d, SbPlan& pl) {
+static bool sb_plan(long long B, long long C, int d, SbPlan& pl, bool has_ids = false, bool has_mask = false) {
   if (B <= 0 || C < B || d <= 0 || d > 64) return false;
   pl.q_tiles = ceil_div(B, 128); pl.c_tiles = ceil_div(C, 128);
   pl.parts_q = sb_parts(pl.q_tiles, pl.c_tiles);   // dq: X = q blocks, Y = c tiles
@@ -348,6 +385,10 @@ static bool sb_plan(long long B, long long C, int d, SbPlan& pl) {
   pl.o_bias = take((size_t)pl.c_tiles * 128 * 4);
   size_t pq = pl.parts_q > 1 ? (size_t)pl.parts_q * B * d * 4 : 0, pc = pl.parts_c > 1 ? (size_t)pl.parts_c * C * d * 4 : 0;
   pl.o_partial = take(pq > pc ? pq : pc);
+  pl.o_idlo = take(has_ids ? (size_t)pl.c_tiles * 128 * 4 : 0);
+  pl.o_idhi = take(has_ids ? (size_t)pl.c_tiles * 128 * 4 : 0);
+  pl.o_mbits = take(has_mask ? (size_t)pl.q_tiles * 128 * pl.c_tiles * 4 * 4 : 0);     // [q rows][c words]
+  pl.o_mbits_t = take(has_mask ? (size_t)pl.c_tiles * 128 * pl.q_tiles * 4 * 4 : 0);   // [c rows][q words]
   pl.total = o;
   return true;
 }
@@ -368,12 +409,19 @@ __global__ void __launch_bounds__(256) sb_pad_kernel(const float* __restrict__ s
   if (i < npad) pad[i] = i < n ? src[i] : 0.f;
 }
 
-extern "C" int tfrs_inbatch_softmax_tc_bwd(const float* q, const float* c, int64_t B, int64_t C, int d, float inv_temperature,
-                                           const float* sample_weight, const float* candidate_bias, const float* lse,
-                                           const float* grad_loss, float* dq, float* dc, void* ws, size_t ws_bytes, void* stream) {
+extern "C" size_t tfrs_inbatch_softmax_tc_bwd_ex_workspace_bytes(int64_t B, int64_t C, int d, int has_ids, int has_mask) {
+  SbPlan pl;
+  return sb_plan(B, C, d, pl, has_ids != 0, has_mask != 0) ? pl.total : 0;
+}
+
+extern "C" int tfrs_inbatch_softmax_tc_bwd_ex(const float* q, const float* c, int64_t B, int64_t C, int d, float inv_temperature,
+                                              const float* sample_weight, const float* candidate_bias,
+                                              const int64_t* candidate_ids, const uint8_t* score_mask, const float* lse,
+                                              const float* grad_loss, float* dq, float* dc, void* ws, size_t ws_bytes, void* stream) {
   TFRS_CHECK_ARG(q && c && lse && dq && dc, "inbatch_softmax_tc_bwd: NULL pointer");
   SbPlan pl;
-  if (!sb_plan(B, C, d, pl)) { set_error("inbatch_softmax_tc_bwd: shape outside the tensor-core path (need B <= C, d <= 64)"); return TFRS_ERR_UNSUPPORTED; }
+  const bool ext = candidate_ids || score_mask;
+  if (!sb_plan(B, C, d, pl, candidate_ids != nullptr, score_mask != nullptr)) { set_error("inbatch_softmax_tc_bwd: shape outside the tensor-core path (need B <= C, d <= 64)"); return TFRS_ERR_UNSUPPORTED; }
   if (!ws || ws_bytes < pl.total) { set_error("inbatch_softmax_tc_bwd: workspace too small"); return TFRS_ERR_WORKSPACE_TOO_SMALL; }
   TFRS_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "inbatch_softmax_tc_bwd: workspace must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
@@ -398,24 +446,47 @@ extern "C" int tfrs_inbatch_softmax_tc_bwd(const float* q, const float* c, int64
   TFRS_LAUNCH_CHECK();
   sb_prep_kernel<<<(unsigned)ceil_div(pl.q_tiles * 128, 256), 256, 0, st>>>(lse, sample_weight, B, pl.q_tiles * 128, wst, lse_pad, w_pad);
   TFRS_LAUNCH_CHECK();
-  const size_t smem = 32768 + (size_t)SB_STAGES * SB_STAGE_BYTES + 1024 + 256;
-  TFRS_DYN_SMEM((softmax_tc_bwd_kernel<false, false>), (int)smem);
-  TFRS_DYN_SMEM((softmax_tc_bwd_kernel<true, false>), (int)smem);
-  TFRS_DYN_SMEM((softmax_tc_bwd_kernel<false, true>), (int)smem);
-  TFRS_DYN_SMEM((softmax_tc_bwd_kernel<true, true>), (int)smem);
+  const size_t smem = 32768 + (size_t)SB_STAGES * SB_STAGE_BYTES + 1024 + 32768 + 256;  // X | Y ring | barriers | dX sums | align slack
+  TFRS_DYN_SMEM((softmax_tc_bwd_kernel<false, 0>), (int)smem);
+  TFRS_DYN_SMEM((softmax_tc_bwd_kernel<true, 0>), (int)smem);
+  TFRS_DYN_SMEM((softmax_tc_bwd_kernel<false, 1>), (int)smem);
+  TFRS_DYN_SMEM((softmax_tc_bwd_kernel<true, 1>), (int)smem);
+  TFRS_DYN_SMEM((softmax_tc_bwd_kernel<false, 2>), (int)smem);
+  TFRS_DYN_SMEM((softmax_tc_bwd_kernel<true, 2>), (int)smem);
   SoftmaxBwdParams p{};
   p.xst = qst; p.yst = cst; p.wst = wst; p.lse_pad = lse_pad; p.w_pad = w_pad; p.grad_loss = grad_loss; p.d = d; p.inv_t = inv_temperature;
+  const int mode = ext ? 2 : (candidate_bias ? 1 : 0);
+  if (mode) {   // EXT without a bias runs on a zero bias vector
+    float* cbp = (float*)(w8 + pl.o_bias);
+    if (candidate_bias) sb_pad_kernel<<<(unsigned)ceil_div(pl.c_tiles * 128, 256), 256, 0, st>>>(candidate_bias, C, pl.c_tiles * 128, cbp);
+    else TFRS_CUDA(cudaMemsetAsync(cbp, 0, (size_t)pl.c_tiles * 128 * 4, st));
+    TFRS_LAUNCH_CHECK();
+    p.cbias_pad = cbp;
+  }
+  uint32_t* mbits = nullptr; uint32_t* mbits_t = nullptr;
+  if (candidate_ids) {
+    int* lo = (int*)(w8 + pl.o_idlo); int* hi = (int*)(w8 + pl.o_idhi);
+    sx_ids_split_kernel<<<(unsigned)ceil_div(pl.c_tiles * 128, 256), 256, 0, st>>>((const long long*)candidate_ids, C, pl.c_tiles * 128, lo, hi);
+    TFRS_LAUNCH_CHECK();
+    p.id_lo = lo; p.id_hi = hi;
+  }
+  if (score_mask) {
+    mbits = (uint32_t*)(w8 + pl.o_mbits); mbits_t = (uint32_t*)(w8 + pl.o_mbits_t);
+    const int wc = (int)(pl.c_tiles * 4), wq = (int)(pl.q_tiles * 4);
+    sx_mask_pack_kernel<<<(unsigned)ceil_div(pl.q_tiles * 128 * wc, 256), 256, 0, st>>>(score_mask, B, C, pl.q_tiles * 128, wc, mbits);
+    TFRS_LAUNCH_CHECK();
+    sx_mask_pack_t_kernel<<<dim3((unsigned)ceil_div(pl.c_tiles * 128, 256), (unsigned)wq), 256, 0, st>>>(score_mask, B, C, pl.c_tiles * 128, wq, mbits_t);
+    TFRS_LAUNCH_CHECK();
+  }
   // ---- dq: X = q, Y = c
   p.ximg = qimg; p.yimg = cimg; p.n_x_rows = B; p.n_y_valid = C; p.n_ytiles = pl.c_tiles; p.n_xb = (int)pl.q_tiles; p.parts = pl.parts_q;
   p.part_stride = B * (long long)d; p.out = pl.parts_q > 1 ? partial : dq;
-  if (candidate_bias) {
-    float* cbp = (float*)(w8 + pl.o_bias);
-    sb_pad_kernel<<<(unsigned)ceil_div(pl.c_tiles * 128, 256), 256, 0, st>>>(candidate_bias, C, pl.c_tiles * 128, cbp);
-    TFRS_LAUNCH_CHECK();
-    p.cbias_pad = cbp;
-    softmax_tc_bwd_kernel<false, true><<<(unsigned)(pl.q_tiles * pl.parts_q), SB_THREADS, smem, st>>>(p);
-  } else {
-    softmax_tc_bwd_kernel<false, false><<<(unsigned)(pl.q_tiles * pl.parts_q), SB_THREADS, smem, st>>>(p);
+  p.mbits = mbits; p.mwords = (int)(pl.c_tiles * 4);
+  {
+    const unsigned g = (unsigned)(pl.q_tiles * pl.parts_q);
+    if (mode == 2) softmax_tc_bwd_kernel<false, 2><<<g, SB_THREADS, smem, st>>>(p);
+    else if (mode == 1) softmax_tc_bwd_kernel<false, 1><<<g, SB_THREADS, smem, st>>>(p);
+    else softmax_tc_bwd_kernel<false, 0><<<g, SB_THREADS, smem, st>>>(p);
   }
   TFRS_LAUNCH_CHECK();
   if (pl.parts_q > 1) {
@@ -425,12 +496,24 @@ extern "C" int tfrs_inbatch_softmax_tc_bwd(const float* q, const float* c, int64
   // ---- dc: X = c, Y = q (only the B query rows exist; candidates beyond B are pure negatives)
   p.ximg = cimg; p.yimg = qimg; p.xst = cst; p.yst = qst; p.n_x_rows = C; p.n_y_valid = B; p.n_ytiles = pl.q_tiles; p.n_xb = (int)pl.c_tiles;
   p.parts = pl.parts_c; p.part_stride = C * (long long)d; p.out = pl.parts_c > 1 ? partial : dc;
-  if (candidate_bias) softmax_tc_bwd_kernel<true, true><<<(unsigned)(pl.c_tiles * pl.parts_c), SB_THREADS, smem, st>>>(p);
-  else softmax_tc_bwd_kernel<true, false><<<(unsigned)(pl.c_tiles * pl.parts_c), SB_THREADS, smem, st>>>(p);
+  p.mbits = mbits_t; p.mwords = (int)(pl.q_tiles * 4);
+  {
+    const unsigned g = (unsigned)(pl.c_tiles * pl.parts_c);
+    if (mode == 2) softmax_tc_bwd_kernel<true, 2><<<g, SB_THREADS, smem, st>>>(p);
+    else if (mode == 1) softmax_tc_bwd_kernel<true, 1><<<g, SB_THREADS, smem, st>>>(p);
+    else softmax_tc_bwd_kernel<true, 0><<<g, SB_THREADS, smem, st>>>(p);
+  }
   TFRS_LAUNCH_CHECK();
   if (pl.parts_c > 1) {
     sb_reduce_parts_kernel<<<(unsigned)ceil_div(C * d, 256), 256, 0, st>>>(partial, C * (long long)d, pl.parts_c, dc);
     TFRS_LAUNCH_CHECK();
   }
   return TFRS_OK;
+}
+
+extern "C" int tfrs_inbatch_softmax_tc_bwd(const float* q, const float* c, int64_t B, int64_t C, int d, float inv_temperature,
+                                           const float* sample_weight, const float* candidate_bias, const float* lse,
+                                           const float* grad_loss, float* dq, float* dc, void* ws, size_t ws_bytes, void* stream) {
+  return tfrs_inbatch_softmax_tc_bwd_ex(q, c, B, C, d, inv_temperature, sample_weight, candidate_bias, nullptr, nullptr, lse, grad_loss,
+                                        dq, dc, ws, ws_bytes, stream);
 }

@@ -100,6 +100,11 @@ class Cross(torch.nn.Module):
     if self._projection_dim is None and self._preactivation is None:
       out = ops.cross(x0f, xf, self.kernel, self.bias, float(self._diag_scale or 0.0))
       return out.reshape(*lead, -1)
+    if (self._projection_dim is not None and self._preactivation is None and
+        ops.cross_lowrank_supported(xf.shape[0], xf.shape[1], self._projection_dim)):
+      # low-rank: two tensor-core GEMMs, the cross formula fused into the second one
+      out = ops.cross_lowrank(x0f, xf, self.kernel_u, self.kernel_v, self.bias, float(self._diag_scale or 0.0))
+      return out.reshape(*lead, -1)
     if self._projection_dim is None:
       prod = ops.matmul(xf, self.kernel)
     else:

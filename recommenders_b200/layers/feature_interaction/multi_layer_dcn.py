@@ -59,7 +59,11 @@ class MultiLayerDCN(torch.nn.Module):
     lead = x0.shape[:-1]
     x0f = x0.reshape(-1, x0.shape[-1]).to(torch.float32)
     xl = x0f
+    fused = ops.cross_lowrank_supported(x0f.shape[0], x0f.shape[1], self._projection_dim)
     for i in range(self._num_layers):
+      if fused:   # x0 * ((xl @ U) @ V + b) + xl: two tensor-core GEMMs per layer, formula in the second one's epilogue
+        xl = ops.cross_lowrank(x0f, xl, self.u_kernels[i], self.v_kernels[i], None if self.biases is None else self.biases[i], 0.0)
+        continue
       prod = ops.matmul(ops.matmul(xl, self.u_kernels[i]), self.v_kernels[i])   # (:146-147)
       if self.biases is not None:
         prod = prod + self.biases[i]

@@ -393,10 +393,25 @@ def inbatch_softmax_tc(q: torch.Tensor, c: torch.Tensor, sample_weight: Optional
   return loss.view(()), lse
 
 
+def _ids_i64(candidate_ids, C: int, device) -> torch.Tensor:
+  """candidate ids of any type -> int64 [C] on the device.  Integer tensors are used as they are; anything else (strings,
+  NumPy object arrays, float ids) is factorised on the host -- only EQUALITY of ids matters to accidental-hit removal."""
+  if isinstance(candidate_ids, torch.Tensor) and not candidate_ids.dtype.is_floating_point and candidate_ids.dtype != torch.bool:
+    t = candidate_ids.reshape(-1).to(device=device, dtype=torch.int64).contiguous()
+  else:
+    import numpy as np
+    arr = candidate_ids.detach().cpu().numpy() if isinstance(candidate_ids, torch.Tensor) else np.asarray(candidate_ids)
+    _, inv = np.unique(arr.reshape(-1), return_inverse=True)
+    t = torch.as_tensor(inv.astype(np.int64), device=device)
+  if t.numel() != C:
+    raise ValueError(f"candidate_ids must have one entry per candidate (got {t.numel()}, expected {C})")
+  return t
+
+
 class _InBatchSoftmax(torch.autograd.Function):
 
   @staticmethod
-  def forward(ctx, q, c, sample_weight, inv_temperature, candidate_bias=None):
+  def forward(ctx, q, c, sample_weight, inv_temperature, candidate_bias=None, candidate_ids=None, score_mask=None):
     q = f32c(q, "query_embeddings"); c = f32c(c, "candidate_embeddings")
     B, d = q.shape; C = c.shape[0]
     w = None if sample_weight is None else f32c(sample_weight, "sample_weight").view(-1)
@@ -405,50 +420,63 @@ class _InBatchSoftmax(torch.autograd.Function):
       raise ValueError(f"candidate_bias must have one entry per candidate (got {cb.numel()}, expected {C})")
     if w is not None and w.numel() != B:
       raise ValueError(f"sample_weight must have one entry per query (got {w.numel()}, expected {B})")
-    if cb is not None and not inbatch_softmax_bias_supported(B, C, d):
-      raise NotImplementedError("inbatch_softmax_loss: candidate_bias needs the tensor-core path "
+    ids = None if candidate_ids is None else _ids_i64(candidate_ids, C, q.device)
+    mask = None
+    if score_mask is not None:
+      mask = require_cuda(score_mask, "score_mask")
+      if tuple(mask.shape) != (B, C):
+        raise ValueError(f"score_mask must be [{B},{C}], got {tuple(mask.shape)}")
+      mask = (mask if mask.dtype == torch.bool else mask != 0).contiguous().view(torch.uint8)
+    ext = ids is not None or mask is not None
+    if (cb is not None or ext) and not inbatch_softmax_bias_supported(B, C, d):
+      raise NotImplementedError("inbatch_softmax_loss: candidate_bias / candidate_ids / score_mask need the tensor-core path "
                                 f"(B >= {SOFTMAX_TC_MIN_B}, d <= 64); got B={B}, d={d}")
     loss = torch.empty((1,), dtype=torch.float32, device=q.device)
     lse = torch.empty((B,), dtype=torch.float32, device=q.device)
-    tcb = lib().tfrs_inbatch_softmax_tc_workspace_bytes(B, C, d) if B >= SOFTMAX_TC_MIN_B else 0
+    tcb = lib().tfrs_inbatch_softmax_tc_ex_workspace_bytes(B, C, d, int(ids is not None), int(mask is not None)) \
+        if B >= SOFTMAX_TC_MIN_B else 0
     if tcb:  # tensor-core forward (hi/lo fp16 split, fp32 accumulate, online log-sum-exp epilogue)
       ws = workspace(tcb, q.device, "softmax_tc")
-      check(lib().tfrs_inbatch_softmax_tc_fwd(ptr(q), ptr(c), B, C, d, c_f(inv_temperature), ptr(w), ptr(cb), ptr(loss), ptr(lse),
-                                              ptr(ws), ws.numel(), stream()), "inbatch_softmax_tc_fwd")
+      check(lib().tfrs_inbatch_softmax_tc_fwd_ex(ptr(q), ptr(c), B, C, d, c_f(inv_temperature), ptr(w), ptr(cb), ptr(ids), ptr(mask),
+                                                 ptr(loss), ptr(lse), ptr(ws), ws.numel(), stream()), "inbatch_softmax_tc_fwd")
     else:
       wsb = lib().tfrs_inbatch_softmax_workspace_bytes(B, C, d)
       ws = workspace(wsb, q.device, "softmax")
       check(lib().tfrs_inbatch_softmax_fwd(ptr(q), ptr(c), B, C, d, c_f(inv_temperature), ptr(w), ptr(loss), ptr(lse),
                                            ptr(ws), ws.numel(), stream()), "inbatch_softmax_fwd")
-    ctx.save_for_backward(q, c, lse, w if w is not None else torch.empty(0, device=q.device),
-                          cb if cb is not None else torch.empty(0, device=q.device))
+    empty = torch.empty(0, device=q.device)
+    ctx.save_for_backward(q, c, lse, w if w is not None else empty, cb if cb is not None else empty,
+                          ids if ids is not None else empty, mask if mask is not None else empty)
     ctx.has_w = w is not None
     ctx.has_cb = cb is not None
+    ctx.has_ids = ids is not None
+    ctx.has_mask = mask is not None
     ctx.inv_t = inv_temperature
     ctx.used_tc = bool(tcb)
     return loss.view(())
 
   @staticmethod
   def backward(ctx, g):
-    q, c, lse, w, cb = ctx.saved_tensors
+    q, c, lse, w, cb, ids, mask = ctx.saved_tensors
     B, d = q.shape; C = c.shape[0]
     g = f32c(g, "grad").view(1)
     dq = torch.empty_like(q); dc = torch.empty_like(c)
-    tcb = lib().tfrs_inbatch_softmax_tc_bwd_workspace_bytes(B, C, d) if ctx.used_tc else 0
+    tcb = lib().tfrs_inbatch_softmax_tc_bwd_ex_workspace_bytes(B, C, d, int(ctx.has_ids), int(ctx.has_mask)) if ctx.used_tc else 0
     if tcb:  # tensor-core backward: same split products as the forward pass that produced `lse`
       ws = workspace(tcb, q.device, "softmax_tc_bwd")
-      check(lib().tfrs_inbatch_softmax_tc_bwd(ptr(q), ptr(c), B, C, d, c_f(ctx.inv_t), ptr(w) if ctx.has_w else None,
-                                              ptr(cb) if ctx.has_cb else None, ptr(lse), ptr(g), ptr(dq), ptr(dc), ptr(ws),
-                                              ws.numel(), stream()), "inbatch_softmax_tc_bwd")
-      return dq, dc, None, None, None
-    if ctx.has_cb:
-      raise NotImplementedError("inbatch_softmax_loss backward with candidate_bias needs the tensor-core path")
+      check(lib().tfrs_inbatch_softmax_tc_bwd_ex(ptr(q), ptr(c), B, C, d, c_f(ctx.inv_t), ptr(w) if ctx.has_w else None,
+                                                 ptr(cb) if ctx.has_cb else None, ptr(ids) if ctx.has_ids else None,
+                                                 ptr(mask) if ctx.has_mask else None, ptr(lse), ptr(g), ptr(dq), ptr(dc), ptr(ws),
+                                                 ws.numel(), stream()), "inbatch_softmax_tc_bwd")
+      return dq, dc, None, None, None, None, None
+    if ctx.has_cb or ctx.has_ids or ctx.has_mask:
+      raise NotImplementedError("inbatch_softmax_loss backward with loss options needs the tensor-core path")
     wsb = lib().tfrs_inbatch_softmax_workspace_bytes(B, C, d)
     ws = workspace(wsb, q.device, "softmax")
     check(lib().tfrs_inbatch_softmax_bwd(ptr(q), ptr(c), B, C, d, c_f(ctx.inv_t), ptr(w) if ctx.has_w else None,
                                          ptr(lse), ptr(g), ptr(dq), ptr(dc), ptr(ws), ws.numel(), stream()),
           "inbatch_softmax_bwd")
-    return dq, dc, None, None, None
+    return dq, dc, None, None, None, None, None
 
 
 def inbatch_softmax_bwd_exact(q, c, lse, sample_weight=None, inv_temperature: float = 1.0, grad_loss=None):
@@ -485,11 +513,67 @@ def inbatch_softmax_bias_supported(B: int, C: int, d: int) -> bool:
 
 
 def inbatch_softmax_loss(q: torch.Tensor, c: torch.Tensor, sample_weight: Optional[torch.Tensor] = None,
-                         temperature: Optional[float] = None, candidate_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
-  """sum_i w_i * (logsumexp_j(q_i.c_j / T + b_j) - q_i.c_i / T - b_i)  -- tasks/retrieval.py:178-210 default path;
-  b = candidate_bias (e.g. -log(clip(p, 1e-6, 1)): the sampling-probability correction, :190-192), no gradient."""
+                         temperature: Optional[float] = None, candidate_bias: Optional[torch.Tensor] = None,
+                         candidate_ids=None, score_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+  """sum_i w_i * (logsumexp_j(l_ij) - l_ii),  l_ij = q_i.c_j / T + b_j  -- tasks/retrieval.py:178-210;
+  b = candidate_bias (e.g. -log(clip(p, 1e-6, 1)): the sampling-probability correction, :190-192), no gradient;
+  candidate_ids: accidental-hit removal (:194-200) -- l_ij = MIN_FLOAT where id_j == id_i, j != i;
+  score_mask [B,C]: l_ij = MIN_FLOAT where the mask is False (:202-203)."""
   inv_t = 1.0 if temperature is None else 1.0 / float(temperature)
-  return _InBatchSoftmax.apply(q, c, sample_weight, inv_t, candidate_bias)
+  return _InBatchSoftmax.apply(q, c, sample_weight, inv_t, candidate_bias, candidate_ids, score_mask)
+
+
+# ------------------------------------------------------------------------------------------------
+# hard-negative mining loss (top-K scan + sparse softmax)
+# ------------------------------------------------------------------------------------------------
+def hard_negative_supported(B: int, C: int, d: int, num_hard_negatives: int) -> bool:
+  """True when Retrieval(num_hard_negatives=n) can run on the top-K scan instead of the [B,C] logits."""
+  return num_hard_negatives >= 1 and C >= B and min(num_hard_negatives + 1, C) <= 2048
+
+
+class _HardNegativeSoftmax(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, q, c, num_hard_negatives, sample_weight, inv_temperature):
+    q = f32c(q, "query_embeddings"); c = f32c(c, "candidate_embeddings")
+    B, d = q.shape; C = c.shape[0]
+    if not inv_temperature > 0:
+      raise NotImplementedError("hard_negative_softmax_loss needs a positive temperature")
+    k1 = min(int(num_hard_negatives) + 1, C)
+    w = None if sample_weight is None else f32c(sample_weight, "sample_weight").view(-1)
+    if w is not None and w.numel() != B:
+      raise ValueError(f"sample_weight must have one entry per query (got {w.numel()}, expected {B})")
+    qd, cd = q.detach(), c.detach()
+    if C >= TC_MIN_N and d <= 128 and tc_supported(B, C, d, k1):
+      top_s, top_i = topk_tc(qd, cd, index_build(cd, reuse_slot="hardneg_index"), k1)
+    else:
+      top_s, top_i = topk_scan(qd, cd, k1)
+    pos = rowwise_dot(qd, cd[:B])
+    loss = torch.empty((1,), dtype=torch.float32, device=q.device)
+    coef = torch.empty((B, k1 + 2), dtype=torch.float32, device=q.device)
+    check(lib().tfrs_hardneg_loss_fwd(ptr(top_s), ptr(top_i), B, k1, ptr(pos), c_f(inv_temperature), ptr(w), ptr(loss), ptr(coef),
+                                      stream()), "hardneg_loss_fwd")
+    ctx.save_for_backward(q, c, top_i, coef)
+    ctx.k1 = k1
+    return loss.view(())
+
+  @staticmethod
+  def backward(ctx, g):
+    q, c, top_i, coef = ctx.saved_tensors
+    B, d = q.shape; C = c.shape[0]
+    g = f32c(g, "grad").view(1)
+    dq = torch.empty_like(q); dc = torch.empty_like(c)
+    check(lib().tfrs_hardneg_loss_bwd(ptr(q), ptr(c), B, C, d, ptr(top_i), ctx.k1, ptr(coef), ptr(g), ptr(dq), ptr(dc), stream()),
+          "hardneg_loss_bwd")
+    return dq, dc, None, None, None
+
+
+def hard_negative_softmax_loss(q: torch.Tensor, c: torch.Tensor, num_hard_negatives: int,
+                               sample_weight: Optional[torch.Tensor] = None, temperature: Optional[float] = None) -> torch.Tensor:
+  """Retrieval loss with HardNegativeMining(n) (tasks/retrieval.py:205-210, layers/loss.py:61-111): softmax cross-entropy
+  over the positive and the n highest-scoring other candidates of each query."""
+  inv_t = 1.0 if temperature is None else 1.0 / float(temperature)
+  return _HardNegativeSoftmax.apply(q, c, int(num_hard_negatives), sample_weight, inv_t)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -581,6 +665,71 @@ def cross(x0: torch.Tensor, x: torch.Tensor, W: torch.Tensor, bias: Optional[tor
           ) -> torch.Tensor:
   """x0 * (x @ W + bias + diag_scale * x) + x   (layers/feature_interaction/dcn.py:176-186)."""
   return _Cross.apply(x0, x, W, bias, float(diag_scale))
+
+
+def gemm_tc(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: bool = False) -> torch.Tensor:
+  """op(a) @ op(b) on the tensor cores with fp32 parity (split fp16, ~2^-21 relative error); any shape."""
+  a = f32c(a, "a"); b = f32c(b, "b")
+  M, K = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
+  N = b.shape[0] if trans_b else b.shape[1]
+  if (b.shape[1] if trans_b else b.shape[0]) != K:
+    raise ValueError(f"gemm_tc: inner dimensions differ ({tuple(a.shape)} x {tuple(b.shape)})")
+  out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+  ws = workspace(lib().tfrs_gemm_tc_workspace_bytes(M, N, K), a.device, "gemm_tc")
+  check(lib().tfrs_gemm_tc_f32(int(trans_a), int(trans_b), M, N, K, ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), N, ptr(ws),
+                               ws.numel(), stream()), "gemm_tc")
+  return out
+
+
+class _CrossLowRank(torch.autograd.Function):
+  """x0 * ((x @ U) @ V + bias + diag * x) + x on the tensor cores (forward: 2 GEMMs, formula fused; backward: 4 GEMMs)."""
+
+  @staticmethod
+  def forward(ctx, x0, x, U, V, bias, diag_scale):
+    x0 = f32c(x0, "x0"); x = f32c(x, "x"); U = f32c(U, "kernel_u"); V = f32c(V, "kernel_v")
+    b = None if bias is None else f32c(bias, "bias")
+    B, D = x0.shape; p = U.shape[1]
+    if U.shape != (D, p) or V.shape != (p, D):
+      raise ValueError(f"cross_lowrank: kernels must be [{D},p] and [p,{D}], got {tuple(U.shape)} and {tuple(V.shape)}")
+    out = torch.empty_like(x0)
+    need_grad = any(ctx.needs_input_grad[:5])
+    prod = torch.empty_like(x0) if need_grad else None
+    t = torch.empty((B, p), dtype=torch.float32, device=x0.device)
+    ws = workspace(lib().tfrs_cross_lowrank_tc_workspace_bytes(B, D, p), x0.device, "cross_lowrank")
+    check(lib().tfrs_cross_lowrank_tc_fwd_f32(ptr(x0), ptr(x), ptr(U), ptr(V), ptr(b), B, D, p, D, c_f(diag_scale), ptr(out), ptr(prod),
+                                              ptr(t), ptr(ws), ws.numel(), stream()), "cross_lowrank_tc_fwd")
+    if need_grad:
+      ctx.save_for_backward(x0, x, U, V, t, prod)
+    ctx.diag = diag_scale
+    ctx.has_bias = b is not None
+    return out
+
+  @staticmethod
+  def backward(ctx, g):
+    x0, x, U, V, t, prod = ctx.saved_tensors
+    g = f32c(g, "grad")
+    B, D = x0.shape; p = U.shape[1]
+    n0, n1, n2, n3, n4 = ctx.needs_input_grad[:5]
+    dx0 = torch.empty_like(x0) if n0 else None
+    dx = torch.empty_like(x) if n1 else None
+    dU = torch.empty_like(U) if n2 else None
+    dV = torch.empty_like(V) if n3 else None
+    db = torch.empty((D,), dtype=torch.float32, device=x0.device) if (n4 and ctx.has_bias) else None
+    ws = workspace(lib().tfrs_cross_lowrank_tc_bwd_workspace_bytes(B, D, p), x0.device, "cross_lowrank_bwd")
+    check(lib().tfrs_cross_lowrank_tc_bwd_f32(ptr(x0), ptr(x), ptr(U), ptr(V), ptr(t), ptr(prod), ptr(g), B, D, p, D, c_f(ctx.diag),
+                                              ptr(dx0), ptr(dx), ptr(dU), ptr(dV), ptr(db), ptr(ws), ws.numel(), stream()),
+          "cross_lowrank_tc_bwd")
+    return dx0, dx, dU, dV, db, None
+
+
+def cross_lowrank_supported(B: int, D: int, p: int) -> bool:
+  return B >= CROSS_TC_MIN_B and D >= CROSS_TC_MIN_D and D <= 1024 and 1 <= p <= 1024
+
+
+def cross_lowrank(x0: torch.Tensor, x: torch.Tensor, U: torch.Tensor, V: torch.Tensor, bias: Optional[torch.Tensor],
+                  diag_scale: float = 0.0) -> torch.Tensor:
+  """x0 * ((x @ U) @ V + bias + diag_scale * x) + x  (dcn.py:131-148,178-186; multi_layer_dcn.py:146-148)."""
+  return _CrossLowRank.apply(x0, x, U, V, bias, float(diag_scale))
 
 
 # ------------------------------------------------------------------------------------------------

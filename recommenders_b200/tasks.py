@@ -27,10 +27,11 @@ def _categorical_crossentropy_sum(y_true: torch.Tensor, y_pred: torch.Tensor, sa
 class Retrieval(torch.nn.Module, Task):
   """A factorized retrieval task (tasks/retrieval.py:29-235).
 
-  The default configuration (2-D queries, default loss, no sampling-probability / accidental-hit /
-  score-mask / hard-negative options) runs as ONE fused loss kernel that never materialises the
-  [B, C] logits or the eye() labels; `temperature` is folded into that kernel.  The optional transforms
-  fall back to the exact score matrix + the reference's op sequence."""
+  2-D queries with the default loss run fused and never materialise the [B, C] logits or the eye() labels:
+  `temperature`, the sampling-probability correction, accidental-hit removal and `score_mask` are folded into the
+  tensor-core loss kernels, hard-negative mining runs on the top-K scan.  A custom loss object, multi-head (3-D)
+  queries, batch metrics, or shapes outside the tensor-core range use the exact score matrix + the reference's
+  op sequence."""
 
   def __init__(self, loss: Optional[Callable] = None,
                metrics: Optional[Union[Sequence[tfrs_metrics.Factorized], tfrs_metrics.Factorized]] = None,
@@ -75,18 +76,22 @@ class Retrieval(torch.nn.Module, Task):
            candidate_ids=None, compute_metrics: bool = True, compute_batch_metrics: bool = True,
            score_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     three_d = query_embeddings.dim() == 3
-    other_transforms = (three_d or self._loss is not None or self._remove_accidental_hits or score_mask is not None or
-                        self._num_hard_negatives is not None)
-    # temperature + sampling-probability correction only (the production "sampled softmax with logQ correction"):
-    # the correction is a per-candidate logit bias, folded into the fused tensor-core loss when the shape allows it
-    fused_bias = (candidate_sampling_probability is not None and not other_transforms and
-                  not (compute_batch_metrics and len(self._batch_metrics) > 0) and
-                  ops.inbatch_softmax_bias_supported(query_embeddings.shape[0], candidate_embeddings.shape[0],
-                                                     query_embeddings.shape[-1]))
-    need_scores = not fused_bias and (other_transforms or candidate_sampling_probability is not None or
-                                      (compute_batch_metrics and len(self._batch_metrics) > 0))
     if self._remove_accidental_hits and candidate_ids is None:
       raise ValueError("When accidental hit removal is enabled, candidate ids must be supplied.")
+    wants_batch_scores = compute_batch_metrics and len(self._batch_metrics) > 0
+    options = (candidate_sampling_probability is not None or self._remove_accidental_hits or score_mask is not None)
+    # Everything except a custom loss object, 3-D (multi-head) queries and batch metrics (which need the logits) runs
+    # fused: temperature, sampling-probability correction (a per-candidate bias), accidental-hit removal (candidate ids
+    # compared in the epilogue) and score_mask (keep-bits) inside the tensor-core loss; hard-negative mining through the
+    # top-K scan + a sparse loss (`ops.hard_negative_softmax_loss`).  Nothing of size [B, C] is materialised there.
+    fusable = not three_d and self._loss is None and not wants_batch_scores
+    B_, C_, d_ = query_embeddings.shape[0], candidate_embeddings.shape[0], query_embeddings.shape[-1]
+    fused_hard = (fusable and self._num_hard_negatives is not None and not options and
+                  ops.hard_negative_supported(B_, C_, d_, self._num_hard_negatives))
+    fused_opts = (fusable and self._num_hard_negatives is None and options and
+                  ops.inbatch_softmax_bias_supported(B_, C_, d_))
+    plain = not three_d and self._loss is None and self._num_hard_negatives is None and not options
+    need_scores = wants_batch_scores or not (fused_hard or fused_opts or plain)
 
     scores = labels = None
     if need_scores:
@@ -109,12 +114,18 @@ class Retrieval(torch.nn.Module, Task):
       if self._num_hard_negatives is not None:
         scores, labels = loss_layers.HardNegativeMining(self._num_hard_negatives)(scores, labels)
 
-    plain = not (other_transforms or candidate_sampling_probability is not None)
-    if fused_bias:
-      # logits - log(clip(p, 1e-6, 1))  (layers/loss.py:150-158) as a bias vector
-      p_c = torch.as_tensor(candidate_sampling_probability, dtype=torch.float32, device=candidate_embeddings.device).reshape(-1)
-      bias = -torch.log(torch.clamp(p_c, 1e-6, 1.0))
-      loss = ops.inbatch_softmax_loss(query_embeddings, candidate_embeddings, sample_weight, self._temperature, bias)
+    if fused_opts:
+      bias = None
+      if candidate_sampling_probability is not None:
+        # logits - log(clip(p, 1e-6, 1))  (layers/loss.py:150-158) as a bias vector
+        p_c = torch.as_tensor(candidate_sampling_probability, dtype=torch.float32, device=candidate_embeddings.device).reshape(-1)
+        bias = -torch.log(torch.clamp(p_c, 1e-6, 1.0))
+      loss = ops.inbatch_softmax_loss(query_embeddings, candidate_embeddings, sample_weight, self._temperature, bias,
+                                      candidate_ids if self._remove_accidental_hits else None,
+                                      None if score_mask is None else score_mask.to(candidate_embeddings.device))
+    elif fused_hard:
+      loss = ops.hard_negative_softmax_loss(query_embeddings, candidate_embeddings, self._num_hard_negatives, sample_weight,
+                                            self._temperature)
     elif plain:
       loss = ops.inbatch_softmax_loss(query_embeddings, candidate_embeddings, sample_weight, self._temperature)
     elif self._loss is not None:

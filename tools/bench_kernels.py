@@ -72,7 +72,38 @@ with torch.no_grad():
   t = timeit(cross3, iters=5 if not quick else 3, warm=2)
 flops = 3 * 2.0 * B * Dc * Dc
 out["cfg5_cross_fwd_3layers"] = {"seconds": t, "TFLOPs": flops / t / 1e12, "flops": flops, "path": "tcgen05 fp16 hi/lo split GEMM + fused epilogue (B>=1024), exact CUDA-core SGEMM otherwise"}
-del tables, ids_sets, act, x0, Ws
+# one Cross layer forward + backward (the training step's share), then the low-rank variants (p = 256) -- SURVEY 8f-4
+go = torch.randn((B, Dc), generator=g, device=dev)
+def cross_fb():
+  xs = [t.detach().requires_grad_(True) for t in (x0, x0, Ws[0], bs[0])]
+  ops.cross(xs[0], xs[1], xs[2], xs[3], 0.0).backward(go)
+t = timeit(cross_fb, iters=5 if not quick else 3, warm=2)
+out["cfg5_cross_layer_fwd_bwd"] = {"seconds": t, "TFLOPs": 3 * 2.0 * B * Dc * Dc / t / 1e12, "note": "fwd + dx + dW GEMMs, algorithmic flops"}
+P = 256
+Us = [torch.randn((Dc, P), generator=g, device=dev) * 0.05 for _ in range(3)]
+Vs = [torch.randn((P, Dc), generator=g, device=dev) * 0.05 for _ in range(3)]
+def lowrank3():
+  x = x0
+  for U, V, b in zip(Us, Vs, bs):
+    x = ops.cross_lowrank(x0, x, U, V, b, 0.0)
+  return x
+def lowrank3_unfused():
+  x = x0
+  for U, V, b in zip(Us, Vs, bs):
+    x = x0 * (ops.matmul(ops.matmul(x, U), V) + b) + x
+  return x
+with torch.no_grad():
+  t = timeit(lowrank3, iters=5 if not quick else 3, warm=2)
+  t0 = timeit(lowrank3_unfused, iters=3, warm=1)
+fl = 3 * 2 * 2.0 * B * Dc * P
+out["cfg5_multilayer_dcn_p256_fwd_3layers"] = {"seconds": t, "TFLOPs": fl / t / 1e12, "flops": fl, "unfused_cuda_core_seconds": t0,
+                                               "path": "2 tcgen05 split-fp16 GEMMs per layer, cross formula in the second one's epilogue"}
+def lowrank_fb():
+  ys = [t.detach().requires_grad_(True) for t in (x0, x0, Us[0], Vs[0], bs[0])]
+  ops.cross_lowrank(ys[0], ys[1], ys[2], ys[3], ys[4], 0.0).backward(go)
+t = timeit(lowrank_fb, iters=5 if not quick else 3, warm=2)
+out["cfg5_lowrank_layer_fwd_bwd"] = {"seconds": t, "TFLOPs": 3 * 2 * 2.0 * B * Dc * P / t / 1e12, "note": "2 fwd + 4 bwd GEMMs, algorithmic flops"}
+del tables, ids_sets, act, x0, Ws, Us, Vs, go
 
 # ---- config 3: two-tower step pieces, 10M users / 1M items, d=64, batch 16384
 U, I, d, Bt = (10_000_000, 1_000_000, 64, 16384) if not quick else (1_000_000, 100_000, 64, 4096)
