@@ -1,6 +1,7 @@
 // adagrad.cu -- K4: deterministic sparse Adagrad on the rows touched by a batch.
 // Replaces optimizer.apply_gradients(IndexedSlices) (models/base.py:77-78, Adagrad per README.md:84).
-//   1. keys = (id << 24 | position) sorted ascending (bitonic, shared-memory tiles + global strides)
+//   1. keys = (id << 24 | position) grouped by id with positions ascending: bucketed rank sort for a training-step batch
+//      (n <= 16384), bitonic sort (shared-memory tiles + global strides) beyond
 //   2. one warp per run of equal ids: duplicate gradient rows are summed in order of occurrence
 //      (lanes = columns, no float atomics), then  acc += g*g ; var -= lr*g/sqrt(acc+eps)  (or the
 //      legacy sqrt(acc)+eps form).  Every step is a single IEEE fp32 op (no FMA contraction) so the
@@ -60,37 +61,54 @@ ag_bitonic_local(unsigned long long* __restrict__ keys, long long P, long long f
   for (int t = threadIdx.x; t < tile; t += AG_THREADS) keys[base + t] = sk[t];
 }
 
-// n <= AG_RANK_MAX: all-pairs RANK sort.  Keys are unique (the position is part of the key), so the sorted slot of a
-// key is the number of keys below it: every thread owns one key and counts over a quarter of the batch staged through
-// shared memory; the partial counts meet in rank[] (integer atomics: order-independent).  n^2 = 2.7e8 comparisons at the
-// training step's batch (cfg3: 16384 ids) keep the whole chip busy for ~30 us in ONE wave, where the bitonic network
-// needs ~100 barrier-separated stages on two CTAs.
+// n <= AG_RANK_MAX: bucketed RANK sort.  ag_apply only needs the members of an id to be contiguous and in order of
+// occurrence -- not a global order by id.  So: (1) one CTA hashes the ids into AB_BUCKETS buckets (shared-memory histogram,
+// exclusive scan, scatter: equal ids land in the same bucket); (2) keys are unique (the position is part of the key), so the
+// slot of a key inside its bucket is the number of bucket members below it: every thread owns one key and counts over its
+// bucket only (n^2 / AB_BUCKETS comparisons instead of n^2; the all-pairs count over the whole batch was 56 us of the 80 us
+// step at cfg3).  The result is deterministic: the scatter order inside a bucket is not, the ranks are.
 constexpr int AG_RANK_MAX = 16384;
-constexpr int AR_THREADS = 128, AR_TILE = 1024, AR_SPLIT = 4;
-template <typename IdT>
-__global__ void __launch_bounds__(AR_THREADS)
-ag_rank_count(const IdT* __restrict__ ids, long long n, long long rows, unsigned int* __restrict__ rank) {
-  __shared__ unsigned long long tile[AR_TILE];
-  const long long i = (long long)blockIdx.x * AR_THREADS + threadIdx.x;
-  const unsigned long long mine = i < n ? ag_key(ids, i, rows) : ~0ull;
-  const long long per = (n + AR_SPLIT - 1) / AR_SPLIT;
-  const long long j_lo = (long long)blockIdx.y * per, j_hi = min(n, j_lo + per);
-  unsigned int r = 0;
-  for (long long j0 = j_lo; j0 < j_hi; j0 += AR_TILE) {
-    __syncthreads();
-    for (int t = threadIdx.x; t < AR_TILE; t += AR_THREADS) tile[t] = (j0 + t < j_hi) ? ag_key(ids, j0 + t, rows) : ~0ull;
-    __syncthreads();
-#pragma unroll 16
-    for (int t = 0; t < AR_TILE; ++t) r += (tile[t] < mine) ? 1u : 0u;   // padding (~0) is never below a key
-  }
-  if (i < n && r) atomicAdd(&rank[i], r);
+constexpr int AB_BUCKETS = 64, AB_THREADS = 1024;
+__device__ __forceinline__ int ag_bucket(unsigned long long key) {
+  const unsigned int id = (unsigned int)(key >> 24) ^ (unsigned int)(key >> 56);
+  return (int)((id * 0x9E3779B1u) >> 26);   // 6 bits
 }
-
 template <typename IdT>
-__global__ void ag_rank_scatter(const IdT* __restrict__ ids, long long n, long long rows, const unsigned int* __restrict__ rank,
-                                unsigned long long* __restrict__ keys) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) keys[rank[i]] = ag_key(ids, i, rows);
+__global__ void __launch_bounds__(AB_THREADS)
+ag_bucket_scatter(const IdT* __restrict__ ids, long long n, long long rows, unsigned long long* __restrict__ bkeys,
+                  unsigned int* __restrict__ bstart) {
+  __shared__ unsigned int hist[AB_BUCKETS], cur[AB_BUCKETS];
+  if (threadIdx.x < AB_BUCKETS) hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (long long j = threadIdx.x; j < n; j += AB_THREADS) atomicAdd(&hist[ag_bucket(ag_key(ids, j, rows))], 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int a = 0;
+    for (int b = 0; b < AB_BUCKETS; ++b) { cur[b] = a; bstart[b] = a; a += hist[b]; }
+    bstart[AB_BUCKETS] = a;
+  }
+  __syncthreads();
+  for (long long j = threadIdx.x; j < n; j += AB_THREADS) {
+    const unsigned long long k = ag_key(ids, j, rows);
+    bkeys[atomicAdd(&cur[ag_bucket(k)], 1u)] = k;
+  }
+}
+__global__ void __launch_bounds__(128)
+ag_bucket_rank(const unsigned long long* __restrict__ bkeys, long long n, const unsigned int* __restrict__ bstart,
+               unsigned long long* __restrict__ keys) {
+  const long long i = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long mine = bkeys[i];
+  const int b = ag_bucket(mine);
+  const unsigned int s = bstart[b], e = bstart[b + 1];
+  unsigned int r = 0;
+  unsigned int j = s;
+  for (; j + 4 <= e; j += 4) {   // lanes of a warp mostly share the bucket: broadcast loads through L1
+    const unsigned long long k0 = __ldg(bkeys + j), k1 = __ldg(bkeys + j + 1), k2 = __ldg(bkeys + j + 2), k3 = __ldg(bkeys + j + 3);
+    r += (k0 < mine) + (k1 < mine) + (k2 < mine) + (k3 < mine);
+  }
+  for (; j < e; ++j) r += __ldg(bkeys + j) < mine;
+  keys[s + r] = mine;
 }
 
 __global__ void ag_bitonic_global(unsigned long long* __restrict__ keys, long long P, long long size, long long stride) {
@@ -241,7 +259,7 @@ using namespace tfrs;
 extern "C" size_t tfrs_sparse_adagrad_workspace_bytes(int64_t n, int d) {
   (void)d;
   const size_t P = (size_t)ag_pow2(n > 2 ? n : 2);
-  return P * 8 /*keys*/ + P * 4 /*ranks*/ + (P / AG_LONG + 2) * 4 /*long-run list*/ + 1024;
+  return P * 8 /*keys*/ + P * 8 /*bucketed keys*/ + (P / AG_LONG + 2) * 4 /*long-run list*/ + (AB_BUCKETS + 1) * 4 + 1024;
 }
 
 extern "C" int tfrs_sparse_adagrad_f32(float* table, float* accum, int64_t rows, int d, const void* ids,
@@ -258,9 +276,10 @@ extern "C" int tfrs_sparse_adagrad_f32(float* table, float* accum, int64_t rows,
   if (!ws || ws_bytes < tfrs_sparse_adagrad_workspace_bytes(n, d)) { set_error("sparse_adagrad: workspace too small"); return TFRS_ERR_WORKSPACE_TOO_SMALL; }
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* keys = (unsigned long long*)ws;
-  unsigned int* rank = (unsigned int*)(keys + P);
-  unsigned int* long_count = rank + P;
+  unsigned long long* bkeys = keys + P;
+  unsigned int* long_count = (unsigned int*)(bkeys + P);
   unsigned int* long_list = long_count + 1;
+  unsigned int* bstart = long_list + (P / AG_LONG + 1);
   auto apply = [&]() -> int {
     TFRS_CUDA(cudaMemsetAsync(long_count, 0, 4, st));
     ag_apply<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(keys, n, grad_rows, d, table, accum, lr, eps, eps_inside_sqrt, long_count, long_list);
@@ -273,16 +292,11 @@ extern "C" int tfrs_sparse_adagrad_f32(float* table, float* accum, int64_t rows,
     return TFRS_OK;
   };
   if (n <= AG_RANK_MAX) {
-    TFRS_CUDA(cudaMemsetAsync(rank, 0, (size_t)n * 4, st));
-    const dim3 grid((unsigned)ceil_div(n, AR_THREADS), AR_SPLIT);
-    if (ids_dtype == TFRS_I32) {
-      ag_rank_count<int32_t><<<grid, AR_THREADS, 0, st>>>((const int32_t*)ids, n, rows, rank);
-      ag_rank_scatter<int32_t><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((const int32_t*)ids, n, rows, rank, keys);
-    } else {
-      ag_rank_count<int64_t><<<grid, AR_THREADS, 0, st>>>((const int64_t*)ids, n, rows, rank);
-      ag_rank_scatter<int64_t><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((const int64_t*)ids, n, rows, rank, keys);
-    }
-    TFRS_LAUNCH_CHECK(); count_launch(1);
+    if (ids_dtype == TFRS_I32) ag_bucket_scatter<int32_t><<<1, AB_THREADS, 0, st>>>((const int32_t*)ids, n, rows, bkeys, bstart);
+    else ag_bucket_scatter<int64_t><<<1, AB_THREADS, 0, st>>>((const int64_t*)ids, n, rows, bkeys, bstart);
+    TFRS_LAUNCH_CHECK();
+    ag_bucket_rank<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(bkeys, n, bstart, keys);
+    TFRS_LAUNCH_CHECK();
     return apply();
   }
   unsigned kb = (unsigned)ceil_div(P, 256);

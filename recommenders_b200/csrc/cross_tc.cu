@@ -117,61 +117,47 @@ cross_tc_kernel(const CrossParams p) {
       const uint32_t tphase = (it >> 1) & 1;
       const long long mb = t / p.n_nt; const int nt = (int)(t % p.n_nt);
       const int n0 = nt * 128 + half * 64;
-      {
-        // x / x0 of the NEXT tile are pulled into L2 now, one tile time ahead of their use: otherwise every batch of row
-        // loads below waits a full DRAM round trip and the epilogue, not the MMAs, paces the kernel
-        const long long tn = t + gridDim.x;
-        if (tn < n_tiles) {
-          const long long rn = (tn / p.n_nt) * 256 + ab * 128 + quad * 32 + lane;
-          const int cn = (int)(tn % p.n_nt) * 128 + half * 64;
-          if (rn < p.B && cn < p.D) {
-            const int c1 = min(cn + 32, p.D - 1);
-            prefetch_l2(p.x + rn * p.ld + cn); prefetch_l2(p.x + rn * p.ld + c1);
-            prefetch_l2(p.x0 + rn * p.ld + cn); prefetch_l2(p.x0 + rn * p.ld + c1);
-          }
-        }
-      }
       mbar_wait(&t_full[buf], tphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ab * 2 + buf) * 128 + half * 64);
-      uint32_t r[64];
-      tmem_ld64(taddr, r);
-      tmem_ld_wait64(r);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[buf]);
-      // The accumulators arrive one ROW per lane (32 rows x 64 columns per warp).  Global memory wants the other
-      // orientation, so each 32x32 block is transposed in registers (5 butterfly stages of shfl.xor): afterwards
-      // lane l holds COLUMN l of the 32 rows and every x / x0 / out access of the warp is one contiguous 128-byte
-      // segment of a row (row-per-lane accesses would touch 32 DRAM pages per instruction).
+      // The accumulators arrive one ROW per lane.  Global memory wants the other orientation, so each 32x32 block is
+      // transposed in registers (5 butterfly stages of shfl.xor): afterwards lane l holds COLUMN l of the 32 rows and every
+      // x / x0 / out access of the warp is one contiguous 128-byte segment of a row.  The 64 columns are taken from TMEM in
+      // two halves of 32 registers, which leaves room for 16 rows x 2 operands = 32 independent loads in flight per thread:
+      // the epilogue is a latency-bound stream (4 x [B,D] of HBM traffic), and with 4-row batches it, not the MMAs, paced
+      // the kernel (same time at K = 256 as at K = 845).
       const long long row_base = mb * 256 + ab * 128 + quad * 32;
-#pragma unroll
+#pragma unroll 1
       for (int blk = 0; blk < 2; ++blk) {
-        // transposed in place inside r[blk*32 .. blk*32+31] (raw bits; unscaled when used)
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ab * 2 + buf) * 128 + half * 64 + blk * 32), r);
+        tmem_ld_wait32(r);
+        if (blk == 1) {   // both halves are in registers: the MMA warp may reuse this TMEM buffer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[buf]);
+        }
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) {
           const bool upper = (lane & s) != 0;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             if ((i & s) == 0) {
-              const uint32_t lo_v = r[blk * 32 + i], hi_v = r[blk * 32 + (i | s)];
+              const uint32_t lo_v = r[i], hi_v = r[i | s];
               const uint32_t recv = __shfl_xor_sync(0xffffffffu, upper ? lo_v : hi_v, s);
-              r[blk * 32 + i] = upper ? recv : lo_v;
-              r[blk * 32 + (i | s)] = upper ? hi_v : recv;
+              r[i] = upper ? recv : lo_v;
+              r[i | s] = upper ? hi_v : recv;
             }
           }
         }
-        // now a[j] = accumulator of row (row_base + j), column (n0 + blk*32 + lane)
+        // now r[j] = accumulator of row (row_base + j), column (n0 + blk*32 + lane)
         const int col = n0 + blk * 32 + lane;
         if (col < p.D) {
           const float bcol = p.bias ? __ldg(p.bias + col) : 0.f;
-          // rows in batches of 4: all 8 loads are issued before the first store (out may alias x for the
-          // compiler, so it would otherwise serialise load -> store -> load per row)
 #pragma unroll
-          for (int j0 = 0; j0 < 32; j0 += 4) {
-            float xv[4], x0v[4];
+          for (int j0 = 0; j0 < 32; j0 += 16) {
+            float xv[16], x0v[16];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 16; ++u) {
               const long long rr = row_base + j0 + u;
               const bool ok = rr < p.B;
               const long long o = rr * p.ld + col;
@@ -179,11 +165,11 @@ cross_tc_kernel(const CrossParams p) {
               x0v[u] = ok ? __ldg(p.x0 + o) : 0.f;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 16; ++u) {
               const long long rr = row_base + j0 + u;
               if (rr < p.B) {
                 const long long o = rr * p.ld + col;
-                float pv = __uint_as_float(r[blk * 32 + j0 + u]) * unscale + bcol;
+                float pv = __uint_as_float(r[j0 + u]) * unscale + bcol;
                 if (p.diag != 0.f) pv += p.diag * xv[u];
                 if (p.prod) p.prod[o] = pv;
                 p.out[o] = x0v[u] * pv + xv[u];

@@ -128,44 +128,32 @@ split_gemm_kernel(const SgParams p) {
       const int buf = it & 1;
       const uint32_t tphase = (it >> 1) & 1;
       const int n0 = nt * 128 + half * 64;
-      if (MODE == SG_DX || MODE == SG_CROSS) {
-        // The epilogue operands of the NEXT tile are pulled into L2 now, one tile time ahead of their use: without it
-        // every batch of row loads below waits a full DRAM round trip and the epilogue, not the MMAs, paces the kernel.
-        const long long tn = t + gridDim.x;
-        if (tn < n_items) {
-          const long long remn = tn % per_chunk;
-          const long long rn = (remn / p.n_nt) * 256 + ab * 128 + quad * 32 + lane;
-          const int cn = (int)(remn % p.n_nt) * 128 + half * 64;
-          if (rn < p.M && cn < p.N) {
-            if (MODE == SG_CROSS || p.diag != 0.f) { prefetch_l2(p.e0 + rn * p.ld0 + cn); prefetch_l2(p.e0 + rn * p.ld0 + min(cn + 32, (int)p.N - 1)); }
-            prefetch_l2(p.e1 + rn * p.ld1 + cn); prefetch_l2(p.e1 + rn * p.ld1 + min(cn + 32, (int)p.N - 1));
-          }
-        }
-      }
       mbar_wait(&t_full[buf], tphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ab * 2 + buf) * 128 + half * 64);
-      uint32_t r[64];
-      tmem_ld64(taddr, r);
-      tmem_ld_wait64(r);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[buf]);
-      // one accumulator ROW per lane -> transpose each 32x32 block in registers so that lane l holds COLUMN l of
-      // the 32 rows and every global access of the warp is one contiguous 128-byte row segment
+      // one accumulator ROW per lane -> each 32x32 block is transposed in registers so that lane l holds COLUMN l of the 32
+      // rows and every global access of the warp is one contiguous 128-byte row segment.  TMEM is read in two 32-column
+      // halves: 32 accumulator registers leave room for 16-row batches of epilogue loads (see cross_tc.cu).
       const long long row_base = mb * 256 + ab * 128 + quad * 32;
-#pragma unroll
+#pragma unroll 1
       for (int blk = 0; blk < 2; ++blk) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ab * 2 + buf) * 128 + half * 64 + blk * 32), r);
+        tmem_ld_wait32(r);
+        if (blk == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[buf]);
+        }
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) {
           const bool upper = (lane & s) != 0;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             if ((i & s) == 0) {
-              const uint32_t lo_v = r[blk * 32 + i], hi_v = r[blk * 32 + (i | s)];
+              const uint32_t lo_v = r[i], hi_v = r[i | s];
               const uint32_t recv = __shfl_xor_sync(0xffffffffu, upper ? lo_v : hi_v, s);
-              r[blk * 32 + i] = upper ? recv : lo_v;
-              r[blk * 32 + (i | s)] = upper ? hi_v : recv;
+              r[i] = upper ? recv : lo_v;
+              r[i | s] = upper ? hi_v : recv;
             }
           }
         }
@@ -176,53 +164,53 @@ split_gemm_kernel(const SgParams p) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const long long rr = row_base + j;
-              if (rr < p.M) dst[rr * p.N] = __uint_as_float(r[blk * 32 + j]) * unscale;
+              if (rr < p.M) dst[rr * p.N] = __uint_as_float(r[j]) * unscale;
             }
           } else if (MODE == SG_PLAIN) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const long long rr = row_base + j;
-              if (rr < p.M) p.out[rr * p.ld_out + col] = __uint_as_float(r[blk * 32 + j]) * unscale;
+              if (rr < p.M) p.out[rr * p.ld_out + col] = __uint_as_float(r[j]) * unscale;
             }
           } else if (MODE == SG_CROSS) {   // out = x0 * (acc + bias + diag * x) + x   (dcn.py:176-186)
             const float bcol = p.bias ? __ldg(p.bias + col) : 0.f;
 #pragma unroll
-            for (int j0 = 0; j0 < 32; j0 += 4) {   // 8 independent loads in flight before the first store
-              float xv[4], x0v[4];
+            for (int j0 = 0; j0 < 32; j0 += 16) {   // 32 independent loads in flight before the first store
+              float xv[16], x0v[16];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < 16; ++u) {
                 const long long rr = row_base + j0 + u;
                 const bool ok = rr < p.M;
                 x0v[u] = ok ? __ldg(p.e0 + rr * p.ld0 + col) : 0.f;
                 xv[u] = ok ? __ldg(p.e1 + rr * p.ld1 + col) : 0.f;
               }
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < 16; ++u) {
                 const long long rr = row_base + j0 + u;
                 if (rr < p.M) {
-                  float pv = __uint_as_float(r[blk * 32 + j0 + u]) * unscale + bcol;
+                  float pv = __uint_as_float(r[j0 + u]) * unscale + bcol;
                   if (p.diag != 0.f) pv += p.diag * xv[u];
                   if (p.prod) p.prod[rr * p.ld_out + col] = pv;
                   p.out[rr * p.ld_out + col] = x0v[u] * pv + xv[u];
                 }
               }
             }
-          } else {
+          } else {                          // DX: dx = acc + diag * gp + g
 #pragma unroll
-            for (int j0 = 0; j0 < 32; j0 += 4) {  // loads of 4 rows before the first store (out may alias for the compiler)
-              float gpv[4], gv[4];
+            for (int j0 = 0; j0 < 32; j0 += 16) {
+              float gpv[16], gv[16];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < 16; ++u) {
                 const long long rr = row_base + j0 + u;
                 const bool ok = rr < p.M;
                 gpv[u] = (ok && p.diag != 0.f) ? __ldg(p.e0 + rr * p.ld0 + col) : 0.f;
                 gv[u] = ok ? __ldg(p.e1 + rr * p.ld1 + col) : 0.f;
               }
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < 16; ++u) {
                 const long long rr = row_base + j0 + u;
                 if (rr < p.M) {
-                  float v = __uint_as_float(r[blk * 32 + j0 + u]) * unscale + gv[u];
+                  float v = __uint_as_float(r[j0 + u]) * unscale + gv[u];
                   if (p.diag != 0.f) v += p.diag * gpv[u];
                   p.out[rr * p.ld_out + col] = v;
                 }
