@@ -151,29 +151,42 @@ cross_tc_kernel(const CrossParams p) {
         }
         // now r[j] = accumulator of row (row_base + j), column (n0 + blk*32 + lane)
         const int col = n0 + blk * 32 + lane;
-        if (col < p.D) {
+        const long long base = row_base * p.ld + col;
+        const int ldi = (int)p.ld;
+        if (row_base + 32 <= p.B && n0 + blk * 32 + 32 <= p.D) {
+          // interior block (all but the ragged last column block / row block): no per-element predicates or branches and
+          // one 32-bit row offset shared by the four arrays -- the epilogue is INSTRUCTION-bound (ncu: issue slots, not
+          // DRAM or the LSU, limit it; the checked path below costs ~70 instructions per element)
+          const float* __restrict__ xp = p.x + base; const float* __restrict__ x0p = p.x0 + base;
+          float* __restrict__ op = p.out + base; float* __restrict__ pp = p.prod ? p.prod + base : nullptr;
           const float bcol = p.bias ? __ldg(p.bias + col) : 0.f;
+          const float diag = p.diag;
 #pragma unroll
           for (int j0 = 0; j0 < 32; j0 += 16) {
             float xv[16], x0v[16];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const long long rr = row_base + j0 + u;
-              const bool ok = rr < p.B;
-              const long long o = rr * p.ld + col;
-              xv[u] = ok ? __ldg(p.x + o) : 0.f;
-              x0v[u] = ok ? __ldg(p.x0 + o) : 0.f;
-            }
+            for (int u = 0; u < 16; ++u) { const int o = (j0 + u) * ldi; xv[u] = __ldg(xp + o); x0v[u] = __ldg(x0p + o); }
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
-              const long long rr = row_base + j0 + u;
-              if (rr < p.B) {
-                const long long o = rr * p.ld + col;
-                float pv = __uint_as_float(r[j0 + u]) * unscale + bcol;
-                if (p.diag != 0.f) pv += p.diag * xv[u];
-                if (p.prod) p.prod[o] = pv;
-                p.out[o] = x0v[u] * pv + xv[u];
-              }
+              const int o = (j0 + u) * ldi;
+              float pv = fmaf(__uint_as_float(r[j0 + u]), unscale, bcol);
+              pv = fmaf(diag, xv[u], pv);
+              if (pp) pp[o] = pv;
+              op[o] = fmaf(x0v[u], pv, xv[u]);
+            }
+          }
+        } else if (col < p.D) {
+          const float bcol = p.bias ? __ldg(p.bias + col) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const long long rr = row_base + j;
+            if (rr < p.B) {
+              const long long o = rr * p.ld + col;
+              const float xv = __ldg(p.x + o), x0v = __ldg(p.x0 + o);
+              float pv = fmaf(__uint_as_float(r[j]), unscale, bcol);
+              pv = fmaf(p.diag, xv, pv);
+              if (p.prod) p.prod[o] = pv;
+              p.out[o] = fmaf(x0v, pv, xv);
             }
           }
         }

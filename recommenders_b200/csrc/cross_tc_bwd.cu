@@ -158,62 +158,74 @@ split_gemm_kernel(const SgParams p) {
           }
         }
         const int col = n0 + blk * 32 + lane;
-        if (col < p.N) {
-          if (MODE == SG_DW) {
-            float* dst = p.out + (long long)kc * p.M * p.N + col;
+        const bool interior = row_base + 32 <= p.M && n0 + blk * 32 + 32 <= p.N;   // warp-uniform
+        if (MODE == SG_DW || MODE == SG_PLAIN) {
+          float* dst = MODE == SG_DW ? p.out + (long long)kc * p.M * p.N + row_base * p.N + col : p.out + row_base * p.ld_out + col;
+          const int ldo = MODE == SG_DW ? (int)p.N : (int)p.ld_out;
+          if (interior) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const long long rr = row_base + j;
-              if (rr < p.M) dst[rr * p.N] = __uint_as_float(r[j]) * unscale;
-            }
-          } else if (MODE == SG_PLAIN) {
+            for (int j = 0; j < 32; ++j) dst[j * ldo] = __uint_as_float(r[j]) * unscale;
+          } else if (col < p.N) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const long long rr = row_base + j;
-              if (rr < p.M) p.out[rr * p.ld_out + col] = __uint_as_float(r[j]) * unscale;
-            }
-          } else if (MODE == SG_CROSS) {   // out = x0 * (acc + bias + diag * x) + x   (dcn.py:176-186)
+            for (int j = 0; j < 32; ++j)
+              if (row_base + j < p.M) dst[(long long)j * ldo] = __uint_as_float(r[j]) * unscale;
+          }
+        } else if (MODE == SG_CROSS) {   // out = x0 * (acc + bias + diag * x) + x   (dcn.py:176-186)
+          if (interior) {   // no per-element predicates; one 32-bit row offset per array (instruction-bound epilogue, see cross_tc.cu)
+            const float* __restrict__ x0p = p.e0 + row_base * p.ld0 + col; const float* __restrict__ xp = p.e1 + row_base * p.ld1 + col;
+            float* __restrict__ op = p.out + row_base * p.ld_out + col; float* __restrict__ pp = p.prod ? p.prod + row_base * p.ld_out + col : nullptr;
+            const int l0 = (int)p.ld0, l1 = (int)p.ld1, lo = (int)p.ld_out;
             const float bcol = p.bias ? __ldg(p.bias + col) : 0.f;
-#pragma unroll
-            for (int j0 = 0; j0 < 32; j0 += 16) {   // 32 independent loads in flight before the first store
-              float xv[16], x0v[16];
-#pragma unroll
-              for (int u = 0; u < 16; ++u) {
-                const long long rr = row_base + j0 + u;
-                const bool ok = rr < p.M;
-                x0v[u] = ok ? __ldg(p.e0 + rr * p.ld0 + col) : 0.f;
-                xv[u] = ok ? __ldg(p.e1 + rr * p.ld1 + col) : 0.f;
-              }
-#pragma unroll
-              for (int u = 0; u < 16; ++u) {
-                const long long rr = row_base + j0 + u;
-                if (rr < p.M) {
-                  float pv = __uint_as_float(r[j0 + u]) * unscale + bcol;
-                  if (p.diag != 0.f) pv += p.diag * xv[u];
-                  if (p.prod) p.prod[rr * p.ld_out + col] = pv;
-                  p.out[rr * p.ld_out + col] = x0v[u] * pv + xv[u];
-                }
-              }
-            }
-          } else {                          // DX: dx = acc + diag * gp + g
+            const float diag = p.diag;
 #pragma unroll
             for (int j0 = 0; j0 < 32; j0 += 16) {
-              float gpv[16], gv[16];
+              float xv[16], x0v[16];
+#pragma unroll
+              for (int u = 0; u < 16; ++u) { x0v[u] = __ldg(x0p + (j0 + u) * l0); xv[u] = __ldg(xp + (j0 + u) * l1); }
 #pragma unroll
               for (int u = 0; u < 16; ++u) {
-                const long long rr = row_base + j0 + u;
-                const bool ok = rr < p.M;
-                gpv[u] = (ok && p.diag != 0.f) ? __ldg(p.e0 + rr * p.ld0 + col) : 0.f;
-                gv[u] = ok ? __ldg(p.e1 + rr * p.ld1 + col) : 0.f;
+                float pv = fmaf(__uint_as_float(r[j0 + u]), unscale, bcol);
+                pv = fmaf(diag, xv[u], pv);
+                if (pp) pp[(j0 + u) * lo] = pv;
+                op[(j0 + u) * lo] = fmaf(x0v[u], pv, xv[u]);
               }
+            }
+          } else if (col < p.N) {
+            const float bcol = p.bias ? __ldg(p.bias + col) : 0.f;
 #pragma unroll
-              for (int u = 0; u < 16; ++u) {
-                const long long rr = row_base + j0 + u;
-                if (rr < p.M) {
-                  float v = __uint_as_float(r[j0 + u]) * unscale + gv[u];
-                  if (p.diag != 0.f) v += p.diag * gpv[u];
-                  p.out[rr * p.ld_out + col] = v;
-                }
+            for (int j = 0; j < 32; ++j) {
+              const long long rr = row_base + j;
+              if (rr < p.M) {
+                const float x0v = __ldg(p.e0 + rr * p.ld0 + col), xv = __ldg(p.e1 + rr * p.ld1 + col);
+                float pv = fmaf(__uint_as_float(r[j]), unscale, bcol);
+                pv = fmaf(p.diag, xv, pv);
+                if (p.prod) p.prod[rr * p.ld_out + col] = pv;
+                p.out[rr * p.ld_out + col] = fmaf(x0v, pv, xv);
+              }
+            }
+          }
+        } else {                          // DX: dx = acc + diag * gp + g
+          if (interior) {
+            const float* __restrict__ gpp = p.e0 + row_base * p.ld0 + col; const float* __restrict__ gp_ = p.e1 + row_base * p.ld1 + col;
+            float* __restrict__ op = p.out + row_base * p.ld_out + col;
+            const int l0 = (int)p.ld0, l1 = (int)p.ld1, lo = (int)p.ld_out;
+            const float diag = p.diag;
+#pragma unroll
+            for (int j0 = 0; j0 < 32; j0 += 16) {
+              float gv[16], gpv[16];
+#pragma unroll
+              for (int u = 0; u < 16; ++u) { gv[u] = __ldg(gp_ + (j0 + u) * l1); gpv[u] = diag != 0.f ? __ldg(gpp + (j0 + u) * l0) : 0.f; }
+#pragma unroll
+              for (int u = 0; u < 16; ++u) op[(j0 + u) * lo] = fmaf(diag, gpv[u], fmaf(__uint_as_float(r[j0 + u]), unscale, gv[u]));
+            }
+          } else if (col < p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const long long rr = row_base + j;
+              if (rr < p.M) {
+                float v = fmaf(__uint_as_float(r[j]), unscale, __ldg(p.e1 + rr * p.ld1 + col));
+                if (p.diag != 0.f) v = fmaf(p.diag, __ldg(p.e0 + rr * p.ld0 + col), v);
+                p.out[rr * p.ld_out + col] = v;
               }
             }
           }
