@@ -275,6 +275,17 @@ int tfrs_inbatch_softmax_tc_bwd_ex(const float* q, const float* c, int64_t B, in
                                    const uint8_t* score_mask, const float* lse, const float* grad_loss, float* dq, float* dc,
                                    void* ws, size_t ws_bytes, void* stream);
 
+/* Multi-head queries (tasks/retrieval.py:172-176): q is [B,H,d] and  scores_ij = max_h q_ih . c_j  ("maxsim") before the same
+ * loss.  Exact fp32 path: row blocks of the [B*H, C] head scores stay L2-resident, the head maximum is folded while the
+ * row statistics are taken; nothing of size [B,C] reaches the caller.  The gradient goes to the head(s) attaining the maximum
+ * (split evenly among exact ties, as tf.reduce_max's).  dq is [B,H,d]. */
+size_t tfrs_inbatch_softmax_maxsim_workspace_bytes(int64_t B, int H, int64_t C, int d);
+int tfrs_inbatch_softmax_maxsim_fwd(const float* q, const float* c, int64_t B, int H, int64_t C, int d, float inv_temperature,
+                                    const float* sample_weight, float* loss, float* lse, void* ws, size_t ws_bytes, void* stream);
+int tfrs_inbatch_softmax_maxsim_bwd(const float* q, const float* c, int64_t B, int H, int64_t C, int d, float inv_temperature,
+                                    const float* sample_weight, const float* lse, const float* grad_loss, float* dq, float* dc,
+                                    void* ws, size_t ws_bytes, void* stream);
+
 /* Hard-negative mining inside the loss (tasks/retrieval.py:205-210, layers/loss.py:61-111) without the [B,C] logits: the
  * n + 1 best candidates of every query come from the top-K scan above (k1 = min(n + 1, C) entries per query, exact fp32
  * scores, sorted); tfrs_hardneg_loss_fwd keeps the positive (candidate i of query i, score `positive_scores[i]`) plus the

@@ -68,47 +68,78 @@ ag_bitonic_local(unsigned long long* __restrict__ keys, long long P, long long f
 // bucket only (n^2 / AB_BUCKETS comparisons instead of n^2; the all-pairs count over the whole batch was 56 us of the 80 us
 // step at cfg3).  The result is deterministic: the scatter order inside a bucket is not, the ranks are.
 constexpr int AG_RANK_MAX = 16384;
-constexpr int AB_BUCKETS = 64, AB_THREADS = 1024;
+constexpr int AB_BUCKETS = 256, AB_THREADS = 1024, AB_PER_THREAD = AG_RANK_MAX / AB_THREADS, AB_SPLIT = 8;
 __device__ __forceinline__ int ag_bucket(unsigned long long key) {
   const unsigned int id = (unsigned int)(key >> 24) ^ (unsigned int)(key >> 56);
-  return (int)((id * 0x9E3779B1u) >> 26);   // 6 bits
+  return (int)((id * 0x9E3779B1u) >> 24);   // 8 bits
 }
+// one CTA: the batch's keys live in registers between the histogram and the scatter pass
 template <typename IdT>
 __global__ void __launch_bounds__(AB_THREADS)
 ag_bucket_scatter(const IdT* __restrict__ ids, long long n, long long rows, unsigned long long* __restrict__ bkeys,
-                  unsigned int* __restrict__ bstart) {
+                  unsigned int* __restrict__ bstart, unsigned int* __restrict__ rank) {
   __shared__ unsigned int hist[AB_BUCKETS], cur[AB_BUCKETS];
+  unsigned long long k[AB_PER_THREAD];
+#pragma unroll
+  for (int u = 0; u < AB_PER_THREAD; ++u) {
+    const long long j = threadIdx.x + (long long)u * AB_THREADS;
+    k[u] = j < n ? ag_key(ids, j, rows) : ~0ull;
+    if (j < n) rank[j] = 0;
+  }
   if (threadIdx.x < AB_BUCKETS) hist[threadIdx.x] = 0;
   __syncthreads();
-  for (long long j = threadIdx.x; j < n; j += AB_THREADS) atomicAdd(&hist[ag_bucket(ag_key(ids, j, rows))], 1u);
+#pragma unroll
+  for (int u = 0; u < AB_PER_THREAD; ++u)
+    if (k[u] != ~0ull) atomicAdd(&hist[ag_bucket(k[u])], 1u);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned int a = 0;
-    for (int b = 0; b < AB_BUCKETS; ++b) { cur[b] = a; bstart[b] = a; a += hist[b]; }
-    bstart[AB_BUCKETS] = a;
+  if (threadIdx.x < 32) {   // exclusive scan of the 256 counters: 8 per lane + a warp scan
+    unsigned int c[8], tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i] = hist[threadIdx.x * 8 + i]; tot += c[i]; }
+    unsigned int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o); if ((int)threadIdx.x >= o) inc += v; }
+    unsigned int a = inc - tot;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { cur[threadIdx.x * 8 + i] = a; bstart[threadIdx.x * 8 + i] = a; a += c[i]; }
+    if (threadIdx.x == 31) bstart[AB_BUCKETS] = a;
   }
   __syncthreads();
-  for (long long j = threadIdx.x; j < n; j += AB_THREADS) {
-    const unsigned long long k = ag_key(ids, j, rows);
-    bkeys[atomicAdd(&cur[ag_bucket(k)], 1u)] = k;
-  }
+#pragma unroll
+  for (int u = 0; u < AB_PER_THREAD; ++u)
+    if (k[u] != ~0ull) bkeys[atomicAdd(&cur[ag_bucket(k[u])], 1u)] = k[u];
 }
+// rank of a key inside its bucket = number of bucket members below it; blockIdx.y takes one slice of the bucket, so a hot
+// id's bucket (a tenth of a Zipf batch) is counted by AB_SPLIT threads per key instead of one
 __global__ void __launch_bounds__(128)
 ag_bucket_rank(const unsigned long long* __restrict__ bkeys, long long n, const unsigned int* __restrict__ bstart,
-               unsigned long long* __restrict__ keys) {
+               unsigned int* __restrict__ rank) {
   const long long i = (long long)blockIdx.x * 128 + threadIdx.x;
   if (i >= n) return;
   const unsigned long long mine = bkeys[i];
   const int b = ag_bucket(mine);
   const unsigned int s = bstart[b], e = bstart[b + 1];
+  const unsigned int per = (e - s + AB_SPLIT - 1) / AB_SPLIT;
+  unsigned int j = s + blockIdx.y * per;
+  const unsigned int j1 = min(e, j + per);
   unsigned int r = 0;
-  unsigned int j = s;
-  for (; j + 4 <= e; j += 4) {   // lanes of a warp mostly share the bucket: broadcast loads through L1
-    const unsigned long long k0 = __ldg(bkeys + j), k1 = __ldg(bkeys + j + 1), k2 = __ldg(bkeys + j + 2), k3 = __ldg(bkeys + j + 3);
-    r += (k0 < mine) + (k1 < mine) + (k2 < mine) + (k3 < mine);
+  for (; j + 8 <= j1; j += 8) {   // lanes of a warp mostly share the bucket: broadcast loads, 8 in flight
+    unsigned long long kk[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) kk[u] = __ldg(bkeys + j + u);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) r += kk[u] < mine;
   }
-  for (; j < e; ++j) r += __ldg(bkeys + j) < mine;
-  keys[s + r] = mine;
+  for (; j < j1; ++j) r += __ldg(bkeys + j) < mine;
+  if (r) atomicAdd(&rank[i], r);
+}
+__global__ void __launch_bounds__(256)
+ag_bucket_place(const unsigned long long* __restrict__ bkeys, long long n, const unsigned int* __restrict__ bstart,
+                const unsigned int* __restrict__ rank, unsigned long long* __restrict__ keys) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long mine = bkeys[i];
+  keys[bstart[ag_bucket(mine)] + rank[i]] = mine;
 }
 
 __global__ void ag_bitonic_global(unsigned long long* __restrict__ keys, long long P, long long size, long long stride) {
@@ -181,7 +212,7 @@ ag_apply(const unsigned long long* __restrict__ keys, long long n, const float* 
 // Hot ids (Zipf batches: one id can own a tenth of the batch): one CTA per long run.  All 256 threads stream the run's
 // gradient rows into a shared-memory tile (AL_ROWS rows in flight per step), then one thread per column adds the tile's
 // rows IN ORDER -- the chain is fp32 adds on shared memory, not DRAM round trips.
-constexpr int AL_THREADS = 256, AL_ROWS = 64;   // rows per tile: min(AL_ROWS, 64 KB / row bytes)
+constexpr int AL_THREADS = 256, AL_ROWS = 256;  // rows per tile: min(AL_ROWS, 64 KB / row bytes)
 __global__ void __launch_bounds__(AL_THREADS)
 ag_apply_long(const unsigned long long* __restrict__ keys, long long n, const float* __restrict__ grad, int d,
               float* __restrict__ table, float* __restrict__ accum, float lr, float eps, int eps_inside,
@@ -259,7 +290,7 @@ using namespace tfrs;
 extern "C" size_t tfrs_sparse_adagrad_workspace_bytes(int64_t n, int d) {
   (void)d;
   const size_t P = (size_t)ag_pow2(n > 2 ? n : 2);
-  return P * 8 /*keys*/ + P * 8 /*bucketed keys*/ + (P / AG_LONG + 2) * 4 /*long-run list*/ + (AB_BUCKETS + 1) * 4 + 1024;
+  return P * 8 /*keys*/ + P * 8 /*bucketed keys*/ + P * 4 /*ranks*/ + (P / AG_LONG + 2) * 4 /*long-run list*/ + (AB_BUCKETS + 1) * 4 + 1024;
 }
 
 extern "C" int tfrs_sparse_adagrad_f32(float* table, float* accum, int64_t rows, int d, const void* ids,
@@ -280,6 +311,7 @@ extern "C" int tfrs_sparse_adagrad_f32(float* table, float* accum, int64_t rows,
   unsigned int* long_count = (unsigned int*)(bkeys + P);
   unsigned int* long_list = long_count + 1;
   unsigned int* bstart = long_list + (P / AG_LONG + 1);
+  unsigned int* rank = bstart + AB_BUCKETS + 1;
   auto apply = [&]() -> int {
     TFRS_CUDA(cudaMemsetAsync(long_count, 0, 4, st));
     ag_apply<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(keys, n, grad_rows, d, table, accum, lr, eps, eps_inside_sqrt, long_count, long_list);
@@ -292,10 +324,12 @@ extern "C" int tfrs_sparse_adagrad_f32(float* table, float* accum, int64_t rows,
     return TFRS_OK;
   };
   if (n <= AG_RANK_MAX) {
-    if (ids_dtype == TFRS_I32) ag_bucket_scatter<int32_t><<<1, AB_THREADS, 0, st>>>((const int32_t*)ids, n, rows, bkeys, bstart);
-    else ag_bucket_scatter<int64_t><<<1, AB_THREADS, 0, st>>>((const int64_t*)ids, n, rows, bkeys, bstart);
+    if (ids_dtype == TFRS_I32) ag_bucket_scatter<int32_t><<<1, AB_THREADS, 0, st>>>((const int32_t*)ids, n, rows, bkeys, bstart, rank);
+    else ag_bucket_scatter<int64_t><<<1, AB_THREADS, 0, st>>>((const int64_t*)ids, n, rows, bkeys, bstart, rank);
     TFRS_LAUNCH_CHECK();
-    ag_bucket_rank<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(bkeys, n, bstart, keys);
+    ag_bucket_rank<<<dim3((unsigned)ceil_div(n, 128), AB_SPLIT), 128, 0, st>>>(bkeys, n, bstart, rank);
+    TFRS_LAUNCH_CHECK();
+    ag_bucket_place<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(bkeys, n, bstart, rank, keys);
     TFRS_LAUNCH_CHECK();
     return apply();
   }

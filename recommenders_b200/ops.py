@@ -523,6 +523,45 @@ def inbatch_softmax_loss(q: torch.Tensor, c: torch.Tensor, sample_weight: Option
   return _InBatchSoftmax.apply(q, c, sample_weight, inv_t, candidate_bias, candidate_ids, score_mask)
 
 
+class _MaxSimSoftmax(torch.autograd.Function):
+  """In-batch softmax loss on multi-head queries [B,H,d]: scores = max over heads (tasks/retrieval.py:172-176)."""
+
+  @staticmethod
+  def forward(ctx, q, c, sample_weight, inv_temperature):
+    q = f32c(q, "query_embeddings"); c = f32c(c, "candidate_embeddings")
+    B, H, d = q.shape; C = c.shape[0]
+    w = None if sample_weight is None else f32c(sample_weight, "sample_weight").view(-1)
+    if w is not None and w.numel() != B:
+      raise ValueError(f"sample_weight must have one entry per query (got {w.numel()}, expected {B})")
+    loss = torch.empty((1,), dtype=torch.float32, device=q.device)
+    lse = torch.empty((B,), dtype=torch.float32, device=q.device)
+    ws = workspace(lib().tfrs_inbatch_softmax_maxsim_workspace_bytes(B, H, C, d), q.device, "softmax")
+    check(lib().tfrs_inbatch_softmax_maxsim_fwd(ptr(q), ptr(c), B, H, C, d, c_f(inv_temperature), ptr(w), ptr(loss), ptr(lse),
+                                                ptr(ws), ws.numel(), stream()), "inbatch_softmax_maxsim_fwd")
+    ctx.save_for_backward(q, c, lse, w if w is not None else torch.empty(0, device=q.device))
+    ctx.has_w = w is not None
+    ctx.inv_t = inv_temperature
+    return loss.view(())
+
+  @staticmethod
+  def backward(ctx, g):
+    q, c, lse, w = ctx.saved_tensors
+    B, H, d = q.shape; C = c.shape[0]
+    g = f32c(g, "grad").view(1)
+    dq = torch.empty_like(q); dc = torch.empty_like(c)
+    ws = workspace(lib().tfrs_inbatch_softmax_maxsim_workspace_bytes(B, H, C, d), q.device, "softmax")
+    check(lib().tfrs_inbatch_softmax_maxsim_bwd(ptr(q), ptr(c), B, H, C, d, c_f(ctx.inv_t), ptr(w) if ctx.has_w else None, ptr(lse),
+                                                ptr(g), ptr(dq), ptr(dc), ptr(ws), ws.numel(), stream()), "inbatch_softmax_maxsim_bwd")
+    return dq, dc, None, None
+
+
+def inbatch_softmax_maxsim_loss(q: torch.Tensor, c: torch.Tensor, sample_weight: Optional[torch.Tensor] = None,
+                                temperature: Optional[float] = None) -> torch.Tensor:
+  """sum_i w_i (logsumexp_j(max_h q_ih.c_j / T) - max_h q_ih.c_i / T) for q [B,H,d] (tasks/retrieval.py:172-210)."""
+  inv_t = 1.0 if temperature is None else 1.0 / float(temperature)
+  return _MaxSimSoftmax.apply(q, c, sample_weight, inv_t)
+
+
 # ------------------------------------------------------------------------------------------------
 # hard-negative mining loss (top-K scan + sparse softmax)
 # ------------------------------------------------------------------------------------------------

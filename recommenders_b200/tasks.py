@@ -87,11 +87,15 @@ class Retrieval(torch.nn.Module, Task):
     fusable = not three_d and self._loss is None and not wants_batch_scores
     B_, C_, d_ = query_embeddings.shape[0], candidate_embeddings.shape[0], query_embeddings.shape[-1]
     fused_hard = (fusable and self._num_hard_negatives is not None and not options and
+                  (self._temperature is None or self._temperature > 0) and
                   ops.hard_negative_supported(B_, C_, d_, self._num_hard_negatives))
     fused_opts = (fusable and self._num_hard_negatives is None and options and
                   ops.inbatch_softmax_bias_supported(B_, C_, d_))
     plain = not three_d and self._loss is None and self._num_hard_negatives is None and not options
-    need_scores = wants_batch_scores or not (fused_hard or fused_opts or plain)
+    # multi-head queries (maxsim, :172-176) with the default loss: the head maximum is folded inside the blocked loss kernels
+    fused_maxsim = (three_d and self._loss is None and self._num_hard_negatives is None and not options and
+                    (self._temperature is None or self._temperature > 0))
+    need_scores = wants_batch_scores or not (fused_hard or fused_opts or plain or fused_maxsim)
 
     scores = labels = None
     if need_scores:
@@ -126,6 +130,8 @@ class Retrieval(torch.nn.Module, Task):
     elif fused_hard:
       loss = ops.hard_negative_softmax_loss(query_embeddings, candidate_embeddings, self._num_hard_negatives, sample_weight,
                                             self._temperature)
+    elif fused_maxsim:
+      loss = ops.inbatch_softmax_maxsim_loss(query_embeddings, candidate_embeddings, sample_weight, self._temperature)
     elif plain:
       loss = ops.inbatch_softmax_loss(query_embeddings, candidate_embeddings, sample_weight, self._temperature)
     elif self._loss is not None:

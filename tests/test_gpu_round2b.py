@@ -224,3 +224,40 @@ def test_gather_hot_rows_bit_exact(ops, idt, dim):
   out = ops.gather(tables, ids)
   exp = np.concatenate([orc.gather(t.cpu().numpy(), i.cpu().numpy()) for t, i in zip(tables, ids)], 1)
   assert np.array_equal(out.cpu().numpy(), exp)
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-head queries: maxsim folded into the blocked loss (tasks/retrieval.py:172-176)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,C,d,temp,weighted", [(2, 2, 3, 3, None, False), (300, 4, 500, 32, 0.5, True), (1000, 2, 1000, 64, None, False)])
+def test_maxsim_loss_fused(ops, B, H, C, d, temp, weighted):
+  q = _rand((B, H, d), 111, 0.5); c = _rand((C, d), 112, 0.5)
+  w = (torch.rand((B,), device="cuda") + 0.5) if weighted else None
+  qg = q.clone().requires_grad_(True); cg = c.clone().requires_grad_(True)
+  loss = ops.inbatch_softmax_maxsim_loss(qg, cg, w, temp)
+  loss.backward()
+  ref = orc.retrieval_loss(q.cpu().numpy(), c.cpu().numpy(), None if w is None else w.cpu().numpy(), temperature=temp)
+  assert abs(float(loss) - ref) <= 1e-5 * abs(ref), (float(loss), ref)
+  # float64 gradient: G goes to the arg-max head
+  q64 = q.cpu().numpy().astype(np.float64); c64 = c.cpu().numpy().astype(np.float64)
+  t = 1.0 if temp is None else temp
+  sh = np.einsum("bhd,cd->bhc", q64, c64)
+  s = sh.max(1) / t
+  m = s.max(1, keepdims=True); p = np.exp(s - m); p /= p.sum(1, keepdims=True)
+  g = (p - np.eye(B, C)) * ((np.ones(B) if w is None else w.cpu().numpy().astype(np.float64))[:, None] / t)
+  sel = (sh == sh.max(1, keepdims=True)).astype(np.float64)
+  sel /= sel.sum(1, keepdims=True)
+  gh = sel * g[:, None, :]
+  _close(qg.grad.cpu().numpy(), np.einsum("bhc,cd->bhd", gh, c64), 1e-5, "dq")
+  _close(cg.grad.cpu().numpy(), np.einsum("bhc,bhd->cd", gh, q64), 1e-5, "dc")
+
+
+def test_retrieval_task_maxsim_known_answer(ops, monkeypatch):
+  """retrieval_test.py:255-298: q [2,2,3] -> maxsim scores [[2,5,5],[3,7,7]]; the task must not build them with eager ops."""
+  import recommenders_b200 as tfrs
+  q = torch.tensor([[[0., 1, 0], [1, 1, 0]], [[0, 1, 1], [1, 0, 1]]], device="cuda")   # any heads: compare with the oracle
+  c = torch.tensor([[0., 1, 0], [0, 1, 1], [1, 1, 0]], device="cuda")
+  monkeypatch.setattr(ops, "scores", lambda *a, **k: (_ for _ in ()).throw(AssertionError("logits were materialised")))
+  loss = tfrs.tasks.Retrieval()(q, c, compute_metrics=False)
+  ref = orc.retrieval_loss(q.cpu().numpy(), c.cpu().numpy())
+  assert abs(float(loss) - ref) <= 1e-6 * max(1.0, abs(ref))
