@@ -18,6 +18,7 @@ for what in "$@"; do
     newtests2) step pytest_new2 900 python -m pytest tests/test_gpu_round2b.py -q -m gpu -p no:cacheprovider --timeout 180 ;;
     ncukern)  step ncu_kern_launches 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file "$out/launches_kernels.csv" python tools/kernel_step_probe.py 2 ;;
     ncukfull) step ncu_kern_full 600 ncu --set full --clock-control none --import-source on -k regex:"gather_warpchunk|ag_|cross_tc_kernel" -s 13 -c 13 -f -o "$out/prof_kernels" python tools/kernel_step_probe.py 2 ;;
+    ncugather) step ncu_gather 300 ncu --set full --clock-control none --import-source on -k regex:"gather_warpchunk" -c 4 -f -o "$out/prof_gather" python tools/kernel_step_probe.py 2 ;;
     ncusel)   step ncu_sel 300 ncu --set full --clock-control none --import-source on -k regex:"tc_select|tc_rescore|tc_threshold" -s 9 -c 3 -f -o "$out/prof_finalize" python bench.py --steps 2 --warmup 3 --no-secondary --no-cpu-baseline ;;
     crossalign) step cross_align 120 python tools/cross_align_probe.py ;;
     multi)    step pytest_multi 600 python -m pytest tests/test_gpu_multi.py -q -m gpu -p no:cacheprovider ;;
