@@ -396,6 +396,8 @@ class BruteForce(TopK):
     self._shard = None  # (global_offset, ShardComm)
     self.use_tensor_cores = True
 
+  _warned_slow_path = False
+
   def index(self, candidates: Tensor, identifiers: Optional[Identifiers] = None) -> "BruteForce":
     if identifiers is None:
       identifiers_ = None
@@ -443,6 +445,14 @@ class BruteForce(TopK):
   def _local_topk(self, queries: Tensor, k: int, offset: int, out=None):
     if self._tc_ok(queries.shape[0], k):
       return ops.topk_tc(queries, self._candidates, self._tc_index, k, index_offset=offset, out=out)
+    n, d = self._candidates.shape
+    if self.use_tensor_cores and n >= ops.TC_MIN_N and not BruteForce._warned_slow_path:
+      # same results, ~20x slower: say so once instead of silently leaving the tensor-core path
+      BruteForce._warned_slow_path = True
+      import warnings
+      warnings.warn(f"BruteForce: a {n} x {d} corpus with k={k} is outside the tensor-core scan's range (d <= 128, k <= "
+                    f"{ops.TC_MAX_K}, corpus >= ~256*k rows); running the exact CUDA-core scan instead (same results, "
+                    "roughly 20x slower).", RuntimeWarning, stacklevel=3)
     return ops.topk_scan(queries, self._candidates, k, index_offset=offset, out=out)
 
   def call(self, queries, k: Optional[int] = None):
