@@ -434,8 +434,9 @@ def main():
   return 0
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of tc_scan_kernel<FILTER> at cfg2 on one GPU (ncu --set full, per launch)
-TRAFFIC_CFG2_FILTER = 170.9e6
+# dram__bytes_read.sum + dram__bytes_write.sum of tc_scan_kernel<FILTER> at cfg2 on one GPU, per launch
+# (ncu --set full, profiles/r02_tc_scan_metrics.csv: 132.87 MB read + 31.38 MB written)
+TRAFFIC_CFG2_FILTER = 164.25e6
 
 
 def _time_ms(torch, fn, iters=20, warm=3):

@@ -401,3 +401,72 @@ def test_softmax_backward_barrier_protocol_has_no_deadlock_or_phase_overrun():
   for n_iter in list(range(1, 40)) + [63, 64, 65, 128]:
     for seed in range(6):
       _simulate_softmax_bwd_protocol(n_iter, seed)
+
+
+# ------------------------------------------------------------------------------------------------
+# Retrieval.call routing (host logic only: the kernels are replaced by recorders, tensors stay on the CPU)
+# ------------------------------------------------------------------------------------------------
+def _routing_case(monkeypatch, supported=True):
+  import torch
+  from recommenders_b200 import ops, tasks
+  calls = []
+
+  def rec(name):
+    def f(*a, **k):
+      calls.append((name, a, k))
+      return torch.zeros((), requires_grad=True)
+    return f
+  monkeypatch.setattr(ops, "inbatch_softmax_loss", rec("fused"))
+  monkeypatch.setattr(ops, "hard_negative_softmax_loss", rec("hardneg"))
+  monkeypatch.setattr(ops, "inbatch_softmax_maxsim_loss", rec("maxsim"))
+  monkeypatch.setattr(ops, "inbatch_softmax_bias_supported", lambda B, C, d: supported)
+  monkeypatch.setattr(ops, "hard_negative_supported", lambda B, C, d, n: supported)
+  monkeypatch.setattr(ops, "scores", lambda q, c: (calls.append(("scores", (q, c), {})), q @ c.T)[1])
+  return tasks, calls
+
+
+def test_retrieval_routes_loss_options_to_fused_kernels(monkeypatch):
+  import torch
+  tasks, calls = _routing_case(monkeypatch)
+  q, c = torch.randn(8, 4), torch.randn(12, 4)
+  ids = torch.arange(12); mask = torch.ones(8, 12, dtype=torch.bool); prob = torch.full((12,), 0.1)
+  tasks.Retrieval()(q, c, compute_metrics=False)
+  assert [n for n, *_ in calls] == ["fused"] and calls[-1][1][4:] == ()          # plain: no options passed
+  calls.clear()
+  tasks.Retrieval(temperature=0.5, remove_accidental_hits=True)(q, c, candidate_ids=ids, score_mask=mask,
+                                                                candidate_sampling_probability=prob, compute_metrics=False)
+  (name, a, _), = calls
+  assert name == "fused" and a[3] == 0.5 and a[4] is not None and a[5] is ids and a[6] is not None
+  assert torch.allclose(a[4], -torch.log(prob))                                   # the correction travels as a bias vector
+  calls.clear()
+  tasks.Retrieval(remove_accidental_hits=False)(q, c, candidate_ids=ids, score_mask=mask, compute_metrics=False)
+  assert calls[0][1][5] is None                                                   # ids given but the option is off: not used
+  calls.clear()
+  tasks.Retrieval(num_hard_negatives=3, temperature=2.0)(q, c, compute_metrics=False)
+  assert [n for n, *_ in calls] == ["hardneg"] and calls[0][1][2] == 3
+  calls.clear()
+  tasks.Retrieval()(torch.randn(8, 2, 4), c, compute_metrics=False)
+  assert [n for n, *_ in calls] == ["maxsim"]
+
+
+def test_retrieval_falls_back_to_the_reference_sequence_when_needed(monkeypatch):
+  import torch
+  tasks, calls = _routing_case(monkeypatch, supported=False)
+  q, c = torch.randn(8, 4), torch.randn(12, 4)
+  ids = torch.arange(12)
+  # shapes outside the tensor-core range: the options run on the exact score matrix, in the reference's order
+  loss = tasks.Retrieval(remove_accidental_hits=True, num_hard_negatives=2)(q, c, candidate_ids=ids, compute_metrics=False)
+  assert [n for n, *_ in calls] == ["scores"] and loss.dim() == 0
+  calls.clear()
+  # hard negatives combined with a mask, a custom loss object, or batch metrics always need the logits
+  tasks2, calls2 = _routing_case(monkeypatch, supported=True)
+  tasks2.Retrieval(num_hard_negatives=2)(q, c, score_mask=torch.ones(8, 12, dtype=torch.bool), compute_metrics=False)
+  assert [n for n, *_ in calls2] == ["scores"]
+  calls2.clear()
+  tasks2.Retrieval(loss=lambda y, s, w=None: s.sum())(q, c, compute_metrics=False)
+  assert [n for n, *_ in calls2] == ["scores"]
+  calls2.clear()
+  tasks2.Retrieval(num_hard_negatives=2, temperature=-1.0)(q, c, compute_metrics=False)   # order-reversing temperature
+  assert [n for n, *_ in calls2] == ["scores"]
+  with pytest.raises(ValueError):
+    tasks2.Retrieval(remove_accidental_hits=True)(q, c, compute_metrics=False)
