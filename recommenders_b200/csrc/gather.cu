@@ -111,8 +111,9 @@ gather_warpchunk_kernel(GatherParams p, long long n, float* __restrict__ out, lo
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&hot_bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  n_hot = __syncthreads_count(n_hot) + 0;   // >= 1 hot id per counted thread; two chunks per thread are folded below
-  // __syncthreads_count counts THREADS with a non-zero predicate: good enough for the decision (a lower bound of the hits)
+  // __syncthreads_count counts the THREADS that hold at least one hot id: a lower bound of the hits, good enough for the
+  // decision (stage when the hits clearly outnumber half of the H rows the copy costs)
+  n_hot = __syncthreads_count(n_hot);
   const bool staged = (long long)n_hot > H / 2 && H > 0;
   if (staged) {
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&hot_bar);

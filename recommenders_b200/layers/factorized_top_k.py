@@ -224,27 +224,32 @@ class _HostStager:
     if self.used[s]:
       self.h2d_done[s].synchronize()            # host: the previous copy out of pinned[s] has finished
       self.copy_stream.wait_event(self.scan_done[s])   # device: the scan that read dev[s] has finished
+    # pageable host pieces are packed into the pinned staging buffer (contiguous runs -> one H2D each); pieces that are
+    # ALREADY pinned (a corpus kept in page-locked memory) are copied straight from where they are: no host memcpy
     at = 0
-    for p in pieces:                              # host pieces -> one pinned run; device pieces copied on the side stream
+    for p in pieces:
       r = int(p.shape[0])
-      if not p.is_cuda:
+      if not p.is_cuda and not p.is_pinned():
         self.pinned[s][at:at + r].copy_(p)
       at += r
     with torch.cuda.stream(self.copy_stream):
       at = 0
       run0 = None
       for p in pieces + [None]:
-        host = p is not None and not p.is_cuda
-        if host and run0 is None:
+        staged_host = p is not None and not p.is_cuda and not p.is_pinned()
+        if staged_host and run0 is None:
           run0 = at
-        if (not host) and run0 is not None:       # flush the contiguous host run [run0, at)
+        if (not staged_host) and run0 is not None:       # flush the contiguous staged run [run0, at)
           self.dev[s][run0:at].copy_(self.pinned[s][run0:at], non_blocking=True)
           self.h2d_bytes += (at - run0) * self.d * 4
           run0 = None
         if p is not None:
-          if p.is_cuda:
-            self.dev[s][at:at + int(p.shape[0])].copy_(p, non_blocking=True)
-          at += int(p.shape[0])
+          r = int(p.shape[0])
+          if p.is_cuda or p.is_pinned():
+            self.dev[s][at:at + r].copy_(p, non_blocking=True)
+            if not p.is_cuda:
+              self.h2d_bytes += r * self.d * 4
+          at += r
       self.h2d_done[s].record(self.copy_stream)
     torch.cuda.current_stream().wait_event(self.h2d_done[s])
     self.used[s] = True
