@@ -336,6 +336,12 @@ size_t tfrs_cross_tc_workspace_bytes(int64_t B, int D);
 int tfrs_cross_tc_fwd_f32(const float* x0, const float* x, const void* wbuf, const float* bias, int64_t B, int D,
                           int64_t ld, float diag_scale, float* out, float* prod, void* ws, size_t ws_bytes,
                           void* stream);
+/* The same forward for a STACK of cross layers (the reference chains `x = cross(x0, x)`): `out_amax_bits` (nullable, one
+ * uint32 on the device) receives max |out| as float bits, accumulated by the epilogue; passing it as `x_amax_bits` of the
+ * next layer replaces that layer's pass over x for the power-of-two rescale statistic (identical bits, identical result). */
+int tfrs_cross_tc_fwd_ex_f32(const float* x0, const float* x, const void* wbuf, const float* bias, int64_t B, int D,
+                             int64_t ld, float diag_scale, float* out, float* prod, const unsigned int* x_amax_bits,
+                             unsigned int* out_amax_bits, void* ws, size_t ws_bytes, void* stream);
 
 /* K5b with both GEMMs on the tensor cores (same contract and outputs as tfrs_cross_bwd_f32): dx = gp.W^T + diag*gp + g
  * and dW = x^T.gp as split-fp16 tcgen05 GEMMs (dW accumulates the batch in chunks of 1024 rows, partials summed in

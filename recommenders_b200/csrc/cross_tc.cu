@@ -33,6 +33,7 @@ struct CrossParams {
   float* out; float* prod;
   long long B; int D; long long ld;
   int kb, n_mb, n_nt;
+  unsigned int* out_amax;     // nullable: max |out| (float bits) accumulated by the epilogue -- the next layer's rescale statistic
 };
 
 __global__ void __launch_bounds__(CX_THREADS, 1)
@@ -111,6 +112,7 @@ cross_tc_kernel(const CrossParams p) {
     const int ew = warp - 4;
     const int half = ew >> 3, ab = (ew >> 2) & 1, quad = ew & 3;
     const float unscale = ldexpf(1.0f, -(p.xst->exp + p.wst->exp));
+    float amax_out = 0.f;       // max |out| over this thread's elements (only used when p.out_amax is given)
     int it = 0;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -172,7 +174,9 @@ cross_tc_kernel(const CrossParams p) {
               float pv = fmaf(__uint_as_float(r[j0 + u]), unscale, bcol);
               pv = fmaf(diag, xv[u], pv);
               if (pp) pp[o] = pv;
-              op[o] = fmaf(x0v[u], pv, xv[u]);
+              const float ov = fmaf(x0v[u], pv, xv[u]);
+              op[o] = ov;
+              amax_out = fmaxf(amax_out, fabsf(ov));
             }
           }
         } else if (col < p.D) {
@@ -186,11 +190,18 @@ cross_tc_kernel(const CrossParams p) {
               float pv = fmaf(__uint_as_float(r[j]), unscale, bcol);
               pv = fmaf(p.diag, xv, pv);
               if (p.prod) p.prod[o] = pv;
-              p.out[o] = fmaf(x0v, pv, xv);
+              const float ov = fmaf(x0v, pv, xv);
+              p.out[o] = ov;
+              amax_out = fmaxf(amax_out, fabsf(ov));
             }
           }
         }
       }
+    }
+    if (p.out_amax) {   // same statistic, same bits, as a cx_amax_kernel pass over `out` (max is order-independent)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) amax_out = fmaxf(amax_out, __shfl_xor_sync(0xffffffffu, amax_out, o));
+      if (lane == 0 && amax_out > 0.f) atomicMax(p.out_amax, __float_as_uint(amax_out));
     }
   }
   tc_fence_before();
@@ -233,9 +244,9 @@ extern "C" size_t tfrs_cross_tc_workspace_bytes(int64_t B, int D) {
   return 1024 + cx_img_bytes(ceil_div(B, 256) * 256, D);
 }
 
-extern "C" int tfrs_cross_tc_fwd_f32(const float* x0, const float* x, const void* wbuf, const float* bias, int64_t B, int D,
-                                     int64_t ld, float diag_scale, float* out, float* prod, void* ws, size_t ws_bytes,
-                                     void* stream) {
+extern "C" int tfrs_cross_tc_fwd_ex_f32(const float* x0, const float* x, const void* wbuf, const float* bias, int64_t B, int D,
+                                        int64_t ld, float diag_scale, float* out, float* prod, const unsigned int* x_amax_bits,
+                                        unsigned int* out_amax_bits, void* ws, size_t ws_bytes, void* stream) {
   TFRS_CHECK_ARG(x0 && x && wbuf && out, "cross_tc_fwd: NULL pointer");
   TFRS_CHECK_ARG(B > 0 && D > 0 && ld >= D, "cross_tc_fwd: bad shape");
   TFRS_CHECK_ARG(diag_scale >= 0.f, "`diag_scale` should be non-negative. Got `diag_scale` = %g", diag_scale);
@@ -248,8 +259,12 @@ extern "C" int tfrs_cross_tc_fwd_f32(const float* x0, const float* x, const void
   const int n_mb = (int)ceil_div(B, 256);
   const int n_nt = (int)ceil_div(D, 128);
   TFRS_CUDA(cudaMemsetAsync(ws, 0, 1024, st));
-  cx_amax_kernel<<<(unsigned)(148 * 8), 256, 0, st>>>(x, B, D, ld, xs);
-  TFRS_LAUNCH_CHECK();
+  if (x_amax_bits) {   // max |x| is already known (the previous layer's epilogue produced it): no pass over x
+    TFRS_CUDA(cudaMemcpyAsync(&xs->amax_bits, x_amax_bits, sizeof(unsigned int), cudaMemcpyDeviceToDevice, st));
+  } else {
+    cx_amax_kernel<<<(unsigned)(148 * 8), 256, 0, st>>>(x, B, D, ld, xs);
+    TFRS_LAUNCH_CHECK();
+  }
   cx_exp_kernel<<<1, 1, 0, st>>>(xs);
   TFRS_LAUNCH_CHECK();
   {
@@ -258,10 +273,11 @@ extern "C" int tfrs_cross_tc_fwd_f32(const float* x0, const float* x, const void
     cx_split_image_kernel<false><<<blocks, 256, 0, st>>>(x, B, D, ld, kb, (long long)n_mb * 2, xs, ximg);
     TFRS_LAUNCH_CHECK();
   }
+  if (out_amax_bits) TFRS_CUDA(cudaMemsetAsync(out_amax_bits, 0, sizeof(unsigned int), st));
   CrossParams p{};
   p.ximg = ximg; p.wimg = (const unsigned char*)wbuf + 1024; p.xst = xs; p.wst = (const CxStats*)wbuf;
   p.x0 = x0; p.x = x; p.bias = bias; p.diag = diag_scale; p.out = out; p.prod = prod;
-  p.B = B; p.D = D; p.ld = ld; p.kb = kb; p.n_mb = n_mb; p.n_nt = n_nt;
+  p.B = B; p.D = D; p.ld = ld; p.kb = kb; p.n_mb = n_mb; p.n_nt = n_nt; p.out_amax = out_amax_bits;
   const size_t smem = (size_t)CX_STAGES * CX_STAGE_BYTES + 1024 + 256;
   TFRS_DYN_SMEM(cross_tc_kernel, (int)smem);
   long long tiles = (long long)n_mb * n_nt;
@@ -269,4 +285,10 @@ extern "C" int tfrs_cross_tc_fwd_f32(const float* x0, const float* x, const void
   cross_tc_kernel<<<grid, CX_THREADS, smem, st>>>(p);
   TFRS_LAUNCH_CHECK();
   return TFRS_OK;
+}
+
+extern "C" int tfrs_cross_tc_fwd_f32(const float* x0, const float* x, const void* wbuf, const float* bias, int64_t B, int D,
+                                     int64_t ld, float diag_scale, float* out, float* prod, void* ws, size_t ws_bytes,
+                                     void* stream) {
+  return tfrs_cross_tc_fwd_ex_f32(x0, x, wbuf, bias, B, D, ld, diag_scale, out, prod, nullptr, nullptr, ws, ws_bytes, stream);
 }

@@ -96,10 +96,13 @@ class Cross(torch.nn.Module):
       raise ValueError("`x0` and `x` dimension mismatch! Got `x0` dimension {}, and x "
                        "dimension {}. This case is not supported yet.".format(x0.shape[-1], x.shape[-1]))
     lead = x0.shape[:-1]
-    x0f = x0.reshape(-1, x0.shape[-1]); xf = x.reshape(-1, x.shape[-1])
+    # 2-D inputs are passed through as the SAME tensor objects: a stacked layer recognises its predecessor's output (and
+    # the statistics its kernel attached to it) by identity
+    x0f = x0 if x0.dim() == 2 else x0.reshape(-1, x0.shape[-1])
+    xf = x if x.dim() == 2 else x.reshape(-1, x.shape[-1])
     if self._projection_dim is None and self._preactivation is None:
       out = ops.cross(x0f, xf, self.kernel, self.bias, float(self._diag_scale or 0.0))
-      return out.reshape(*lead, -1)
+      return out if len(lead) == 1 else out.reshape(*lead, -1)
     if (self._projection_dim is not None and self._preactivation is None and
         ops.cross_lowrank_supported(xf.shape[0], xf.shape[1], self._projection_dim)):
       # low-rank: two tensor-core GEMMs, the cross formula fused into the second one

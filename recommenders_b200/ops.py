@@ -655,7 +655,7 @@ def cross_weight_image(W: torch.Tensor) -> torch.Tensor:
 class _Cross(torch.autograd.Function):
 
   @staticmethod
-  def forward(ctx, x0, x, W, bias, diag_scale):
+  def forward(ctx, x0, x, W, bias, diag_scale, x_amax):
     x0 = f32c(x0, "x0"); x = f32c(x, "x"); W = f32c(W, "kernel")
     b = None if bias is None else f32c(bias, "bias")
     B, D = x0.shape
@@ -663,12 +663,15 @@ class _Cross(torch.autograd.Function):
     need_grad = any(ctx.needs_input_grad[:4])
     prod = torch.empty_like(x0) if need_grad else None
     ctx.used_tc = B >= CROSS_TC_MIN_B and D >= CROSS_TC_MIN_D and W.shape == (D, D)
+    # max |out| as float bits, produced by the tensor-core epilogue: the next layer of a stack uses it as its rescale
+    # statistic instead of a pass over its input (0 on the exact path: "unknown")
+    out_amax = torch.zeros((1,), dtype=torch.int32, device=x0.device)
     if ctx.used_tc:
       wimg = cross_weight_image(W)
       wsb = lib().tfrs_cross_tc_workspace_bytes(B, D)
       ws = workspace(wsb, x0.device, "cross_tc")
-      check(lib().tfrs_cross_tc_fwd_f32(ptr(x0), ptr(x), ptr(wimg), ptr(b), B, D, D, c_f(diag_scale), ptr(out), ptr(prod),
-                                        ptr(ws), ws.numel(), stream()), "cross_tc_fwd")
+      check(lib().tfrs_cross_tc_fwd_ex_f32(ptr(x0), ptr(x), ptr(wimg), ptr(b), B, D, D, c_f(diag_scale), ptr(out), ptr(prod),
+                                           ptr(x_amax), ptr(out_amax), ptr(ws), ws.numel(), stream()), "cross_tc_fwd")
     else:
       check(lib().tfrs_cross_fwd_f32(ptr(x0), ptr(x), ptr(W), ptr(b), B, D, D, c_f(diag_scale), ptr(out), ptr(prod),
                                      stream()), "cross_fwd")
@@ -676,10 +679,11 @@ class _Cross(torch.autograd.Function):
       ctx.save_for_backward(x0, x, W, prod)
     ctx.diag = diag_scale
     ctx.has_bias = b is not None
-    return out
+    ctx.mark_non_differentiable(out_amax)
+    return out, out_amax
 
   @staticmethod
-  def backward(ctx, g):
+  def backward(ctx, g, _g_amax=None):
     x0, x, W, prod = ctx.saved_tensors
     g = f32c(g, "grad")
     B, D = x0.shape
@@ -692,18 +696,30 @@ class _Cross(torch.autograd.Function):
       ws = workspace(lib().tfrs_cross_tc_bwd_workspace_bytes(B, D), x0.device, "cross_tc_bwd")
       check(lib().tfrs_cross_tc_bwd_f32(ptr(x0), ptr(x), ptr(W), ptr(prod), ptr(g), B, D, D, c_f(ctx.diag), ptr(dx0), ptr(dx),
                                         ptr(dW), ptr(db), ptr(ws), ws.numel(), stream()), "cross_tc_bwd")
-      return dx0, dx, dW, db, None
+      return dx0, dx, dW, db, None, None
     wsb = lib().tfrs_cross_bwd_workspace_bytes(B, D)
     ws = workspace(wsb, x0.device, "cross")
     check(lib().tfrs_cross_bwd_f32(ptr(x0), ptr(x), ptr(W), ptr(prod), ptr(g), B, D, D, c_f(ctx.diag), ptr(dx0), ptr(dx),
                                    ptr(dW), ptr(db), ptr(ws), ws.numel(), stream()), "cross_bwd")
-    return dx0, dx, dW, db, None
+    return dx0, dx, dW, db, None, None
 
 
 def cross(x0: torch.Tensor, x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], diag_scale: float = 0.0
           ) -> torch.Tensor:
-  """x0 * (x @ W + bias + diag_scale * x) + x   (layers/feature_interaction/dcn.py:176-186)."""
-  return _Cross.apply(x0, x, W, bias, float(diag_scale))
+  """x0 * (x @ W + bias + diag_scale * x) + x   (layers/feature_interaction/dcn.py:176-186).
+
+  Stacked layers (`x = cross(x0, x)`): the output carries max |out| from the kernel's epilogue (`_tfrs_amax`), and a later
+  call whose `x` is that very tensor, unmodified, skips its statistics pass over x -- same bits, one HBM pass less."""
+  hint = getattr(x, "_tfrs_amax", None)
+  x_amax = None
+  if (hint is not None and hint[1] == x._version and hint[2] == x.data_ptr() and x.is_cuda and x.dtype == torch.float32 and
+      x.is_contiguous() and x.shape == x0.shape):
+    x_amax = hint[0]
+  out, out_amax = _Cross.apply(x0, x, W, bias, float(diag_scale), x_amax)
+  B, D = out.shape
+  if B >= CROSS_TC_MIN_B and D >= CROSS_TC_MIN_D:
+    out._tfrs_amax = (out_amax, out._version, out.data_ptr())
+  return out
 
 
 def gemm_tc(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: bool = False) -> torch.Tensor:

@@ -261,3 +261,37 @@ def test_retrieval_task_maxsim_known_answer(ops, monkeypatch):
   loss = tfrs.tasks.Retrieval()(q, c, compute_metrics=False)
   ref = orc.retrieval_loss(q.cpu().numpy(), c.cpu().numpy())
   assert abs(float(loss) - ref) <= 1e-6 * max(1.0, abs(ref))
+
+
+def test_cross_stack_reuses_the_epilogue_statistic(ops):
+  """x = cross(x0, x) chains: layer l+1 takes max|x| from layer l's epilogue instead of a pass over x -- identical bits."""
+  import recommenders_b200 as tfrs
+  B, D = 2304, 200
+  x0 = _rand((B, D), 121, 0.5)
+  layers = [tfrs.layers.dcn.Cross() for _ in range(3)]
+  with torch.no_grad():
+    x = x0
+    for l in layers:
+      x = l(x0, x)
+      am, ver, ptr_ = x._tfrs_amax
+      assert ver == x._version and ptr_ == x.data_ptr()
+      assert int(am.item()) == int(x.abs().max().view(torch.int32).item())      # float bits of max |out|
+    y = x0
+    for l in layers:
+      y = l(x0, y.clone())                                                        # a copy carries no statistic: full pass
+  assert torch.equal(x, y)
+  ref = orc.cross(x0.cpu().numpy(), None, layers[0].kernel.detach().cpu().numpy(), layers[0].bias.detach().cpu().numpy())
+  _close(layers[0](x0).detach().cpu().numpy(), ref, 1e-5, "first layer")
+  # an in-place edit invalidates the statistic (version check): the result must still be right
+  with torch.no_grad():
+    z = layers[0](x0)
+    z.mul_(64.0)
+    out = layers[1](x0, z)
+    assert torch.equal(out, layers[1](x0, z.clone()))
+  # gradients still flow through the stack
+  xs = x0.clone().requires_grad_(True)
+  h = xs
+  for l in layers:
+    h = l(xs, h)
+  h.sum().backward()
+  assert torch.isfinite(xs.grad).all() and all(torch.isfinite(l.kernel.grad).all() for l in layers)
