@@ -470,3 +470,21 @@ def test_retrieval_falls_back_to_the_reference_sequence_when_needed(monkeypatch)
   assert [n for n, *_ in calls2] == ["scores"]
   with pytest.raises(ValueError):
     tasks2.Retrieval(remove_accidental_hits=True)(q, c, compute_metrics=False)
+
+
+def test_candidate_ids_of_any_type_become_int64_codes():
+  """Accidental-hit removal only needs EQUALITY of ids: strings / object arrays / float ids are factorised on the host."""
+  import numpy as np
+  import torch
+  from recommenders_b200 import ops
+  dev = torch.device("cpu")
+  s = np.asarray(["b", "a", "b", "c", "a"])
+  codes = ops._ids_i64(s, 5, dev)
+  assert codes.dtype == torch.int64 and codes[0] == codes[2] and codes[1] == codes[4] and len(set(codes.tolist())) == 3
+  t = torch.tensor([7, 7, 2 ** 40 + 1, 2 ** 40 + 1, -3])
+  assert torch.equal(ops._ids_i64(t, 5, dev), t)                       # integer tensors are used as they are
+  f = torch.tensor([0.5, 1.5, 0.5, 2.0, 1.5])
+  cf = ops._ids_i64(f, 5, dev)
+  assert cf[0] == cf[2] and cf[1] == cf[4] and cf[3] != cf[0]
+  with pytest.raises(ValueError):
+    ops._ids_i64(s, 6, dev)
