@@ -488,3 +488,47 @@ def test_candidate_ids_of_any_type_become_int64_codes():
   assert cf[0] == cf[2] and cf[1] == cf[4] and cf[3] != cf[0]
   with pytest.raises(ValueError):
     ops._ids_i64(s, 6, dev)
+
+
+def test_bucketed_rank_sort_groups_ids_in_order_of_occurrence():
+  """CPU model of csrc/adagrad.cu's bucketed rank sort: whatever order the scatter's atomics produce inside a bucket, the
+  ranks (number of bucket members below a key) place every id's members contiguously and in order of occurrence -- all the
+  segmented Adagrad update needs -- and the result does not depend on the scatter order."""
+  import numpy as np
+  rng = np.random.RandomState(3)
+
+  def bucket(key):
+    idv = ((key >> np.uint64(24)) ^ (key >> np.uint64(56))).astype(np.uint32)
+    return ((idv.astype(np.uint64) * np.uint64(0x9E3779B1)) & np.uint64(0xFFFFFFFF)).astype(np.uint32) >> np.uint32(24)
+
+  def sort_once(ids, seed):
+    n = len(ids)
+    keys = (ids.astype(np.uint64) << np.uint64(24)) | np.arange(n, dtype=np.uint64)
+    b = bucket(keys)
+    order = np.random.RandomState(seed).permutation(n)           # the nondeterministic part: arrival order of the atomics
+    bkeys, bstart = [], [0]
+    for v in range(256):
+      m = order[b[order] == v]
+      bkeys.extend(keys[m]); bstart.append(len(bkeys))
+    bkeys = np.asarray(bkeys, np.uint64)
+    out = np.zeros(n, np.uint64)
+    for v in range(256):
+      seg = bkeys[bstart[v]:bstart[v + 1]]
+      for key in seg:
+        out[bstart[v] + int((seg < key).sum())] = key             # rank inside the bucket (keys are unique)
+    return out
+
+  for ids in (rng.randint(0, 50, size=700), rng.randint(0, 10 ** 9, size=900), np.zeros(300, np.int64),
+              (rng.zipf(1.3, size=800) % 1000)):
+    ids = np.asarray(ids, np.int64)
+    a, b2 = sort_once(ids, 1), sort_once(ids, 2)
+    assert np.array_equal(a, b2)                                   # deterministic despite the scatter order
+    assert np.array_equal(np.sort(a), np.sort((ids.astype(np.uint64) << np.uint64(24)) | np.arange(len(ids), dtype=np.uint64)))
+    out_ids = (a >> np.uint64(24)).astype(np.int64); pos = (a & np.uint64(0xFFFFFF)).astype(np.int64)
+    seen = set()
+    for i in range(len(a)):
+      if i and out_ids[i] == out_ids[i - 1]:
+        assert pos[i] > pos[i - 1]                                 # members in order of occurrence
+      else:
+        assert out_ids[i] not in seen                              # every id forms ONE contiguous run
+        seen.add(out_ids[i])
