@@ -159,18 +159,28 @@ def stream() -> ctypes.c_void_p:
   return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-_ws_cache = {}
+_ws_cache = {}          # (device, stream, slot) -> uint8 tensor; insertion order = recency (re-inserted on every use)
+_WS_CACHE_MAX = 64      # entries; the least recently used buffers are dropped beyond this (streams come and go)
 
 
 def workspace(nbytes: int, device: torch.device, slot: str = "default") -> torch.Tensor:
-  """A per-(device, stream, slot) scratch buffer that only grows (caller-provided scratch of the C ABI)."""
+  """A per-(device, stream, slot) scratch buffer that only grows (caller-provided scratch of the C ABI).  The cache is
+  bounded: least-recently-used entries are dropped (the caching allocator keeps a dropped buffer alive until the work
+  already enqueued on its stream has finished)."""
   key = (device.index if device.index is not None else torch.cuda.current_device(),
          torch.cuda.current_stream().cuda_stream, slot)
-  buf = _ws_cache.get(key)
+  buf = _ws_cache.pop(key, None)
   if buf is None or buf.numel() < nbytes:
     buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-    _ws_cache[key] = buf
+  _ws_cache[key] = buf
+  while len(_ws_cache) > _WS_CACHE_MAX:
+    _ws_cache.pop(next(iter(_ws_cache)))
   return buf
+
+
+def release_workspaces() -> None:
+  """Drops every cached scratch buffer (e.g. after an evaluation pass whose shapes will not come back)."""
+  _ws_cache.clear()
 
 
 def ids_dtype_code(t: torch.Tensor) -> int:

@@ -532,3 +532,29 @@ def test_bucketed_rank_sort_groups_ids_in_order_of_occurrence():
       else:
         assert out_ids[i] not in seen                              # every id forms ONE contiguous run
         seen.add(out_ids[i])
+
+
+def test_workspace_cache_is_bounded(monkeypatch):
+  """_ffi.workspace keeps at most _WS_CACHE_MAX buffers (least recently used dropped) and grows a slot on demand."""
+  import torch
+  from recommenders_b200 import _ffi
+
+  class _S:
+    cuda_stream = 0
+  made = []
+  monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _S())
+  monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+  real_empty = torch.empty
+  monkeypatch.setattr(torch, "empty", lambda n, dtype=None, device=None: (made.append(n), real_empty(n, dtype=dtype))[1])
+  _ffi.release_workspaces()
+  dev = torch.device("cpu")
+  a = _ffi.workspace(1000, dev, "a")
+  assert _ffi.workspace(500, dev, "a") is a and len(made) == 1          # reused while large enough
+  assert _ffi.workspace(5000, dev, "a").numel() >= 5000 and len(made) == 2
+  for i in range(_ffi._WS_CACHE_MAX + 10):
+    _ffi.workspace(256, dev, f"slot{i}")
+    _ffi.workspace(256, dev, "a")                                         # keeps "a" recent
+  assert len(_ffi._ws_cache) == _ffi._WS_CACHE_MAX and any(k[2] == "a" for k in _ffi._ws_cache)
+  assert not any(k[2] == "slot0" for k in _ffi._ws_cache)
+  _ffi.release_workspaces()
+  assert not _ffi._ws_cache
